@@ -1,0 +1,132 @@
+// dev_pixel.cuh - premultiplied-pixel arithmetic and the composition operators.
+//
+// Reference semantics restated here (nothing is copied; the reference packs 4x16-bit lanes into one u64, we keep two
+// u32 words holding the lanes {.R.B} and {.A.G}, which is the natural width for the GPU's 32-bit integer pipes):
+//   - U32_8888::div255/div256/addus8     blend2d/pipeline/reference/pixelgeneric_p.h:390-405
+//   - CompOp_SrcCopy_Op / SrcOver / Plus blend2d/pipeline/reference/compopgeneric_p.h:24-81
+//   - Multiply / Screen (JIT only)       blend2d/pipeline/jit/compoppart.cpp:4325-4461, 4591-4640
+//   - udiv255                            blend2d/pixelops/scalar_p.h:34  (KAT: pixelops/scalar_test.cpp:19-31)
+//   - FillAnalytic_Base::calc_mask       blend2d/pipeline/reference/fillgeneric_p.h:381-387
+#pragma once
+#include "dev_common.cuh"
+
+namespace b2d {
+
+// Two 16-bit lanes in one 32-bit word.
+struct Lanes2 { uint32_t rb, ag; };
+
+B2D_HD Lanes2 unpack(uint32_t p) { return Lanes2{ p & 0x00FF00FFu, (p >> 8) & 0x00FF00FFu }; }
+B2D_HD uint32_t pack(Lanes2 u) { return (u.rb & 0x00FF00FFu) | ((u.ag & 0x00FF00FFu) << 8); }
+
+// ((x + 128) + ((x + 128) >> 8)) >> 8 on each 16-bit lane; exact for lane values <= 65025 + 254.
+B2D_HD uint32_t div255_2(uint32_t x) {
+  uint32_t u = x + 0x00800080u;
+  return ((u + ((u >> 8) & 0x00FF00FFu)) >> 8) & 0x00FF00FFu;
+}
+B2D_HD uint32_t div256_2(uint32_t x) { return (x >> 8) & 0x00FF00FFu; }
+
+B2D_HD Lanes2 mul(Lanes2 a, uint32_t m) { return Lanes2{ a.rb * m, a.ag * m }; }
+B2D_HD Lanes2 add(Lanes2 a, Lanes2 b) { return Lanes2{ a.rb + b.rb, a.ag + b.ag }; }
+B2D_HD Lanes2 div255(Lanes2 a) { return Lanes2{ div255_2(a.rb), div255_2(a.ag) }; }
+B2D_HD Lanes2 div256(Lanes2 a) { return Lanes2{ div256_2(a.rb), div256_2(a.ag) }; }
+
+// Saturating add of two {0..255} lane pairs (U32_8888::addus8).
+B2D_HD uint32_t addus8_2(uint32_t a, uint32_t b) {
+  uint32_t v = a + b;
+  uint32_t msk = ((v >> 8) & 0x00010001u) * 0xFFu;
+  return (v | msk) & 0x00FF00FFu;
+}
+
+B2D_HD uint32_t udiv255(uint32_t x) { return ((x + 0x80u) * 0x101u) >> 16; }
+
+// 16-bit-lane helpers for the JIT-specified operators (pmullw / paddw wrap at 16 bits, pmulhuw for div255).
+B2D_HD uint32_t jit_div255_u16(uint32_t x) { return (((x + 0x80u) & 0xFFFFu) * 0x101u) >> 16; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Composition operators: d' = op(d, s, m) with m in [1, 255].  m == 0 leaves d unchanged for every operator below
+// (the callers skip such pixels), m == 255 reproduces the reference's "opaque" variants exactly.
+// ---------------------------------------------------------------------------------------------------------------
+
+// SrcCopy: (d*(255-m) + s*m).div255()                                      compopgeneric_p.h:38-40
+B2D_HD uint32_t comp_src_copy(uint32_t d, uint32_t s, uint32_t m) {
+  Lanes2 du = unpack(d), su = unpack(s);
+  uint32_t im = m ^ 0xFFu;
+  return pack(div255(add(mul(du, im), mul(su, m))));
+}
+
+// SrcOver: s' = (s*m).div255(); d' = s' + (d*(255 - s'.a)).div255()        compopgeneric_p.h:54-62
+// The final "+" is a plain 32-bit add of packed pixels in the reference; kept as such.
+B2D_HD uint32_t comp_src_over(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t sm = pack(div255(mul(unpack(s), m)));
+  uint32_t ia = (sm >> 24) ^ 0xFFu;
+  return sm + pack(div255(mul(unpack(d), ia)));
+}
+
+// Plus: addus8(d, (s*m).div255())                                          compopgeneric_p.h:74-80
+B2D_HD uint32_t comp_plus(uint32_t d, uint32_t s, uint32_t m) {
+  Lanes2 du = unpack(d);
+  Lanes2 sm = div255(mul(unpack(s), m));
+  return pack(Lanes2{ addus8_2(du.rb, sm.rb), addus8_2(du.ag, sm.ag) });
+}
+
+B2D_HD uint32_t sat8(uint32_t v) { return v > 255u ? 255u : v; }
+
+// Multiply: S = div255(S*m); D' = div255(D*(S + 255 - Sa) + S*(255 - Da))   jit/compoppart.cpp:4408-4441
+B2D_HD uint32_t comp_multiply(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t out = 0;
+  uint32_t sa = jit_div255_u16(((s >> 24) * m) & 0xFFFFu);
+  uint32_t da = d >> 24;
+  uint32_t isa = 255u - sa;
+  uint32_t ida = 255u - da;
+  #pragma unroll
+  for (int sh = 0; sh < 32; sh += 8) {
+    uint32_t sc = jit_div255_u16((((s >> sh) & 0xFFu) * m) & 0xFFFFu);
+    uint32_t dc = (d >> sh) & 0xFFu;
+    uint32_t y = (isa + sc) & 0xFFFFu;
+    uint32_t v = ((dc * y) & 0xFFFFu) + ((ida * sc) & 0xFFFFu);
+    out |= sat8(jit_div255_u16(v & 0xFFFFu)) << sh;
+  }
+  return out;
+}
+
+// Screen: S = div255(S*m); D' = div255(D*(255 - S)) + S                    jit/compoppart.cpp:4614-4630
+B2D_HD uint32_t comp_screen(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t out = 0;
+  #pragma unroll
+  for (int sh = 0; sh < 32; sh += 8) {
+    uint32_t sc = jit_div255_u16((((s >> sh) & 0xFFu) * m) & 0xFFFFu);
+    uint32_t dc = (d >> sh) & 0xFFu;
+    uint32_t v = jit_div255_u16((dc * (255u - sc)) & 0xFFFFu) + sc;
+    out |= sat8(v & 0xFFFFu) << sh;
+  }
+  return out;
+}
+
+enum CompOpId : uint32_t { kOpSrcOver = 0, kOpSrcCopy = 1, kOpPlus = 12, kOpMultiply = 15, kOpScreen = 16 };
+
+B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) {
+  switch (comp_op) {
+    case kOpSrcOver:  return comp_src_over(d, s, m);
+    case kOpSrcCopy:  return comp_src_copy(d, s, m);
+    case kOpPlus:     return comp_plus(d, s, m);
+    case kOpMultiply: return comp_multiply(d, s, m);
+    default:          return comp_screen(d, s, m);
+  }
+}
+
+// Coverage accumulator -> 8-bit mask.  `cov` is the running u32 sum that starts at 256 << 9 on every scanline.
+// fillgeneric_p.h:381-387: m = min(abs((sar(cov, 9) & rule) - 256), 256) * alpha >> 8.
+B2D_HD uint32_t calc_mask(uint32_t cov, uint32_t fill_rule_mask, uint32_t alpha) {
+  int32_t c = int32_t(cov) >> 9;                          // IntOps::sar on the reinterpreted value
+  uint32_t m = (uint32_t(c) & fill_rule_mask) - 256u;
+  int32_t mi = int32_t(m);
+  uint32_t a = uint32_t(mi < 0 ? -mi : mi);
+  a = a < 256u ? a : 256u;
+  return (a * alpha) >> 8;
+}
+
+// Source pixel format adaptation (PixelIO<P32_A8R8G8B8, fmt>::fetch, pixelgeneric_p.h:632-676).
+B2D_HD uint32_t adapt_src_xrgb32(uint32_t p) { return p | 0xFF000000u; }
+B2D_HD uint32_t adapt_src_a8(uint32_t a) { return a * 0x01010101u; }
+
+} // namespace b2d

@@ -1,0 +1,127 @@
+// dev_tile.cuh - per-tile pieces of the compositor that are plain scalar code: the coverage sink, the classification of
+// an edge against a tile, the axis-unaligned box mask and the command bounding box.  Shared by the CUDA kernel
+// (kernels.cu) and the test-only host simulator (tests/hostsim).
+#pragma once
+#include "dev_common.cuh"
+#include "dev_raster.cuh"
+#include "../../include/b2dgpu.h"
+
+namespace b2d {
+
+// Mask of an axis-unaligned box at pixel (x, y) - closed form of FillData::init_box_u_8bpc_24x8()'s mask-command
+// program (pipeline/pipedefs_p.h:644-815) as interpreted by FillMask_Base (fillgeneric_p.h:67-162): per-column weight
+// times per-row weight, with the reference's shifts.  Rows/columns whose mask is 0 are skipped there and here.
+struct BoxUParams {
+  int ax0, ay0, ax1, ay1;
+  uint32_t wx_first, wx_last;      // weights of the first / last column (256 for interior columns)
+  uint32_t fy0_a, fy1_a, alpha;    // row weights already multiplied by alpha
+};
+
+B2D_HD BoxUParams box_u_setup(const int32_t* box, uint32_t alpha) {
+  BoxUParams b;
+  int x0 = box[0], y0 = box[1], x1 = box[2], y1 = box[3];
+  b.ax0 = int(uint32_t(x0) >> 8); b.ay0 = int(uint32_t(y0) >> 8);
+  b.ax1 = int(uint32_t(x1 + 0xFF) >> 8); b.ay1 = int(uint32_t(y1 + 0xFF) >> 8);
+  uint32_t fx0 = uint32_t(x0) & 0xFFu, fy0 = uint32_t(y0) & 0xFFu;
+  uint32_t fx1 = (uint32_t(x1 - 1) & 0xFFu) + 1u, fy1 = (uint32_t(y1 - 1) & 0xFFu) + 1u;
+  uint32_t w = uint32_t(b.ax1 - b.ax0), h = uint32_t(b.ay1 - b.ay0);
+  fy0 = (h == 1 ? fy1 : 256u) - fy0;
+  b.fy0_a = fy0 * alpha;
+  b.fy1_a = fy1 * alpha;
+  b.alpha = alpha;
+  if (w == 1) { b.wx_first = fx1 - fx0; b.wx_last = b.wx_first; }
+  else { b.wx_first = 256u - fx0; b.wx_last = fx1; }
+  return b;
+}
+
+B2D_HD uint32_t box_u_mask(const BoxUParams& b, int x, int y) {
+  if (x < b.ax0 || x >= b.ax1 || y < b.ay0 || y >= b.ay1) return 0u;
+  uint32_t wx = (x == b.ax0) ? b.wx_first : (x == b.ax1 - 1) ? b.wx_last : 256u;
+  if (y == b.ay0) return (wx * b.fy0_a) >> 16;
+  if (y == b.ay1 - 1) return (wx * b.fy1_a) >> 16;
+  return (wx * b.alpha) >> 8;
+}
+
+// Adapter from the rasterizer's merge(x, cover, area) to a tile: cells left of the tile go to the row's carry
+// (backdrop), cells right of it are dropped.  `Store` provides add_cell(row, rel_x, v) and add_carry(row, v).
+template<typename Store>
+struct TileSink {
+  Store& store;
+  int tx0;
+  int row;
+  uint32_t touched;
+
+  B2D_HD TileSink(Store& s, int tx0_) : store(s), tx0(tx0_), row(0), touched(0) {}
+  B2D_HD void put(int x, uint32_t v) {
+    if (!v) return;
+    int rel = x - tx0;
+    if (rel < 0) { store.add_carry(row, v); touched = 1; }
+    else if (rel < kTileW) { store.add_cell(row, rel, v); touched = 1; }
+  }
+  B2D_HD void merge(int x, uint32_t cover, uint32_t area) {
+    put(x, (cover << 9) - area);
+    put(x + 1, area);
+  }
+};
+
+// Accumulates one edge into the tile whose top-left pixel is (tx0, ty0).  Edges entirely left of the tile only
+// contribute their signed y-extent per row (every scanline's cells sum to cover << 9): that goes to `left_acc`, one
+// register per row, which the caller reduces across threads before touching shared memory.  Returns true when the
+// edge wrote anything through `store`.
+template<typename Store>
+B2D_HD bool tile_accumulate_edge(b2dgpu_edge ed, int tx0, int ty0, Store& store, uint32_t* left_acc) {
+  uint32_t sign_bit = 0;
+  if (ed.y0 > ed.y1) { int t = ed.x0; ed.x0 = ed.x1; ed.x1 = t; t = ed.y0; ed.y0 = ed.y1; ed.y1 = t; sign_bit = 1; }
+  const int ey_first = ed.y0 >> 8, ey_last = (ed.y1 - 1) >> 8;
+  if (ey_last < ty0 || ey_first >= ty0 + kTileH) return false;
+  const int cx_min = tmin(ed.x0, ed.x1) >> 8, cx_max = tmax(ed.x0, ed.x1) >> 8;
+  if (cx_min >= tx0 + kTileW) return false;                     // entirely right: contributes nothing here
+
+  if (cx_max + 1 < tx0) {
+    #pragma unroll
+    for (int r = 0; r < kTileH; r++) {
+      int yt = (ty0 + r) << 8;
+      int cov = tmin(ed.y1, yt + 256) - tmax(ed.y0, yt);
+      if (cov > 0) left_acc[r] += uint32_t(sign_bit ? -cov : cov) << 9;
+    }
+    return false;
+  }
+
+  EdgeState st;
+  if (!edge_prepare(st, ed.x0, ed.y0, ed.x1, ed.y1, sign_bit)) return false;
+  const int y_from = tmax(ey_first, ty0);
+  const int y_to = tmin(ey_last, ty0 + kTileH - 1);
+  edge_advance_to_y(st, y_from);
+  TileSink<Store> sink(store, tx0);
+  for (int y = y_from; y <= y_to; y++) {
+    sink.row = y - ty0;
+    if (edge_step_scanline(st, sink)) break;
+  }
+  return sink.touched != 0;
+}
+
+// Pixel bounding box [x0,x1) x [y0,y1) of a command, clipped to the rows [y_begin, y_end) of a `width`-wide target;
+// all zeros when the command cannot touch it.  `bb_fixed` = 24.8 bounds of an analytic command's edges.
+struct CmdBox { int x0, y0, x1, y1; };
+
+B2D_HD CmdBox command_pixel_box(const b2dgpu_command& cmd, uint32_t edge_count, int fx0, int fy0, int fx1, int fy1,
+                                int width, int y_begin, int y_end) {
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  if (cmd.type == B2DGPU_CMD_FILL_BOX_A) {
+    x0 = cmd.box[0]; y0 = cmd.box[1]; x1 = cmd.box[2]; y1 = cmd.box[3];
+  }
+  else if (cmd.type == B2DGPU_CMD_FILL_BOX_U) {
+    x0 = cmd.box[0] >> 8; y0 = cmd.box[1] >> 8; x1 = (cmd.box[2] + 0xFF) >> 8; y1 = (cmd.box[3] + 0xFF) >> 8;
+  }
+  else if (edge_count && fx0 <= fx1 && fy0 < fy1) {
+    x0 = fx0 >> 8; x1 = (fx1 >> 8) + 1;
+    y0 = fy0 >> 8; y1 = ((fy1 - 1) >> 8) + 1;
+  }
+  x0 = tmax(x0, 0); y0 = tmax(y0, y_begin); x1 = tmin(x1, width); y1 = tmin(y1, y_end);
+  CmdBox b;
+  if (x0 >= x1 || y0 >= y1 || cmd.alpha == 0) { b.x0 = b.y0 = b.x1 = b.y1 = 0; }
+  else { b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1; }
+  return b;
+}
+
+} // namespace b2d

@@ -1,0 +1,515 @@
+// kernels.cu - the sm_100a kernels of libb2dgpu and their launchers.
+//
+//   K1  k_build_edges<count|write>   one thread per path segment: transform -> clip -> monotone split -> flatten
+//                                    (FP64, no FMA) -> 24.8 integer edges.  Two passes (count, exclusive scan, write)
+//                                    give every command a contiguous, deterministic edge range.
+//   K1b k_scan_*                     exclusive prefix sum of the per-segment edge counts.
+//   K1c k_analytic_bbox / k_finalize_commands   per-command pixel bounding boxes used for tile culling.
+//   K2+K3 k_tile_render<BPP>         one CTA per 128x8 destination tile.  The tile's pixels are loaded ONCE into
+//                                    registers (16-byte vector loads, one warp per row), every command whose bounding
+//                                    box touches the tile is replayed in submission order - coverage accumulation into
+//                                    shared-memory cells with atomics, warp-shuffle prefix scan, mask, fetch, composite -
+//                                    and the tile is stored ONCE.  This is the GPU form of the reference's per-band
+//                                    command replay (blend2d/raster/workerproc.cpp:166-299) fused with its FillBoxA /
+//                                    FillMask / FillAnalytic pipelines (pipeline/reference/fillgeneric_p.h:22-388).
+//
+// No tensor cores: nothing on this path is a dense contraction.  Compile with -fmad=false (see dev_flatten.cuh).
+#include "kernels.h"
+#include "dev_pixel.cuh"
+#include "dev_raster.cuh"
+#include "dev_flatten.cuh"
+#include "dev_fetch.cuh"
+#include "dev_tile.cuh"
+
+#include <cuda_runtime.h>
+#include <limits.h>
+
+namespace b2d {
+
+// =================================================================================================================
+// K1 - edge builder
+// =================================================================================================================
+
+struct CountOut {
+  uint32_t n;
+  __device__ __forceinline__ void edge(int, int, int, int) { n++; }
+};
+
+struct WriteOut {
+  b2dgpu_edge* dst;
+  uint32_t n;
+  int min_x, min_y, max_x, max_y;
+  __device__ __forceinline__ void edge(int x0, int y0, int x1, int y1) {
+    b2dgpu_edge e; e.x0 = x0; e.y0 = y0; e.x1 = x1; e.y1 = y1;
+    dst[n++] = e;
+    min_x = min(min_x, min(x0, x1)); max_x = max(max_x, max(x0, x1));
+    min_y = min(min_y, min(y0, y1)); max_y = max(max_y, max(y0, y1));
+  }
+};
+
+template<typename Out>
+__device__ __forceinline__ void build_segment(const BuildParams& P, uint32_t seg_index, Out& out) {
+  const b2dgpu_segment seg = P.segments[seg_index];
+  const b2dgpu_command& cmd = P.commands[seg.command];
+  const b2dgpu_geometry_state& gs = P.states[cmd.state_index];
+
+  GeomXform xf;
+  xf.m00 = gs.m[0]; xf.m01 = gs.m[1]; xf.m10 = gs.m[2]; xf.m11 = gs.m[3]; xf.m20 = gs.m[4]; xf.m21 = gs.m[5];
+  xf.affine = gs.transform_type > 2u;
+
+  ClipBox cb;
+  cb.x0 = gs.clip[0]; cb.y0 = gs.clip[1]; cb.x1 = gs.clip[2]; cb.y1 = gs.clip[3];
+  cb.ix0 = trunc_i(cb.x0); cb.ix1 = trunc_i(cb.x1);
+
+  const double2* v = reinterpret_cast<const double2*>(P.vertices);
+  const uint32_t kind = seg.p1_kind & 3u;
+  const uint32_t i1 = seg.p1_kind >> 2;
+
+  double2 a = v[seg.p0];
+  double2 b = v[i1];
+  P2 p0 = xform(xf, mk(a.x, a.y));
+  P2 p1 = xform(xf, mk(b.x, b.y));
+
+  if (kind == B2DGPU_SEG_LINE) {
+    build_line(p0, p1, cb, out);
+  }
+  else if (kind == B2DGPU_SEG_CUBIC) {
+    double2 c = v[i1 + 1], d = v[i1 + 2];
+    build_cubic(p0, p1, xform(xf, mk(c.x, c.y)), xform(xf, mk(d.x, d.y)), cb, gs.tolerance_sq, out);
+  }
+  else {
+    // Quad, or conic: the reference flattens a conic through its quad machinery using vertex[+2] as the end point
+    // (EdgeSourcePath::next_conic_to, edgebuilder_p.h:267-272; FlattenMonoConic :666-768).
+    double2 c = v[i1 + (kind == B2DGPU_SEG_CONIC ? 2u : 1u)];
+    build_quad(p0, p1, xform(xf, mk(c.x, c.y)), cb, gs.tolerance_sq, out);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_count_edges(BuildParams P) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.segment_count) return;
+  CountOut out; out.n = 0;
+  build_segment(P, i, out);
+  P.seg_counts[i] = out.n;
+}
+
+__global__ void __launch_bounds__(128) k_write_edges(BuildParams P) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.segment_count) return;
+  uint32_t begin = P.seg_offsets[i];
+  uint32_t end = P.seg_offsets[i + 1];
+  if (begin == end) return;
+  if (end > P.edge_capacity - P.edge_base) {           // capacity is checked on the host too; never write past it
+    atomicOr(P.error_flag, 1u);
+    return;
+  }
+  WriteOut out;
+  out.dst = P.edges + P.edge_base + begin;
+  out.n = 0;
+  out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
+  build_segment(P, i, out);
+  int4* bb = P.cmd_bbox_fixed + P.segments[i].command;
+  atomicMin(&bb->x, out.min_x); atomicMin(&bb->y, out.min_y);
+  atomicMax(&bb->z, out.max_x); atomicMax(&bb->w, out.max_y);
+}
+
+// =================================================================================================================
+// K1b - exclusive scan (u32), 2048 items per block.
+// =================================================================================================================
+enum { kScanThreads = 256, kScanItems = 8, kScanBlock = kScanThreads * kScanItems };
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_warp, uint32_t& total) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (kScanThreads / 32) ? s_warp[lane] : 0u;
+    uint32_t winc = w;
+    #pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < (kScanThreads / 32)) s_warp[lane] = winc - w;
+    if (lane == (kScanThreads / 32) - 1) s_warp[8] = winc;
+  }
+  __syncthreads();
+  total = s_warp[8];
+  return s_warp[warp] + inc - v;
+}
+
+// out[i] = exclusive prefix of in[0..n); block_sums[b] = sum of block b.  `out` has n + 1 entries when `tail` != 0.
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocks(const uint32_t* in, uint32_t* out, uint32_t* block_sums, uint32_t n) {
+  __shared__ uint32_t s_warp[9];
+  const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+  #pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan_256(sum, s_warp, total);
+  #pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* out, const uint32_t* block_offsets, uint32_t n, uint32_t* total_out) {
+  const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
+  const uint32_t add = block_offsets[blockIdx.x];
+  #pragma unroll
+  for (int k = 0; k < kScanItems; k++)
+    if (base + k < n) out[base + k] += add;
+  if (total_out && blockIdx.x == 0 && threadIdx.x == 0) {
+    // block_offsets has one extra entry holding the grand total (written by the level above).
+    out[n] = block_offsets[gridDim.x];
+    *total_out = block_offsets[gridDim.x];
+  }
+}
+
+// Single-block scan for <= kScanBlock items; writes out[n] = total as well.
+__global__ void __launch_bounds__(kScanThreads) k_scan_small(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out) {
+  __shared__ uint32_t s_warp[9];
+  const uint32_t base = threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint32_t sum = 0;
+  #pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    sum += v[k];
+  }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan_256(sum, s_warp, total);
+  #pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (threadIdx.x == 0) {
+    out[n] = total;
+    if (total_out) *total_out = total;
+  }
+}
+
+// =================================================================================================================
+// K1c - command bounding boxes
+// =================================================================================================================
+__global__ void k_init_bbox(int4* bbox, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bbox[i] = make_int4(INT_MAX, INT_MAX, INT_MIN, INT_MIN);
+}
+
+// One warp per command with caller-supplied edges.
+__global__ void __launch_bounds__(256) k_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox) {
+  uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t lane = threadIdx.x & 31;
+  if (c >= ncmd) return;
+  const b2dgpu_command& cmd = cmds[c];
+  if (cmd.type != B2DGPU_CMD_FILL_ANALYTIC) return;
+  int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+  for (uint32_t i = lane; i < cmd.data_count; i += 32) {
+    b2dgpu_edge e = edges[cmd.data_offset + i];
+    mnx = min(mnx, min(e.x0, e.x1)); mxx = max(mxx, max(e.x0, e.x1));
+    mny = min(mny, min(e.y0, e.y1)); mxy = max(mxy, max(e.y0, e.y1));
+  }
+  mnx = __reduce_min_sync(0xFFFFFFFFu, mnx); mny = __reduce_min_sync(0xFFFFFFFFu, mny);
+  mxx = __reduce_max_sync(0xFFFFFFFFu, mxx); mxy = __reduce_max_sync(0xFFFFFFFFu, mxy);
+  if (lane == 0) bbox[c] = make_int4(mnx, mny, mxx, mxy);
+}
+
+__global__ void k_finalize_commands(FinalizeParams P) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.command_count) return;
+  const b2dgpu_command cmd = P.commands[c];
+  uint32_t e_begin = 0, e_count = 0;
+  if (cmd.type == B2DGPU_CMD_FILL_ANALYTIC) {
+    e_begin = cmd.data_offset; e_count = cmd.data_count;
+  }
+  else if (cmd.type == B2DGPU_CMD_FILL_GEOMETRY) {
+    uint32_t o0 = P.seg_offsets[cmd.data_offset];
+    uint32_t o1 = P.seg_offsets[cmd.data_offset + cmd.data_count];
+    e_begin = P.edge_base + o0; e_count = o1 - o0;
+  }
+  int4 bb = P.cmd_bbox_fixed[c];
+  CmdBox box = command_pixel_box(cmd, e_count, bb.x, bb.y, bb.z, bb.w, P.width, P.y_begin, P.y_end);
+  int x0 = box.x0, y0 = box.y0, x1 = box.x1, y1 = box.y1;
+  P.cmd_bbox_px[c] = make_int4(x0, y0, x1, y1);
+  P.cmd_edges[c] = make_uint2(e_begin, e_count);
+}
+
+// =================================================================================================================
+// K2 + K3 - tile compositor
+// =================================================================================================================
+
+// Shared-memory cell store of one tile (u32 wrap-around adds: order independent).
+struct SmemStore {
+  uint32_t* cells;      // kTileH x kTileW
+  uint32_t* carry;      // kTileH
+  __device__ __forceinline__ void add_cell(int row, int rel, uint32_t v) { atomicAdd(cells + row * kTileW + rel, v); }
+  __device__ __forceinline__ void add_carry(int row, uint32_t v) { atomicAdd(carry + row, v); }
+};
+
+template<int BPP>
+__global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
+  __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];
+  __shared__ uint32_t s_carry[kTileH];
+  __shared__ uint32_t s_list[kTileThreads];
+  __shared__ uint32_t s_wcount[kTileH];
+  __shared__ uint32_t s_any[4];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int row = tid >> 5;
+  const int tile_x = blockIdx.x % P.tiles_x;
+  const int tile_y = blockIdx.x / P.tiles_x;
+  const int tx0 = tile_x * kTileW;
+  const int ty0 = P.y_begin + tile_y * kTileH;          // absolute y of the tile's first row
+  const int px = tx0 + lane * 4;
+  const int py = ty0 + row;
+
+  // Load the destination once.
+  uint8_t* dst_row = P.dst + size_t(py - P.y_begin) * P.dst_stride;
+  uint32_t d[4];
+  if (BPP == 4) {
+    uint4 v = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  else {
+    uint32_t v = *reinterpret_cast<const uint32_t*>(dst_row + px);
+    d[0] = (v & 0xFFu) * 0x01010101u; d[1] = ((v >> 8) & 0xFFu) * 0x01010101u;
+    d[2] = ((v >> 16) & 0xFFu) * 0x01010101u; d[3] = (v >> 24) * 0x01010101u;
+  }
+  bool dirty = false;
+  uint32_t px_written = 0;
+
+  // Zero the coverage scratch.
+  *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
+  if (tid < kTileH) s_carry[tid] = 0;
+  if (tid < 4) s_any[tid] = 0;
+  __syncthreads();
+
+  uint32_t iter = 0;      // counts analytic commands processed by this CTA (indexes the rotating s_any flags)
+
+  for (uint32_t base = 0; base < P.command_count; base += kTileThreads) {
+    // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
+    uint32_t c = base + tid;
+    bool hit = false;
+    if (c < P.command_count) {
+      int4 bb = P.cmd_bbox_px[c];
+      hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
+    }
+    uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+    if (lane == 0) s_wcount[row] = __popc(ballot);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    #pragma unroll
+    for (int w = 0; w < kTileH; w++) {
+      uint32_t cnt = s_wcount[w];
+      if (w < row) wbase += cnt;
+      total += cnt;
+    }
+    if (hit) s_list[wbase + __popc(ballot & ((1u << lane) - 1u))] = c;
+    __syncthreads();
+
+    for (uint32_t k = 0; k < total; k++) {
+      const uint32_t ci = s_list[k];
+      const b2dgpu_command& cmd = P.commands[ci];
+      const uint32_t type = cmd.type;
+      const uint32_t sig = cmd.signature;
+      const uint32_t alpha = cmd.alpha;
+      uint32_t m[4] = { 0, 0, 0, 0 };
+
+      if (type == B2DGPU_CMD_FILL_BOX_A) {
+        // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
+        if (py >= cmd.box[1] && py < cmd.box[3]) {
+          #pragma unroll
+          for (int i = 0; i < 4; i++) m[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
+        }
+      }
+      else if (type == B2DGPU_CMD_FILL_BOX_U) {
+        BoxUParams bu = box_u_setup(cmd.box, alpha);
+        #pragma unroll
+        for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
+      }
+      else {
+        // ---- K2: accumulate cover/area cells of this command's edges that touch the tile ----
+        const uint2 er = P.cmd_edges[ci];
+        const uint32_t slot = iter & 3u;
+        iter++;
+        uint32_t touched = 0;
+        uint32_t left_acc[kTileH];
+        #pragma unroll
+        for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
+
+        SmemStore store{ &s_cells[0][0], s_carry };
+        for (uint32_t e = tid; e < er.y; e += kTileThreads) {
+          if (tile_accumulate_edge(P.edges[er.x + e], tx0, ty0, store, left_acc)) touched = 1;
+        }
+
+        // Warp-aggregate the "entirely left" covers: one shared atomic per warp and row instead of one per edge.
+        #pragma unroll
+        for (int r = 0; r < kTileH; r++) {
+          uint32_t v = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
+          if (v && lane == 0) { atomicAdd(&s_carry[r], v); touched = 1; }
+        }
+        if (touched) s_any[slot] = 1;
+        __syncthreads();                                              // A: cells complete
+
+        if (tid == 0) s_any[(slot + 2) & 3u] = 0;
+        if (!s_any[slot]) continue;                                   // nothing of this command reaches the tile
+
+        // ---- K3 (mask part): prefix-scan the row's cells, re-zero them, derive 8-bit masks ----
+        uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
+        *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
+        const uint32_t carry = s_carry[row];
+        uint32_t s0 = cv.x, s1 = s0 + cv.y, s2 = s1 + cv.z, s3 = s2 + cv.w;
+        uint32_t inc = s3;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
+        const uint32_t rule = cmd.fill_rule_mask;
+        m[0] = calc_mask(cov_base + s0, rule, alpha);
+        m[1] = calc_mask(cov_base + s1, rule, alpha);
+        m[2] = calc_mask(cov_base + s2, rule, alpha);
+        m[3] = calc_mask(cov_base + s3, rule, alpha);
+        // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
+        {
+          const int4 bb = P.cmd_bbox_px[ci];
+          #pragma unroll
+          for (int i = 0; i < 4; i++) if (px + i >= bb.z) m[i] = 0;
+        }
+        __syncwarp();
+        if (lane == 0) s_carry[row] = 0;
+        __syncthreads();                                              // B: cells re-zeroed before the next command
+      }
+
+      // ---- K3 (fetch + composite) ----
+      if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
+
+      FetchEnv env;
+      env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
+      env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
+      env.solid = cmd.solid_prgb32;
+      env.fd = P.fetch_data + cmd.fetch_index;
+      env.bayer = P.bayer;
+      env.origin_x = P.origin_x; env.origin_y = P.origin_y;
+      const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
+
+      RowCtx rc;
+      fetch_row_init(env, uint32_t(py), rc);
+
+      #pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (m[i]) {
+          uint32_t s = fetch_pixel(env, rc, uint32_t(px + i), uint32_t(py));
+          if (BPP == 1) s = (s >> 24) * 0x01010101u;
+          d[i] = composite(comp_op, d[i], s, m[i]);
+          px_written++;
+        }
+      }
+      dirty = true;
+    }
+    __syncthreads();        // s_list is rewritten by the next chunk
+  }
+
+  if (dirty) {
+    if (BPP == 4) {
+      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d[0], d[1], d[2], d[3]);
+    }
+    else {
+      uint32_t v = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
+      *reinterpret_cast<uint32_t*>(dst_row + px) = v;
+    }
+  }
+
+  px_written = __reduce_add_sync(0xFFFFFFFFu, px_written);
+  if (lane == 0 && px_written) atomicAdd(P.pixel_counter, (unsigned long long)px_written);
+}
+
+// =================================================================================================================
+// Launchers (host)
+// =================================================================================================================
+static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int launch_count_edges(const BuildParams& P, cudaStream_t s) {
+  if (!P.segment_count) return 0;
+  k_count_edges<<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
+  return 1;
+}
+
+int launch_write_edges(const BuildParams& P, cudaStream_t s) {
+  if (!P.segment_count) return 0;
+  k_write_edges<<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
+  return 1;
+}
+
+// Exclusive scan of in[0..n) into out[0..n], out[n] = total, *total_out = total.  `scratch` needs
+// scan_scratch_items(n) u32.  Returns the number of kernels launched.
+size_t scan_scratch_items(uint32_t n) {
+  size_t total = 0;
+  uint32_t m = n;
+  while (m > kScanBlock) {
+    m = div_up(m, kScanBlock);
+    total += size_t(m) + 1;
+  }
+  return total + 8;
+}
+
+int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s) {
+  if (n <= kScanBlock) {
+    k_scan_small<<<1, kScanThreads, 0, s>>>(in, out, n, total_out);
+    return 1;
+  }
+  uint32_t nb = div_up(n, kScanBlock);
+  uint32_t* block_sums = scratch;               // nb + 1 entries; scanned in place
+  k_scan_blocks<<<nb, kScanThreads, 0, s>>>(in, out, block_sums, n);
+  int launches = 1;
+  // Scan the block sums in place (out == in is fine: every element is read before it is written by its own thread,
+  // and blocks only touch their own range).
+  launches += launch_exclusive_scan(block_sums, block_sums, nb, scratch + nb + 1, nullptr, s);
+  k_scan_add<<<nb, kScanThreads, 0, s>>>(out, block_sums, n, total_out);
+  return launches + 1;
+}
+
+int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s) {
+  if (!n) return 0;
+  k_init_bbox<<<div_up(n, 256), 256, 0, s>>>(bbox, n);
+  return 1;
+}
+
+int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s) {
+  if (!ncmd) return 0;
+  k_analytic_bbox<<<div_up(ncmd * 32, 256), 256, 0, s>>>(cmds, ncmd, edges, bbox);
+  return 1;
+}
+
+int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s) {
+  if (!P.command_count) return 0;
+  k_finalize_commands<<<div_up(P.command_count, 256), 256, 0, s>>>(P);
+  return 1;
+}
+
+int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
+  if (!P.command_count) return 0;
+  uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
+  if (!tiles) return 0;
+  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, 0, s>>>(P);
+  else k_tile_render<1><<<tiles, kTileThreads, 0, s>>>(P);
+  return 1;
+}
+
+} // namespace b2d

@@ -1,0 +1,63 @@
+// kernels.h - parameter blocks and launch entry points of the libb2dgpu kernels (see kernels.cu).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/b2dgpu.h"
+
+namespace b2d {
+
+struct BuildParams {
+  const double* vertices;                 // x,y pairs
+  const b2dgpu_segment* segments;
+  uint32_t segment_count;
+  const b2dgpu_command* commands;
+  const b2dgpu_geometry_state* states;
+  uint32_t* seg_counts;                   // count pass: edges per segment
+  const uint32_t* seg_offsets;            // write pass: exclusive scan of seg_counts (segment_count + 1 entries)
+  b2dgpu_edge* edges;                     // device edge array (caller-supplied edges first, built edges after)
+  uint32_t edge_base;                     // index of the first built edge
+  uint32_t edge_capacity;                 // total capacity of `edges`
+  int4* cmd_bbox_fixed;                   // per command: min x, min y, max x, max y in 24.8
+  uint32_t* error_flag;
+};
+
+struct FinalizeParams {
+  const b2dgpu_command* commands;
+  uint32_t command_count;
+  const uint32_t* seg_offsets;
+  uint32_t edge_base;
+  const int4* cmd_bbox_fixed;
+  int4* cmd_bbox_px;                      // clipped pixel box [x0,x1) x [y0,y1) used for tile culling
+  uint2* cmd_edges;                       // (first edge, edge count)
+  int width;
+  int y_begin, y_end;                     // rows of the full image owned by this target
+};
+
+struct TileParams {
+  uint8_t* dst;                           // first byte of row `y_begin`
+  intptr_t dst_stride;
+  int tiles_x, tiles_y;
+  int y_begin;
+  const b2dgpu_command* commands;
+  uint32_t command_count;
+  const int4* cmd_bbox_px;
+  const uint2* cmd_edges;
+  const b2dgpu_edge* edges;
+  const b2dgpu_fetch_data* fetch_data;
+  const uint8_t* bayer;
+  int origin_x, origin_y;
+  unsigned long long* pixel_counter;
+};
+
+// Each launcher returns the number of kernels it launched.
+int launch_count_edges(const BuildParams& P, cudaStream_t s);
+int launch_write_edges(const BuildParams& P, cudaStream_t s);
+size_t scan_scratch_items(uint32_t n);
+int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s);
+int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
+int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
+int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
+int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s);
+
+} // namespace b2d

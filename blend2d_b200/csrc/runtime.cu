@@ -1,0 +1,837 @@
+// runtime.cu - implementation of the C-ABI declared in include/b2dgpu.h.
+//
+// Host-side plumbing only: device/stream ownership, the device-resident canvas, batch serialisation (one pinned staging
+// block -> one H2D copy -> pointer patching), and the kernel sequence  K1 count -> scan -> K1 write -> finalize ->
+// K2+K3 tile render.  No pixel is ever computed on the host: if CUDA is unavailable every entry point fails.
+#include "kernels.h"
+#include "dev_common.cuh"
+
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace b2d;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static b2dgpu_result fail(b2dgpu_result code, const char* what, const char* detail = nullptr) {
+  g_last_error = what;
+  if (detail) { g_last_error += ": "; g_last_error += detail; }
+  return code;
+}
+
+static b2dgpu_result cuda_fail(cudaError_t e, const char* what) {
+  b2dgpu_result code = (e == cudaErrorMemoryAllocation) ? B2DGPU_ERROR_OUT_OF_MEMORY : B2DGPU_ERROR_UNKNOWN;
+  return fail(code, what, cudaGetErrorString(e));
+}
+
+#define CU_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return cuda_fail(e__, #expr); } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small helpers
+// ---------------------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DevBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct PinnedBuffer {
+  void* ptr = nullptr;
+  size_t cap = 0;
+  cudaEvent_t free_event = nullptr;       // recorded after the last async copy that reads this buffer
+  bool in_flight = false;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr; cap = 0;
+    size_t want = align_up(bytes + bytes / 4, 1 << 20);
+    cudaError_t e = cudaMallocHost(&ptr, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; if (free_event) cudaEventDestroy(free_event); free_event = nullptr; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Objects
+// ---------------------------------------------------------------------------------------------------------------
+struct b2dgpu_runtime {
+  // --- layout of bl::Pipeline::PipeRuntime (pipeline/piperuntime_p.h:39-62) ---
+  uint8_t runtime_type;                     // PipeRuntimeType: 0 static, 1 JIT; 2 = GPU (new)
+  uint8_t runtime_flags;                    // PipeRuntimeFlags::kIsolated = 1: destroyed on detach
+  uint16_t runtime_size;
+  uint32_t _pad;
+  void (*destroy_fn)(b2dgpu_runtime*);
+  b2dgpu_result (*test_fn)(b2dgpu_runtime*, uint32_t, b2dgpu_dispatch_data*, void*);
+  b2dgpu_result (*get_fn)(b2dgpu_runtime*, uint32_t, b2dgpu_dispatch_data*, void*);
+  // --- private ---
+  uint32_t magic;
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  std::mutex mutex;
+
+  uint8_t* d_bayer;
+  unsigned long long* d_pixel_counter;
+  uint32_t* d_scalars;                      // [0] = total built edges, [1] = error flag
+  uint32_t* h_scalars;                      // pinned mirror
+
+  PinnedBuffer staging[2];
+  int staging_next;
+  DevBuffer oneshot_block;                  // device block reused by b2dgpu_submit()
+  DevBuffer oneshot_edges;
+  PinnedBuffer image_staging;
+
+  b2dgpu_stats stats;
+};
+
+struct b2dgpu_target {
+  b2dgpu_runtime* rt;
+  int w, h;                                 // h = rows held here (slab height)
+  int full_h, y0;
+  uint32_t format;
+  int bpp;
+  uint8_t* d_pixels;
+  size_t stride;
+  int padded_w, padded_h;
+};
+
+// Offsets of the sections inside a device block.
+struct BlockLayout {
+  size_t commands, fetch_data, vertices, segments, states, supplied_edges, blobs;
+  size_t seg_counts, seg_offsets, scan_scratch, bbox_fixed, bbox_px, cmd_edges;
+  size_t upload_bytes;                      // sections [0, upload_bytes) are filled on the host and copied
+  size_t total_bytes;
+};
+
+struct b2dgpu_batch {
+  b2dgpu_runtime* rt;
+  DevBuffer block;
+  DevBuffer edges;
+  BlockLayout lay;
+  uint32_t command_count, fetch_count, supplied_edges, vertex_count, segment_count, state_count;
+  int origin_x, origin_y;
+  bool has_analytic;
+  uint32_t built_edges;                     // known after the first render
+  bool built_known;
+  bool edges_staged;                        // supplied edges already copied into `edges`
+};
+
+static const uint32_t kRuntimeMagic = 0xB2D09B00u;
+
+// ---------------------------------------------------------------------------------------------------------------
+// Seam B
+// ---------------------------------------------------------------------------------------------------------------
+static void fill_func_token(void*, const void*, const void*) {
+  fprintf(stderr, "b2dgpu: a GPU FillFunc token was called on the CPU; GPU pipelines only run through b2dgpu_submit()\n");
+  abort();
+}
+
+static bool signature_supported(uint32_t sig) {
+  uint32_t dst = B2DGPU_SIG_DST_FORMAT(sig), src = B2DGPU_SIG_SRC_FORMAT(sig);
+  uint32_t op = B2DGPU_SIG_COMP_OP(sig), fill = B2DGPU_SIG_FILL_TYPE(sig), fetch = B2DGPU_SIG_FETCH_TYPE(sig);
+  if (sig & B2DGPU_SIG_PENDING_FLAG) return false;
+  if (!(dst == B2DGPU_FORMAT_PRGB32 || dst == B2DGPU_FORMAT_XRGB32 || dst == B2DGPU_FORMAT_A8 ||
+        dst == B2DGPU_FORMAT_FRGB32 || dst == B2DGPU_FORMAT_ZERO32)) return false;
+  if (!(op == B2DGPU_COMP_OP_SRC_OVER || op == B2DGPU_COMP_OP_SRC_COPY || op == B2DGPU_COMP_OP_PLUS ||
+        op == B2DGPU_COMP_OP_MULTIPLY || op == B2DGPU_COMP_OP_SCREEN)) return false;
+  if (fill < B2DGPU_FILL_BOX_A || fill > B2DGPU_FILL_ANALYTIC) return false;
+  if (fetch > B2DGPU_FETCH_GRADIENT_CONIC_DITHER) return false;
+  if (fetch >= B2DGPU_FETCH_PATTERN_ALIGNED_BLIT && fetch <= B2DGPU_FETCH_PATTERN_AFFINE_BI_OPT) {
+    if (!(src == B2DGPU_FORMAT_PRGB32 || src == B2DGPU_FORMAT_XRGB32 || src == B2DGPU_FORMAT_A8 ||
+          src == B2DGPU_FORMAT_FRGB32 || src == B2DGPU_FORMAT_ZERO32)) return false;
+  }
+  return true;
+}
+
+static b2dgpu_result runtime_lookup(b2dgpu_runtime* rt, uint32_t signature, b2dgpu_dispatch_data* out, bool is_test) {
+  if (!rt || rt->magic != kRuntimeMagic || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_get: invalid argument");
+  if (!signature_supported(signature))
+    return fail(is_test ? B2DGPU_ERROR_NO_ENTRY : B2DGPU_ERROR_NOT_IMPLEMENTED, "signature not implemented by the GPU runtime");
+  out->fill_func = fill_func_token;
+  out->fetch_func = nullptr;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_runtime_test(b2dgpu_runtime* rt, uint32_t signature, b2dgpu_dispatch_data* out, void*) {
+  return runtime_lookup(rt, signature, out, true);
+}
+extern "C" b2dgpu_result b2dgpu_runtime_get(b2dgpu_runtime* rt, uint32_t signature, b2dgpu_dispatch_data* out, void*) {
+  return runtime_lookup(rt, signature, out, false);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Runtime
+// ---------------------------------------------------------------------------------------------------------------
+static void make_bayer_table(uint8_t* t) {
+  // 16x16 ordered-dither matrix, each row stored twice (32 entries) - blend2d/tables/tables_p.h:452-473.  Generated:
+  // rank = bit-interleave of (x ^ y, x) from the least significant coordinate bit to the most significant rank bits,
+  // value = rank - (rank >= 128).
+  for (uint32_t y = 0; y < 16; y++)
+    for (uint32_t x = 0; x < 16; x++) {
+      uint32_t r = 0;
+      for (uint32_t i = 0; i < 4; i++) {
+        uint32_t xb = (x >> i) & 1u, yb = (y >> i) & 1u;
+        r |= ((xb ^ yb) << (2 * (3 - i) + 1)) | (xb << (2 * (3 - i)));
+      }
+      uint8_t v = uint8_t(r - (r >= 128u));
+      t[y * 32 + x] = v;
+      t[y * 32 + 16 + x] = v;
+    }
+}
+
+static void runtime_destroy_thunk(b2dgpu_runtime* rt) { b2dgpu_runtime_destroy(rt); }
+
+extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b2dgpu_runtime** out) {
+  if (!out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_create: out is null");
+  *out = nullptr;
+  int device = info ? info->device : 0;
+
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(B2DGPU_ERROR_NOT_INITIALIZED, "no CUDA device available (there is no CPU fallback)", e != cudaSuccess ? cudaGetErrorString(e) : nullptr);
+  if (device < 0 || device >= count) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_create: invalid device ordinal");
+  CU_TRY(cudaSetDevice(device));
+
+  b2dgpu_runtime* rt = new (std::nothrow) b2dgpu_runtime();
+  if (!rt) return fail(B2DGPU_ERROR_OUT_OF_MEMORY, "b2dgpu_runtime_create: out of host memory");
+  rt->runtime_type = 2;
+  rt->runtime_flags = 1;
+  rt->runtime_size = uint16_t(sizeof(b2dgpu_runtime));
+  rt->_pad = 0;
+  rt->destroy_fn = runtime_destroy_thunk;
+  rt->test_fn = [](b2dgpu_runtime* r, uint32_t s, b2dgpu_dispatch_data* o, void* c) { return b2dgpu_runtime_test(r, s, o, c); };
+  rt->get_fn = [](b2dgpu_runtime* r, uint32_t s, b2dgpu_dispatch_data* o, void* c) { return b2dgpu_runtime_get(r, s, o, c); };
+  rt->magic = kRuntimeMagic;
+  rt->device = device;
+  rt->stream = nullptr;
+  rt->own_stream = false;
+  rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
+  rt->staging_next = 0;
+  memset(&rt->stats, 0, sizeof(rt->stats));
+
+  if (info && info->stream) rt->stream = (cudaStream_t)info->stream;
+  else {
+    e = cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete rt; return cuda_fail(e, "cudaStreamCreate"); }
+    rt->own_stream = true;
+  }
+
+  uint8_t bayer[512];
+  make_bayer_table(bayer);
+  if ((e = cudaMalloc((void**)&rt->d_bayer, 512)) != cudaSuccess ||
+      (e = cudaMemcpy(rt->d_bayer, bayer, 512, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&rt->d_pixel_counter, 8)) != cudaSuccess ||
+      (e = cudaMemset(rt->d_pixel_counter, 0, 8)) != cudaSuccess ||
+      (e = cudaMalloc((void**)&rt->d_scalars, 64)) != cudaSuccess ||
+      (e = cudaMemset(rt->d_scalars, 0, 64)) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&rt->h_scalars, 64)) != cudaSuccess) {
+    b2dgpu_runtime_destroy(rt);
+    return cuda_fail(e, "b2dgpu_runtime_create: device allocation");
+  }
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
+  *out = rt;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
+  if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_destroy: invalid runtime");
+  cudaSetDevice(rt->device);
+  cudaStreamSynchronize(rt->stream);
+  if (rt->d_bayer) cudaFree(rt->d_bayer);
+  if (rt->d_pixel_counter) cudaFree(rt->d_pixel_counter);
+  if (rt->d_scalars) cudaFree(rt->d_scalars);
+  if (rt->h_scalars) cudaFreeHost(rt->h_scalars);
+  for (int i = 0; i < 2; i++) rt->staging[i].release();
+  rt->image_staging.release();
+  rt->oneshot_block.release();
+  rt->oneshot_edges.release();
+  if (rt->own_stream) cudaStreamDestroy(rt->stream);
+  rt->magic = 0;
+  delete rt;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_sync(b2dgpu_runtime* rt) {
+  if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_sync: invalid runtime");
+  CU_TRY(cudaStreamSynchronize(rt->stream));
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_get_stats(b2dgpu_runtime* rt, b2dgpu_stats* out, int reset) {
+  if (!rt || rt->magic != kRuntimeMagic || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_get_stats: invalid argument");
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+  unsigned long long px = 0;
+  CU_TRY(cudaMemcpyAsync(rt->h_scalars + 8, rt->d_pixel_counter, 8, cudaMemcpyDeviceToHost, rt->stream));
+  CU_TRY(cudaStreamSynchronize(rt->stream));
+  memcpy(&px, rt->h_scalars + 8, 8);
+  rt->stats.pixels_composited = px;
+  *out = rt->stats;
+  if (reset) {
+    memset(&rt->stats, 0, sizeof(rt->stats));
+    CU_TRY(cudaMemsetAsync(rt->d_pixel_counter, 0, 8, rt->stream));
+  }
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" const char* b2dgpu_last_error_message(void) { return g_last_error.c_str(); }
+extern "C" uint32_t b2dgpu_abi_version(void) { return 1; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Targets
+// ---------------------------------------------------------------------------------------------------------------
+static int format_bpp(uint32_t format) {
+  switch (format) {
+    case B2DGPU_FORMAT_PRGB32: case B2DGPU_FORMAT_XRGB32: case B2DGPU_FORMAT_FRGB32: case B2DGPU_FORMAT_ZERO32: return 4;
+    case B2DGPU_FORMAT_A8: return 1;
+    default: return 0;
+  }
+}
+
+extern "C" b2dgpu_result b2dgpu_target_create_slab(b2dgpu_runtime* rt, int32_t w, int32_t full_h, int32_t y0, int32_t y1, uint32_t format, b2dgpu_target** out) {
+  if (!rt || rt->magic != kRuntimeMagic || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_create: invalid argument");
+  int bpp = format_bpp(format);
+  if (!bpp || w <= 0 || full_h <= 0 || w > 65535 || full_h > 65535 || y0 < 0 || y1 > full_h || y0 >= y1)
+    return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_create: invalid size or format");
+  cudaSetDevice(rt->device);
+  b2dgpu_target* t = new (std::nothrow) b2dgpu_target();
+  if (!t) return fail(B2DGPU_ERROR_OUT_OF_MEMORY, "b2dgpu_target_create: out of host memory");
+  t->rt = rt; t->w = w; t->h = y1 - y0; t->full_h = full_h; t->y0 = y0; t->format = format; t->bpp = bpp;
+  t->padded_w = int(align_up(size_t(w), kTileW));
+  t->padded_h = int(align_up(size_t(t->h), kTileH));
+  t->stride = size_t(t->padded_w) * bpp;
+  t->d_pixels = nullptr;
+  cudaError_t e = cudaMalloc((void**)&t->d_pixels, t->stride * t->padded_h);
+  if (e != cudaSuccess) { delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMalloc(canvas)"); }
+  e = cudaMemsetAsync(t->d_pixels, 0, t->stride * t->padded_h, rt->stream);
+  if (e != cudaSuccess) { cudaFree(t->d_pixels); delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMemset"); }
+  *out = t;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_target_create(b2dgpu_runtime* rt, int32_t w, int32_t h, uint32_t format, b2dgpu_target** out) {
+  return b2dgpu_target_create_slab(rt, w, h, 0, h, format, out);
+}
+
+extern "C" b2dgpu_result b2dgpu_target_destroy(b2dgpu_target* t) {
+  if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_destroy: null");
+  cudaSetDevice(t->rt->device);
+  cudaStreamSynchronize(t->rt->stream);
+  cudaFree(t->d_pixels);
+  delete t;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_target_clear(b2dgpu_target* t) {
+  if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_clear: null");
+  cudaSetDevice(t->rt->device);
+  CU_TRY(cudaMemsetAsync(t->d_pixels, 0, t->stride * t->padded_h, t->rt->stream));
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_target_device_view(b2dgpu_target* t, void** dev_ptr, intptr_t* stride, int32_t* padded_w, int32_t* padded_h) {
+  if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_device_view: null");
+  if (dev_ptr) *dev_ptr = t->d_pixels;
+  if (stride) *stride = intptr_t(t->stride);
+  if (padded_w) *padded_w = t->padded_w;
+  if (padded_h) *padded_h = t->padded_h;
+  return B2DGPU_SUCCESS;
+}
+
+// The host image covers the FULL image; a slab target transfers only its own rows [y0, y0 + h).
+static b2dgpu_result target_copy(b2dgpu_target* t, const b2dgpu_image_data* img, bool upload) {
+  if (!t || !img || !img->pixel_data) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target copy: invalid argument");
+  if (img->w != t->w || img->h != t->full_h || format_bpp(img->format) != t->bpp)
+    return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target copy: image size/format mismatch");
+  b2dgpu_runtime* rt = t->rt;
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+  size_t row_bytes = size_t(t->w) * t->bpp;
+  uint8_t* host = static_cast<uint8_t*>(img->pixel_data) + intptr_t(t->y0) * img->stride;
+  // Pageable host memory: stage through a pinned buffer so the copy runs at full PCIe rate and stays stream ordered.
+  size_t bytes = row_bytes * t->h;
+  CU_TRY(rt->image_staging.ensure(bytes));
+  uint8_t* stage = static_cast<uint8_t*>(rt->image_staging.ptr);
+  if (upload) {
+    CU_TRY(cudaStreamSynchronize(rt->stream));                 // previous use of the staging buffer
+    for (int y = 0; y < t->h; y++) memcpy(stage + size_t(y) * row_bytes, host + intptr_t(y) * img->stride, row_bytes);
+    CU_TRY(cudaMemcpy2DAsync(t->d_pixels, t->stride, stage, row_bytes, row_bytes, t->h, cudaMemcpyHostToDevice, rt->stream));
+    rt->stats.h2d_bytes += bytes;
+  }
+  else {
+    CU_TRY(cudaMemcpy2DAsync(stage, row_bytes, t->d_pixels, t->stride, row_bytes, t->h, cudaMemcpyDeviceToHost, rt->stream));
+    CU_TRY(cudaStreamSynchronize(rt->stream));
+    for (int y = 0; y < t->h; y++) memcpy(host + intptr_t(y) * img->stride, stage + size_t(y) * row_bytes, row_bytes);
+    rt->stats.d2h_bytes += bytes;
+  }
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_target_upload(b2dgpu_target* t, const b2dgpu_image_data* src) { return target_copy(t, src, true); }
+extern "C" b2dgpu_result b2dgpu_target_download(b2dgpu_target* t, const b2dgpu_image_data* dst) { return target_copy(t, dst, false); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch serialisation
+// ---------------------------------------------------------------------------------------------------------------
+struct BlobRef { const void* host; size_t bytes; size_t offset; };
+
+struct FetchUse { uint32_t fetch_type; uint32_t src_format; bool used; };
+
+static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
+  if (!v || v->struct_size < sizeof(b2dgpu_batch_view)) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: bad struct_size");
+  if (v->command_count && !v->commands) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: commands is null");
+  for (uint32_t i = 0; i < v->command_count; i++) {
+    const b2dgpu_command& c = v->commands[i];
+    if (c.type < B2DGPU_CMD_FILL_BOX_A || c.type > B2DGPU_CMD_FILL_GEOMETRY) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: unknown command type");
+    if (!signature_supported(c.signature)) return fail(B2DGPU_ERROR_NOT_IMPLEMENTED, "batch view: command signature not implemented");
+    if (c.alpha > 255) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: alpha out of range");
+    if (B2DGPU_SIG_FETCH_TYPE(c.signature) != B2DGPU_FETCH_SOLID && c.fetch_index >= v->fetch_count)
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: fetch_index out of range");
+    if (c.type == B2DGPU_CMD_FILL_ANALYTIC && (uint64_t(c.data_offset) + c.data_count > v->edge_count))
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: edge range out of bounds");
+    if (c.type == B2DGPU_CMD_FILL_GEOMETRY) {
+      if (uint64_t(c.data_offset) + c.data_count > v->segment_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment range out of bounds");
+      if (c.state_index >= v->geometry_state_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: state_index out of range");
+    }
+    if ((c.type == B2DGPU_CMD_FILL_BOX_A || c.type == B2DGPU_CMD_FILL_BOX_U) && !(c.box[0] < c.box[2] && c.box[1] < c.box[3]))
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: empty box");
+  }
+  for (uint32_t i = 0; i < v->segment_count; i++) {
+    const b2dgpu_segment& s = v->segments[i];
+    uint32_t kind = s.p1_kind & 3u, i1 = s.p1_kind >> 2;
+    uint32_t extra = kind == B2DGPU_SEG_LINE ? 0u : kind == B2DGPU_SEG_QUAD ? 1u : 2u;
+    if (s.p0 >= v->vertex_count || uint64_t(i1) + extra >= v->vertex_count || s.command >= v->command_count)
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment references out of range");
+  }
+  return B2DGPU_SUCCESS;
+}
+
+static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, BlockLayout& L) {
+  size_t off = 0;
+  auto add = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
+  L.commands = add(sizeof(b2dgpu_command) * v->command_count);
+  L.fetch_data = add(sizeof(b2dgpu_fetch_data) * v->fetch_count);
+  L.vertices = add(sizeof(double) * 2 * v->vertex_count);
+  L.segments = add(sizeof(b2dgpu_segment) * v->segment_count);
+  L.states = add(sizeof(b2dgpu_geometry_state) * v->geometry_state_count);
+  L.supplied_edges = add(sizeof(b2dgpu_edge) * v->edge_count);
+  L.blobs = add(blob_bytes);
+  L.upload_bytes = align_up(off, 256);
+  off = L.upload_bytes;
+  L.seg_counts = add(sizeof(uint32_t) * (size_t(v->segment_count) + 1));
+  L.seg_offsets = add(sizeof(uint32_t) * (size_t(v->segment_count) + 1));
+  L.scan_scratch = add(sizeof(uint32_t) * scan_scratch_items(v->segment_count));
+  L.bbox_fixed = add(sizeof(int4) * v->command_count);
+  L.bbox_px = add(sizeof(int4) * v->command_count);
+  L.cmd_edges = add(sizeof(uint2) * v->command_count);
+  L.total_bytes = align_up(off, 256);
+}
+
+// Serialises `v` into `host_block` (size lay.upload_bytes) with fetch-data pointers patched to `dev_base + offset`.
+static b2dgpu_result serialize_batch(const b2dgpu_batch_view* v, std::vector<BlobRef>& blobs, const BlockLayout& L, uint8_t* host_block, const uint8_t* dev_base) {
+  memcpy(host_block + L.commands, v->commands, sizeof(b2dgpu_command) * v->command_count);
+  if (v->vertex_count) memcpy(host_block + L.vertices, v->vertices, sizeof(double) * 2 * v->vertex_count);
+  if (v->segment_count) memcpy(host_block + L.segments, v->segments, sizeof(b2dgpu_segment) * v->segment_count);
+  if (v->geometry_state_count) memcpy(host_block + L.states, v->geometry_states, sizeof(b2dgpu_geometry_state) * v->geometry_state_count);
+  if (v->edge_count) memcpy(host_block + L.supplied_edges, v->edges, sizeof(b2dgpu_edge) * v->edge_count);
+  for (const BlobRef& b : blobs) memcpy(host_block + L.blobs + b.offset, b.host, b.bytes);
+
+  b2dgpu_fetch_data* fd = reinterpret_cast<b2dgpu_fetch_data*>(host_block + L.fetch_data);
+  if (v->fetch_count) memcpy(fd, v->fetch_data, sizeof(b2dgpu_fetch_data) * v->fetch_count);
+  return B2DGPU_SUCCESS;
+}
+
+// Collects the host memory referenced by fetch data (gradient LUTs, pattern pixels), de-duplicated by address.
+static b2dgpu_result collect_blobs(const b2dgpu_batch_view* v, std::vector<FetchUse>& uses, std::vector<BlobRef>& blobs,
+                                   std::vector<size_t>& fetch_blob, size_t& blob_bytes) {
+  uses.assign(v->fetch_count, FetchUse{0, 0, false});
+  for (uint32_t i = 0; i < v->command_count; i++) {
+    const b2dgpu_command& c = v->commands[i];
+    uint32_t ft = B2DGPU_SIG_FETCH_TYPE(c.signature);
+    if (ft == B2DGPU_FETCH_SOLID) continue;
+    FetchUse& u = uses[c.fetch_index];
+    uint32_t sf = B2DGPU_SIG_SRC_FORMAT(c.signature);
+    if (u.used && (u.fetch_type != ft || u.src_format != sf)) {
+      // The same FetchData may legitimately be used with different fill types only; fetch type/format must agree.
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: one fetch_data entry used with two different fetch types");
+    }
+    u.fetch_type = ft; u.src_format = sf; u.used = true;
+  }
+
+  std::unordered_map<const void*, size_t> seen;
+  fetch_blob.assign(v->fetch_count, size_t(-1));
+  blob_bytes = 0;
+  for (uint32_t i = 0; i < v->fetch_count; i++) {
+    if (!uses[i].used) continue;
+    const b2dgpu_fetch_data& fd = v->fetch_data[i];
+    const void* host = nullptr;
+    size_t bytes = 0;
+    if (uses[i].fetch_type >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD) {
+      bool dither = uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_PAD || uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_ROR ||
+                    uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_PAD || uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_ROR ||
+                    uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_CONIC_DITHER;
+      host = fd.gradient.lut.data;
+      bytes = size_t(fd.gradient.lut.size) * (dither ? 8 : 4);
+      if (!host || !bytes) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: gradient without a LUT");
+    }
+    else {
+      const b2dgpu_pattern_source& s = fd.pattern.src;
+      if (!s.pixel_data || s.w <= 0 || s.h <= 0 || s.stride <= 0) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: invalid pattern source");
+      host = s.pixel_data;
+      bytes = size_t(s.stride) * size_t(s.h - 1) + size_t(s.w) * (uses[i].src_format == B2DGPU_FORMAT_A8 ? 1 : 4);
+    }
+    auto it = seen.find(host);
+    if (it != seen.end() && blobs[it->second].bytes >= bytes) { fetch_blob[i] = it->second; continue; }
+    BlobRef b; b.host = host; b.bytes = bytes; b.offset = align_up(blob_bytes, 256);
+    blob_bytes = b.offset + bytes;
+    seen[host] = blobs.size();
+    fetch_blob[i] = blobs.size();
+    blobs.push_back(b);
+  }
+  return B2DGPU_SUCCESS;
+}
+
+struct PreparedBatch {
+  BlockLayout lay;
+  std::vector<BlobRef> blobs;
+  std::vector<FetchUse> uses;
+  std::vector<size_t> fetch_blob;
+  bool has_analytic;
+};
+
+static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb) {
+  b2dgpu_result r = validate_batch(v);
+  if (r) return r;
+  size_t blob_bytes = 0;
+  r = collect_blobs(v, pb.uses, pb.blobs, pb.fetch_blob, blob_bytes);
+  if (r) return r;
+  plan_layout(v, blob_bytes, pb.lay);
+  pb.has_analytic = false;
+  for (uint32_t i = 0; i < v->command_count; i++) if (v->commands[i].type == B2DGPU_CMD_FILL_ANALYTIC) pb.has_analytic = true;
+  return B2DGPU_SUCCESS;
+}
+
+// Fills the pinned block and copies it to `dev_block`.
+static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v, PreparedBatch& pb, uint8_t* dev_block) {
+  PinnedBuffer& st = rt->staging[rt->staging_next];
+  rt->staging_next ^= 1;
+  if (st.in_flight) { CU_TRY(cudaEventSynchronize(st.free_event)); st.in_flight = false; }
+  CU_TRY(st.ensure(pb.lay.upload_bytes));
+  uint8_t* host_block = static_cast<uint8_t*>(st.ptr);
+  serialize_batch(v, pb.blobs, pb.lay, host_block, dev_block);
+
+  // Patch host pointers inside FetchData to their device copies.
+  b2dgpu_fetch_data* fd = reinterpret_cast<b2dgpu_fetch_data*>(host_block + pb.lay.fetch_data);
+  for (uint32_t i = 0; i < v->fetch_count; i++) {
+    if (!pb.uses[i].used) continue;
+    const uint8_t* dev = dev_block + pb.lay.blobs + pb.blobs[pb.fetch_blob[i]].offset;
+    if (pb.uses[i].fetch_type >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD) fd[i].gradient.lut.data = dev;
+    else fd[i].pattern.src.pixel_data = dev;
+  }
+
+  CU_TRY(cudaMemcpyAsync(dev_block, host_block, pb.lay.upload_bytes, cudaMemcpyHostToDevice, rt->stream));
+  CU_TRY(cudaEventRecord(st.free_event, rt->stream));
+  st.in_flight = true;
+  rt->stats.h2d_bytes += pb.lay.upload_bytes;
+  return B2DGPU_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Rendering
+// ---------------------------------------------------------------------------------------------------------------
+struct RenderInput {
+  uint8_t* block;
+  const BlockLayout* lay;
+  DevBuffer* edges;
+  uint32_t command_count, supplied_edges, segment_count;
+  int origin_x, origin_y;
+  bool has_analytic;
+  bool built_known;
+  uint32_t built_edges;
+  bool edges_staged;
+};
+
+static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderInput& in) {
+  const BlockLayout& L = *in.lay;
+  cudaStream_t s = rt->stream;
+  uint8_t* blk = in.block;
+  int launches = 0;
+
+  const b2dgpu_command* d_cmds = reinterpret_cast<const b2dgpu_command*>(blk + L.commands);
+  int4* d_bbox_fixed = reinterpret_cast<int4*>(blk + L.bbox_fixed);
+  uint32_t* d_seg_counts = reinterpret_cast<uint32_t*>(blk + L.seg_counts);
+  uint32_t* d_seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
+
+  launches += launch_init_bbox(d_bbox_fixed, in.command_count, s);
+
+  BuildParams B;
+  B.vertices = reinterpret_cast<const double*>(blk + L.vertices);
+  B.segments = reinterpret_cast<const b2dgpu_segment*>(blk + L.segments);
+  B.segment_count = in.segment_count;
+  B.commands = d_cmds;
+  B.states = reinterpret_cast<const b2dgpu_geometry_state*>(blk + L.states);
+  B.seg_counts = d_seg_counts;
+  B.seg_offsets = d_seg_offsets;
+  B.edge_base = in.supplied_edges;
+  B.cmd_bbox_fixed = d_bbox_fixed;
+  B.error_flag = rt->d_scalars + 1;
+
+  if (in.segment_count) {
+    // K1 pass 1 + scan run on every render: they are part of the path even when the total is already known.
+    launches += launch_count_edges(B, s);
+    launches += launch_exclusive_scan(d_seg_counts, d_seg_offsets, in.segment_count,
+                                      reinterpret_cast<uint32_t*>(blk + L.scan_scratch), rt->d_scalars, s);
+    if (!in.built_known) {
+      // First time this geometry is seen: the edge buffer has to be sized, which needs the total on the host.
+      CU_TRY(cudaMemcpyAsync(rt->h_scalars, rt->d_scalars, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      in.built_edges = rt->h_scalars[0];
+      in.built_known = true;
+      rt->stats.d2h_bytes += 4;
+    }
+  }
+  else {
+    in.built_edges = 0;
+    in.built_known = true;
+  }
+
+  const size_t total_edges = size_t(in.supplied_edges) + in.built_edges;
+  if (total_edges > 0xFFFFFFF0u) return fail(B2DGPU_ERROR_OUT_OF_MEMORY, "too many edges in one batch");
+  {
+    size_t need = total_edges * sizeof(b2dgpu_edge);
+    if (need < 4096) need = 4096;
+    if (need > in.edges->cap) {
+      CU_TRY(cudaStreamSynchronize(s));
+      CU_TRY(in.edges->ensure(need));
+      in.edges_staged = false;
+    }
+    if (!in.edges_staged && in.supplied_edges) {
+      CU_TRY(cudaMemcpyAsync(in.edges->ptr, blk + L.supplied_edges, sizeof(b2dgpu_edge) * in.supplied_edges, cudaMemcpyDeviceToDevice, s));
+    }
+    in.edges_staged = true;
+  }
+  B.edges = static_cast<b2dgpu_edge*>(in.edges->ptr);
+  B.edge_capacity = uint32_t(in.edges->cap / sizeof(b2dgpu_edge));
+
+  if (in.has_analytic)
+    launches += launch_analytic_bbox(d_cmds, in.command_count, B.edges, d_bbox_fixed, s);
+  if (in.segment_count && in.built_edges)
+    launches += launch_write_edges(B, s);
+
+  FinalizeParams F;
+  F.commands = d_cmds;
+  F.command_count = in.command_count;
+  F.seg_offsets = d_seg_offsets;
+  F.edge_base = in.supplied_edges;
+  F.cmd_bbox_fixed = d_bbox_fixed;
+  F.cmd_bbox_px = reinterpret_cast<int4*>(blk + L.bbox_px);
+  F.cmd_edges = reinterpret_cast<uint2*>(blk + L.cmd_edges);
+  F.width = t->w;
+  F.y_begin = t->y0;
+  F.y_end = t->y0 + t->h;
+  launches += launch_finalize_commands(F, s);
+
+  TileParams T;
+  T.dst = t->d_pixels;
+  T.dst_stride = intptr_t(t->stride);
+  T.tiles_x = t->padded_w / kTileW;
+  T.tiles_y = t->padded_h / kTileH;
+  T.y_begin = t->y0;
+  T.commands = d_cmds;
+  T.command_count = in.command_count;
+  T.cmd_bbox_px = F.cmd_bbox_px;
+  T.cmd_edges = F.cmd_edges;
+  T.edges = B.edges;
+  T.fetch_data = reinterpret_cast<const b2dgpu_fetch_data*>(blk + L.fetch_data);
+  T.bayer = rt->d_bayer;
+  T.origin_x = in.origin_x;
+  T.origin_y = in.origin_y;
+  T.pixel_counter = rt->d_pixel_counter;
+  launches += launch_tile_render(T, t->bpp, s);
+
+  CU_TRY(cudaGetLastError());
+  rt->stats.kernel_launches += uint64_t(launches);
+  rt->stats.commands += in.command_count;
+  rt->stats.edges += total_edges;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view) {
+  if (!rt || rt->magic != kRuntimeMagic || !target || target->rt != rt) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: invalid argument");
+  if (!view || view->command_count == 0) return view ? B2DGPU_SUCCESS : fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: view is null");
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+
+  PreparedBatch pb;
+  b2dgpu_result r = prepare_batch(view, pb);
+  if (r) return r;
+
+  if (pb.lay.total_bytes > rt->oneshot_block.cap) {
+    CU_TRY(cudaStreamSynchronize(rt->stream));
+    CU_TRY(rt->oneshot_block.ensure(pb.lay.total_bytes));
+  }
+  uint8_t* blk = static_cast<uint8_t*>(rt->oneshot_block.ptr);
+  r = upload_block(rt, view, pb, blk);
+  if (r) return r;
+
+  RenderInput in;
+  in.block = blk; in.lay = &pb.lay; in.edges = &rt->oneshot_edges;
+  in.command_count = view->command_count; in.supplied_edges = view->edge_count; in.segment_count = view->segment_count;
+  in.origin_x = view->pixel_origin_x; in.origin_y = view->pixel_origin_y;
+  in.has_analytic = pb.has_analytic;
+  in.built_known = false; in.built_edges = 0; in.edges_staged = false;
+  return render_block(rt, target, in);
+}
+
+extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_batch** out) {
+  if (!rt || rt->magic != kRuntimeMagic || !view || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_upload: invalid argument");
+  *out = nullptr;
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+
+  PreparedBatch pb;
+  b2dgpu_result r = prepare_batch(view, pb);
+  if (r) return r;
+
+  b2dgpu_batch* b = new (std::nothrow) b2dgpu_batch();
+  if (!b) return fail(B2DGPU_ERROR_OUT_OF_MEMORY, "b2dgpu_batch_upload: out of host memory");
+  b->rt = rt;
+  b->lay = pb.lay;
+  b->command_count = view->command_count; b->fetch_count = view->fetch_count; b->supplied_edges = view->edge_count;
+  b->vertex_count = view->vertex_count; b->segment_count = view->segment_count; b->state_count = view->geometry_state_count;
+  b->origin_x = view->pixel_origin_x; b->origin_y = view->pixel_origin_y;
+  b->has_analytic = pb.has_analytic;
+  b->built_known = false; b->built_edges = 0;
+
+  cudaError_t e = b->block.ensure(pb.lay.total_bytes);
+  if (e != cudaSuccess) { delete b; return cuda_fail(e, "b2dgpu_batch_upload: cudaMalloc(block)"); }
+  b->edges_staged = false;
+  r = upload_block(rt, view, pb, static_cast<uint8_t*>(b->block.ptr));
+  if (r) { b->block.release(); b->edges.release(); delete b; return r; }
+  *out = b;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_batch_destroy(b2dgpu_batch* b) {
+  if (!b) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_destroy: null");
+  cudaSetDevice(b->rt->device);
+  cudaStreamSynchronize(b->rt->stream);
+  b->block.release();
+  b->edges.release();
+  delete b;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* target, b2dgpu_batch* b) {
+  if (!rt || rt->magic != kRuntimeMagic || !target || target->rt != rt || !b || b->rt != rt)
+    return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_render: invalid argument");
+  if (!b->command_count) return B2DGPU_SUCCESS;
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+  RenderInput in;
+  in.block = static_cast<uint8_t*>(b->block.ptr); in.lay = &b->lay; in.edges = &b->edges;
+  in.command_count = b->command_count; in.supplied_edges = b->supplied_edges; in.segment_count = b->segment_count;
+  in.origin_x = b->origin_x; in.origin_y = b->origin_y;
+  in.has_analytic = b->has_analytic;
+  in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged;
+  // The whole path (K1 count, scan, K1 write, finalize, K2+K3) re-runs on every render; only the host read-back of the
+  // edge total is skipped after the first time because the geometry of a resident batch cannot change.
+  b2dgpu_result r = render_block(rt, target, in);
+  b->built_known = in.built_known; b->built_edges = in.built_edges; b->edges_staged = in.edges_staged;
+  return r;
+}
+
+extern "C" b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_edge* edges_out,
+                                                  uint32_t capacity, uint32_t* count_out, uint32_t* per_command_begin_out) {
+  if (!rt || rt->magic != kRuntimeMagic || !view || !count_out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_debug_build_edges: invalid argument");
+  b2dgpu_batch* b = nullptr;
+  b2dgpu_result r = b2dgpu_batch_upload(rt, view, &b);
+  if (r) return r;
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  cudaSetDevice(rt->device);
+  uint8_t* blk = static_cast<uint8_t*>(b->block.ptr);
+  const BlockLayout& L = b->lay;
+  cudaStream_t s = rt->stream;
+
+  BuildParams B;
+  memset(&B, 0, sizeof(B));
+  B.vertices = reinterpret_cast<const double*>(blk + L.vertices);
+  B.segments = reinterpret_cast<const b2dgpu_segment*>(blk + L.segments);
+  B.segment_count = b->segment_count;
+  B.commands = reinterpret_cast<const b2dgpu_command*>(blk + L.commands);
+  B.states = reinterpret_cast<const b2dgpu_geometry_state*>(blk + L.states);
+  B.seg_counts = reinterpret_cast<uint32_t*>(blk + L.seg_counts);
+  B.seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
+  B.edge_base = 0;
+  B.cmd_bbox_fixed = reinterpret_cast<int4*>(blk + L.bbox_fixed);
+  B.error_flag = rt->d_scalars + 1;
+
+  cudaError_t e = cudaSuccess;
+  uint32_t built = 0;
+  std::vector<uint32_t> offs(size_t(b->segment_count) + 1, 0);
+  if (b->segment_count) {
+    launch_init_bbox(B.cmd_bbox_fixed, b->command_count, s);
+    launch_count_edges(B, s);
+    launch_exclusive_scan(B.seg_counts, reinterpret_cast<uint32_t*>(blk + L.seg_offsets), b->segment_count,
+                          reinterpret_cast<uint32_t*>(blk + L.scan_scratch), rt->d_scalars, s);
+    e = cudaMemcpyAsync(offs.data(), B.seg_offsets, sizeof(uint32_t) * offs.size(), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    built = offs[b->segment_count];
+    if (e == cudaSuccess && built) {
+      e = b->edges.ensure(sizeof(b2dgpu_edge) * size_t(built));
+      if (e == cudaSuccess) {
+        B.edges = static_cast<b2dgpu_edge*>(b->edges.ptr);
+        B.edge_capacity = uint32_t(b->edges.cap / sizeof(b2dgpu_edge));
+        launch_write_edges(B, s);
+        if (edges_out) {
+          uint32_t n = built < capacity ? built : capacity;
+          e = cudaMemcpyAsync(edges_out, B.edges, sizeof(b2dgpu_edge) * n, cudaMemcpyDeviceToHost, s);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      }
+    }
+  }
+  *count_out = built;
+  if (per_command_begin_out) {
+    // Commands own contiguous segment ranges, so their edge ranges follow from the segment offsets.
+    uint32_t last = 0;
+    for (uint32_t i = 0; i < view->command_count; i++) {
+      const b2dgpu_command& c = view->commands[i];
+      if (c.type == B2DGPU_CMD_FILL_GEOMETRY && c.data_count) {
+        per_command_begin_out[i] = offs[c.data_offset];
+        last = offs[c.data_offset + c.data_count];
+      }
+      else per_command_begin_out[i] = last;
+    }
+    per_command_begin_out[view->command_count] = built;
+  }
+  if (e == cudaSuccess) e = cudaGetLastError();
+  b2dgpu_result res = (e == cudaSuccess) ? B2DGPU_SUCCESS : cuda_fail(e, "b2dgpu_debug_build_edges");
+  b->block.release(); b->edges.release(); delete b;
+  return res;
+}

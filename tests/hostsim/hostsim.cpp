@@ -1,0 +1,184 @@
+// hostsim.cpp - TEST-ONLY lockstep simulator of the GPU compositor's scalar device functions.
+//
+// This translation unit includes the very same dev_*.cuh headers that nvcc compiles into the sm_100a kernels and runs
+// them sequentially on the CPU: per path segment -> build_line/quad/cubic, per tile and command -> tile_accumulate_edge,
+// prefix sum, calc_mask, fetch_pixel, composite.  It exists so that the parts of the algorithm that do not depend on
+// CUDA's execution model can be checked against the reference on a machine without a GPU (`pytest -m "not gpu"`).
+// It is built from tests/ into tests/hostsim/_hostsim.so and is NOT part of libb2dgpu.so nor reachable from the
+// blend2d_b200 package: the product has no CPU path.
+#include "../../blend2d_b200/csrc/dev_pixel.cuh"
+#include "../../blend2d_b200/csrc/dev_raster.cuh"
+#include "../../blend2d_b200/csrc/dev_flatten.cuh"
+#include "../../blend2d_b200/csrc/dev_fetch.cuh"
+#include "../../blend2d_b200/csrc/dev_tile.cuh"
+
+#include <limits.h>
+#include <string.h>
+#include <vector>
+
+using namespace b2d;
+
+namespace {
+
+struct VecOut {
+  std::vector<b2dgpu_edge>* v;
+  void edge(int x0, int y0, int x1, int y1) { b2dgpu_edge e; e.x0 = x0; e.y0 = y0; e.x1 = x1; e.y1 = y1; v->push_back(e); }
+};
+
+void build_segment(const b2dgpu_batch_view* B, uint32_t si, VecOut& out) {
+  const b2dgpu_segment seg = B->segments[si];
+  const b2dgpu_command& cmd = B->commands[seg.command];
+  const b2dgpu_geometry_state& gs = B->geometry_states[cmd.state_index];
+  GeomXform xf;
+  xf.m00 = gs.m[0]; xf.m01 = gs.m[1]; xf.m10 = gs.m[2]; xf.m11 = gs.m[3]; xf.m20 = gs.m[4]; xf.m21 = gs.m[5];
+  xf.affine = gs.transform_type > 2u;
+  ClipBox cb;
+  cb.x0 = gs.clip[0]; cb.y0 = gs.clip[1]; cb.x1 = gs.clip[2]; cb.y1 = gs.clip[3];
+  cb.ix0 = trunc_i(cb.x0); cb.ix1 = trunc_i(cb.x1);
+  const double* v = B->vertices;
+  uint32_t kind = seg.p1_kind & 3u, i1 = seg.p1_kind >> 2;
+  P2 p0 = xform(xf, mk(v[seg.p0 * 2], v[seg.p0 * 2 + 1]));
+  P2 p1 = xform(xf, mk(v[i1 * 2], v[i1 * 2 + 1]));
+  if (kind == B2DGPU_SEG_LINE) build_line(p0, p1, cb, out);
+  else if (kind == B2DGPU_SEG_CUBIC)
+    build_cubic(p0, p1, xform(xf, mk(v[(i1 + 1) * 2], v[(i1 + 1) * 2 + 1])), xform(xf, mk(v[(i1 + 2) * 2], v[(i1 + 2) * 2 + 1])), cb, gs.tolerance_sq, out);
+  else {
+    uint32_t i2 = i1 + (kind == B2DGPU_SEG_CONIC ? 2u : 1u);
+    build_quad(p0, p1, xform(xf, mk(v[i2 * 2], v[i2 * 2 + 1])), cb, gs.tolerance_sq, out);
+  }
+}
+
+struct HostStore {
+  uint32_t cells[kTileH][kTileW];
+  uint32_t carry[kTileH];
+  void add_cell(int row, int rel, uint32_t v) { cells[row][rel] += v; }
+  void add_carry(int row, uint32_t v) { carry[row] += v; }
+};
+
+} // namespace
+
+extern "C" {
+
+// Flattens all FILL_GEOMETRY commands.  edges_out may be null to only count.  begins_out: command_count + 1 entries.
+__attribute__((visibility("default")))
+uint32_t hostsim_build_edges(const b2dgpu_batch_view* B, b2dgpu_edge* edges_out, uint32_t capacity, uint32_t* begins_out) {
+  std::vector<b2dgpu_edge> all;
+  VecOut out{ &all };
+  for (uint32_t c = 0; c < B->command_count; c++) {
+    const b2dgpu_command& cmd = B->commands[c];
+    if (begins_out) begins_out[c] = uint32_t(all.size());
+    if (cmd.type != B2DGPU_CMD_FILL_GEOMETRY) continue;
+    for (uint32_t s = 0; s < cmd.data_count; s++) build_segment(B, cmd.data_offset + s, out);
+  }
+  if (begins_out) begins_out[B->command_count] = uint32_t(all.size());
+  if (edges_out) memcpy(edges_out, all.data(), sizeof(b2dgpu_edge) * (all.size() < capacity ? all.size() : capacity));
+  return uint32_t(all.size());
+}
+
+// Renders the batch into a host image, tile by tile, exactly in the order of operations of k_tile_render.
+// `bayer` = 512-byte table (16 rows x 32).  Returns the number of composited pixels.
+__attribute__((visibility("default")))
+uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t stride, int w, int h, uint32_t format, const uint8_t* bayer) {
+  const int bpp = format == B2DGPU_FORMAT_A8 ? 1 : 4;
+  uint64_t written = 0;
+
+  // K1 for every geometry command.
+  std::vector<b2dgpu_edge> edges(B->edges, B->edges + B->edge_count);
+  std::vector<uint32_t> e_begin(B->command_count), e_count(B->command_count);
+  std::vector<CmdBox> boxes(B->command_count);
+  VecOut out{ &edges };
+  for (uint32_t c = 0; c < B->command_count; c++) {
+    const b2dgpu_command& cmd = B->commands[c];
+    e_begin[c] = 0; e_count[c] = 0;
+    if (cmd.type == B2DGPU_CMD_FILL_ANALYTIC) { e_begin[c] = cmd.data_offset; e_count[c] = cmd.data_count; }
+    else if (cmd.type == B2DGPU_CMD_FILL_GEOMETRY) {
+      e_begin[c] = uint32_t(edges.size());
+      for (uint32_t s = 0; s < cmd.data_count; s++) build_segment(B, cmd.data_offset + s, out);
+      e_count[c] = uint32_t(edges.size()) - e_begin[c];
+    }
+    int fx0 = INT_MAX, fy0 = INT_MAX, fx1 = INT_MIN, fy1 = INT_MIN;
+    for (uint32_t i = 0; i < e_count[c]; i++) {
+      const b2dgpu_edge& e = edges[e_begin[c] + i];
+      fx0 = tmin(fx0, tmin(e.x0, e.x1)); fx1 = tmax(fx1, tmax(e.x0, e.x1));
+      fy0 = tmin(fy0, tmin(e.y0, e.y1)); fy1 = tmax(fy1, tmax(e.y0, e.y1));
+    }
+    boxes[c] = command_pixel_box(cmd, e_count[c], fx0, fy0, fx1, fy1, w, 0, h);
+  }
+
+  const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+  static HostStore store;
+  for (int ty = 0; ty < tiles_y; ty++) for (int tx = 0; tx < tiles_x; tx++) {
+    const int tx0 = tx * kTileW, ty0 = ty * kTileH;
+    memset(&store, 0, sizeof(store));
+    for (uint32_t c = 0; c < B->command_count; c++) {
+      const CmdBox& bb = boxes[c];
+      if (!(bb.x0 < tx0 + kTileW && bb.x1 > tx0 && bb.y0 < ty0 + kTileH && bb.y1 > ty0)) continue;
+      const b2dgpu_command& cmd = B->commands[c];
+      const uint32_t sig = cmd.signature, alpha = cmd.alpha;
+      uint32_t masks[kTileH][kTileW];
+      memset(masks, 0, sizeof(masks));
+
+      if (cmd.type == B2DGPU_CMD_FILL_BOX_A) {
+        for (int r = 0; r < kTileH; r++) for (int x = 0; x < kTileW; x++) {
+          int px = tx0 + x, py = ty0 + r;
+          masks[r][x] = (py >= cmd.box[1] && py < cmd.box[3] && px >= cmd.box[0] && px < cmd.box[2]) ? alpha : 0u;
+        }
+      }
+      else if (cmd.type == B2DGPU_CMD_FILL_BOX_U) {
+        BoxUParams bu = box_u_setup(cmd.box, alpha);
+        for (int r = 0; r < kTileH; r++) for (int x = 0; x < kTileW; x++) masks[r][x] = box_u_mask(bu, tx0 + x, ty0 + r);
+      }
+      else {
+        uint32_t left_acc[kTileH];
+        memset(left_acc, 0, sizeof(left_acc));
+        bool touched = false;
+        for (uint32_t e = 0; e < e_count[c]; e++)
+          touched |= tile_accumulate_edge(edges[e_begin[c] + e], tx0, ty0, store, left_acc);
+        for (int r = 0; r < kTileH; r++) if (left_acc[r]) { store.carry[r] += left_acc[r]; touched = true; }
+        if (!touched) continue;
+        for (int r = 0; r < kTileH; r++) {
+          uint32_t cov = (256u << 9) + store.carry[r];
+          for (int x = 0; x < kTileW; x++) {
+            cov += store.cells[r][x];
+            uint32_t m = calc_mask(cov, cmd.fill_rule_mask, alpha);
+            if (tx0 + x >= bb.x1) m = 0;
+            masks[r][x] = m;
+          }
+        }
+        memset(&store, 0, sizeof(store));
+      }
+
+      FetchEnv env;
+      env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
+      env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
+      env.solid = cmd.solid_prgb32;
+      env.fd = B->fetch_data ? B->fetch_data + cmd.fetch_index : nullptr;
+      env.bayer = bayer;
+      env.origin_x = B->pixel_origin_x; env.origin_y = B->pixel_origin_y;
+      const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
+
+      for (int r = 0; r < kTileH; r++) {
+        int py = ty0 + r;
+        if (py >= h) break;
+        RowCtx rc;
+        fetch_row_init(env, uint32_t(py), rc);
+        for (int x = 0; x < kTileW; x++) {
+          int px = tx0 + x;
+          if (px >= w) break;
+          uint32_t m = masks[r][x];
+          if (!m) continue;
+          uint8_t* p = pixels + intptr_t(py) * stride + intptr_t(px) * bpp;
+          uint32_t d = bpp == 4 ? *reinterpret_cast<uint32_t*>(p) : uint32_t(*p) * 0x01010101u;
+          uint32_t s = fetch_pixel(env, rc, uint32_t(px), uint32_t(py));
+          if (bpp == 1) s = (s >> 24) * 0x01010101u;
+          d = composite(comp_op, d, s, m);
+          if (bpp == 4) *reinterpret_cast<uint32_t*>(p) = d; else *p = uint8_t(d >> 24);
+          written++;
+        }
+      }
+    }
+  }
+  return written;
+}
+
+} // extern "C"
