@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference, built from /root/reference into oracle/_ref (travels to the GPU box)."""
+    from oracle import ref_blend2d as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libblend2d_ref.so not built (needs /root/reference): run make -f oracle/Makefile.ref")
+    return R
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    import blend2d_b200 as G
+    return G

@@ -1,0 +1,75 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the UNMODIFIED reference on the same seeded scenes.
+
+Tolerances written here: 0 for solid / pattern / coverage / compositing; gradients are bit-exact too on the reference's
+portable pipeline except the conic gradient's documented +-1 LSB (dev_fetch.cuh conic_row()); the reference's own
+JIT-vs-portable tests allow 2 for radial/conic (blend2d-testing/tests/bl_test_context_utilities.h:113-127).
+"""
+import numpy as np
+import pytest
+
+from tests import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+W0, H0 = 512, 600      # bl_bench canvas (config 0)
+
+
+def compare(ref, gpu, scene, W, H, fmt=1, seed=1, max_diff=0):
+    ri, _ = S.draw(ref, scene, W, H, fmt, seed)
+    gi, gc = S.draw(gpu, scene, W, H, fmt, seed)
+    n, d = S.channel_diff(ri.to_numpy(), gi.to_numpy())
+    gc.close()
+    assert d <= max_diff, f"{n} pixels differ, max channel diff {d}"
+    if max_diff == 0:
+        assert n == 0
+
+
+@pytest.mark.parametrize("kind", ["A", "U"])
+@pytest.mark.parametrize("size", [8, 64, 256])
+def test_bl_bench_rects(ref, gpu, kind, size):
+    compare(ref, gpu, S.rects(kind, 400, size, W0, H0), W0, H0)
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+@pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
+def test_rects_formats_ops(ref, gpu, fmt, op):
+    compare(ref, gpu, S.rects("U", 200, 40, 300, 200, op), 300, 200, fmt)
+
+
+@pytest.mark.parametrize("rule", [0, 1])
+@pytest.mark.parametrize("npts", [10, 40])
+def test_polygons(ref, gpu, rule, npts):
+    compare(ref, gpu, S.polygons(300, 128, npts, W0, H0, rule), W0, H0)
+
+
+@pytest.mark.parametrize("kind", ["quad", "cubic"])
+@pytest.mark.parametrize("rule", [0, 1])
+def test_curve_paths(ref, gpu, kind, rule):
+    compare(ref, gpu, S.curve_paths(kind, 200, W0, H0, rule), W0, H0)
+
+
+@pytest.mark.parametrize("style,tol", [("linear", 0), ("radial", 0), ("conic", 1)])
+@pytest.mark.parametrize("extend", [0, 1, 2])
+def test_gradients(ref, gpu, style, tol, extend):
+    compare(ref, gpu, S.polygons(150, 200, 10, W0, H0, 0, style, extend), W0, H0, max_diff=tol)
+    compare(ref, gpu, S.curve_paths("cubic", 60, W0, H0, 1, style, extend, alpha=0.6), W0, H0, max_diff=tol)
+
+
+@pytest.mark.parametrize("kind", ["rot", "round"])
+@pytest.mark.parametrize("quality", [0, 1])
+@pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
+def test_patterns(ref, gpu, kind, quality, op):
+    compare(ref, gpu, S.pattern_shapes(kind, 150, 96, W0, H0, quality, 1, op), W0, H0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("fmt", [1, 3])
+def test_mixed_fuzz(ref, gpu, seed, fmt):
+    compare(ref, gpu, S.mixed(250, 513, 257), 513, 257, fmt, seed, max_diff=1)
+
+
+def test_4k_config1_slice(ref, gpu):
+    """Config 1 at its real canvas size with a reduced shape count (the oracle needs seconds, not minutes)."""
+    W, H = 3840, 2160
+    compare(ref, gpu, S.curve_paths("quad", 40, W, H, 0, "linear"), W, H)
+    compare(ref, gpu, S.polygons(500, 256, 20, W, H, 1, "radial", 1), W, H)
