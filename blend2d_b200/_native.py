@@ -71,7 +71,8 @@ class BatchView(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pixels_composited", C.c_uint64), ("commands", C.c_uint64),
-                ("edges", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("edges", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("tile_kernel_ms", C.c_double), ("build_kernels_ms", C.c_double), ("tile_kernel_launches", C.c_uint64)]
 
 
 class GradientStop(C.Structure):
@@ -106,6 +107,7 @@ _SIGS = {
     "b2dgpu_batch_render": (_R, [_P, _P, _P]),
     "b2dgpu_sync": (_R, [_P]),
     "b2dgpu_get_stats": (_R, [_P, C.POINTER(Stats), C.c_int]),
+    "b2dgpu_set_profiling": (_R, [_P, C.c_int]),
     "b2dgpu_debug_build_edges": (_R, [_P, C.POINTER(BatchView), C.POINTER(Edge), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b2dgpu_last_error_message": (C.c_char_p, []),
     "b2dgpu_abi_version": (C.c_uint32, []),
@@ -141,6 +143,7 @@ _SIGS = {
     "b2d_context_target": (_P, [_P]),
     "b2d_context_peek_batch": (_R, [_P, C.POINTER(BatchView)]),
     "b2d_context_discard_batch": (_R, [_P]),
+    "b2d_scene_replay": (_R, [_P, _P, C.c_uint32, C.c_uint32]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -114,6 +114,32 @@ B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) 
   }
 }
 
+// d[i] = op(d[i], s[i], m[i]) for the pixels whose mask is non-zero; operator dispatch hoisted out of the loop.
+B2D_HD void composite4(uint32_t comp_op, uint32_t* d, const uint32_t* s, const uint32_t* m) {
+  switch (comp_op) {
+    case kOpSrcOver:
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_over(d[i], s[i], m[i]);
+      break;
+    case kOpSrcCopy:
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_copy(d[i], s[i], m[i]);
+      break;
+    case kOpPlus:
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_plus(d[i], s[i], m[i]);
+      break;
+    case kOpMultiply:
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_multiply(d[i], s[i], m[i]);
+      break;
+    default:
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_screen(d[i], s[i], m[i]);
+      break;
+  }
+}
+
 // Coverage accumulator -> 8-bit mask.  `cov` is the running u32 sum that starts at 256 << 9 on every scanline.
 // fillgeneric_p.h:381-387: m = min(abs((sar(cov, 9) & rule) - 256), 256) * alpha >> 8.
 B2D_HD uint32_t calc_mask(uint32_t cov, uint32_t fill_rule_mask, uint32_t alpha) {

@@ -64,33 +64,49 @@ struct TileSink {
   }
 };
 
-// Accumulates one edge into the tile whose top-left pixel is (tx0, ty0).  Edges entirely left of the tile only
-// contribute their signed y-extent per row (every scanline's cells sum to cover << 9): that goes to `left_acc`, one
-// register per row, which the caller reduces across threads before touching shared memory.  Returns true when the
-// edge wrote anything through `store`.
-template<typename Store>
-B2D_HD bool tile_accumulate_edge(b2dgpu_edge ed, int tx0, int ty0, Store& store, uint32_t* left_acc) {
-  uint32_t sign_bit = 0;
-  if (ed.y0 > ed.y1) { int t = ed.x0; ed.x0 = ed.x1; ed.x1 = t; t = ed.y0; ed.y0 = ed.y1; ed.y1 = t; sign_bit = 1; }
+// Relation of an edge to the tile whose top-left pixel is (tx0, ty0).
+enum : int {
+  kEdgeNone = 0,        // no contribution: other rows, or entirely right of the tile
+  kEdgeLeft = 1,        // entirely left: contributes only its signed y-extent per row to the backdrop
+  kEdgeStraddle = 2     // touches the tile's columns (or the column before them): needs the rasterizer
+};
+
+struct NormEdge { int x0, y0, x1, y1; uint32_t sign_bit; };
+
+// Edges are stored in their original direction; the rasterizer wants top -> bottom plus a sign bit.
+B2D_HD NormEdge normalize_edge(b2dgpu_edge ed) {
+  NormEdge n;
+  if (ed.y0 > ed.y1) { n.x0 = ed.x1; n.y0 = ed.y1; n.x1 = ed.x0; n.y1 = ed.y0; n.sign_bit = 1; }
+  else { n.x0 = ed.x0; n.y0 = ed.y0; n.x1 = ed.x1; n.y1 = ed.y1; n.sign_bit = 0; }
+  return n;
+}
+
+B2D_HD int tile_edge_class(const NormEdge& ed, int tx0, int ty0) {
   const int ey_first = ed.y0 >> 8, ey_last = (ed.y1 - 1) >> 8;
-  if (ey_last < ty0 || ey_first >= ty0 + kTileH) return false;
+  if (ey_last < ty0 || ey_first >= ty0 + kTileH) return kEdgeNone;
   const int cx_min = tmin(ed.x0, ed.x1) >> 8, cx_max = tmax(ed.x0, ed.x1) >> 8;
-  if (cx_min >= tx0 + kTileW) return false;                     // entirely right: contributes nothing here
+  if (cx_min >= tx0 + kTileW) return kEdgeNone;
+  return (cx_max + 1 < tx0) ? kEdgeLeft : kEdgeStraddle;
+}
 
-  if (cx_max + 1 < tx0) {
-    #pragma unroll
-    for (int r = 0; r < kTileH; r++) {
-      int yt = (ty0 + r) << 8;
-      int cov = tmin(ed.y1, yt + 256) - tmax(ed.y0, yt);
-      if (cov > 0) left_acc[r] += uint32_t(sign_bit ? -cov : cov) << 9;
-    }
-    return false;
+// Every scanline's cells of an edge sum to (cover << 9), cover = signed y-extent inside the row: that is all a tile
+// to the right of the edge needs.  One accumulator per tile row.
+B2D_HD void tile_left_cover(const NormEdge& ed, int ty0, uint32_t* left_acc) {
+  #pragma unroll
+  for (int r = 0; r < kTileH; r++) {
+    int yt = (ty0 + r) << 8;
+    int cov = tmin(ed.y1, yt + 256) - tmax(ed.y0, yt);
+    if (cov > 0) left_acc[r] += uint32_t(ed.sign_bit ? -cov : cov) << 9;
   }
+}
 
+// Rasterizes the tile's rows of a straddling edge through `store`.  Returns true when anything was written.
+template<typename Store>
+B2D_HD bool tile_rasterize_edge(const NormEdge& ed, int tx0, int ty0, Store& store) {
   EdgeState st;
-  if (!edge_prepare(st, ed.x0, ed.y0, ed.x1, ed.y1, sign_bit)) return false;
-  const int y_from = tmax(ey_first, ty0);
-  const int y_to = tmin(ey_last, ty0 + kTileH - 1);
+  if (!edge_prepare(st, ed.x0, ed.y0, ed.x1, ed.y1, ed.sign_bit)) return false;
+  const int y_from = tmax(ed.y0 >> 8, ty0);
+  const int y_to = tmin((ed.y1 - 1) >> 8, ty0 + kTileH - 1);
   edge_advance_to_y(st, y_from);
   TileSink<Store> sink(store, tx0);
   for (int y = y_from; y <= y_to; y++) {

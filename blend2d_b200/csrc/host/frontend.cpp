@@ -355,6 +355,7 @@ void make_lut64(uint64_t* d_ptr, uint32_t d_size, const Stop* s_ptr, size_t s_si
 // Objects
 // ---------------------------------------------------------------------------------------------------------------
 struct b2d_image {
+  int refs;
   int32_t w, h;
   uint32_t format;
   int bpp;
@@ -363,6 +364,7 @@ struct b2d_image {
 };
 
 struct b2d_gradient {
+  int refs;
   uint32_t type, extend_mode;
   double values[6];
   Matrix transform;
@@ -376,6 +378,7 @@ struct b2d_gradient {
 };
 
 struct b2d_pattern {
+  int refs;
   b2d_image* image;
   int32_t area[4];
   uint32_t extend_mode;
@@ -392,6 +395,7 @@ extern "C" b2dgpu_result b2d_image_create(int32_t w, int32_t h, uint32_t format,
   if (!bpp || w <= 0 || h <= 0 || w > 65535 || h > 65535) return B2DGPU_ERROR_INVALID_VALUE;
   b2d_image* img = new (std::nothrow) b2d_image();
   if (!img) return B2DGPU_ERROR_OUT_OF_MEMORY;
+  img->refs = 1;
   img->w = w; img->h = h; img->format = format; img->bpp = bpp; img->stride = intptr_t(w) * bpp;
   void* p = nullptr;
   if (posix_memalign(&p, 64, size_t(img->stride) * size_t(h) + 64) != 0) { delete img; return B2DGPU_ERROR_OUT_OF_MEMORY; }
@@ -403,6 +407,7 @@ extern "C" b2dgpu_result b2d_image_create(int32_t w, int32_t h, uint32_t format,
 
 extern "C" b2dgpu_result b2d_image_destroy(b2d_image* img) {
   if (!img) return B2DGPU_ERROR_INVALID_VALUE;
+  if (--img->refs > 0) return B2DGPU_SUCCESS;         // still retained by a pattern / queued command
   free(img->data);
   delete img;
   return B2DGPU_SUCCESS;
@@ -420,6 +425,7 @@ extern "C" b2dgpu_result b2d_gradient_create(uint32_t type, const double* values
   *out = nullptr;
   b2d_gradient* g = new (std::nothrow) b2d_gradient();
   if (!g) return B2DGPU_ERROR_OUT_OF_MEMORY;
+  g->refs = 1;
   g->type = type; g->extend_mode = extend_mode;
   size_t nv = type == B2D_GRADIENT_RADIAL ? 6 : 4;
   memset(g->values, 0, sizeof(g->values));
@@ -467,6 +473,7 @@ extern "C" b2dgpu_result b2d_gradient_create(uint32_t type, const double* values
 
 extern "C" b2dgpu_result b2d_gradient_destroy(b2d_gradient* g) {
   if (!g) return B2DGPU_ERROR_INVALID_VALUE;
+  if (--g->refs > 0) return B2DGPU_SUCCESS;
   delete g;
   return B2DGPU_SUCCESS;
 }
@@ -476,10 +483,12 @@ extern "C" b2dgpu_result b2d_pattern_create(b2d_image* image, const int32_t* are
   *out = nullptr;
   b2d_pattern* p = new (std::nothrow) b2d_pattern();
   if (!p) return B2DGPU_ERROR_OUT_OF_MEMORY;
+  p->refs = 1;
   p->image = image;
+  image->refs++;
   if (area) {
     memcpy(p->area, area, sizeof(p->area));
-    if (p->area[0] < 0 || p->area[1] < 0 || p->area[2] < 0 || p->area[3] < 0 || p->area[0] + p->area[2] > image->w || p->area[1] + p->area[3] > image->h) { delete p; return B2DGPU_ERROR_INVALID_VALUE; }
+    if (p->area[0] < 0 || p->area[1] < 0 || p->area[2] < 0 || p->area[3] < 0 || p->area[0] + p->area[2] > image->w || p->area[1] + p->area[3] > image->h) { image->refs--; delete p; return B2DGPU_ERROR_INVALID_VALUE; }
   }
   else { p->area[0] = 0; p->area[1] = 0; p->area[2] = image->w; p->area[3] = image->h; }
   p->extend_mode = extend_mode;
@@ -491,6 +500,8 @@ extern "C" b2dgpu_result b2d_pattern_create(b2d_image* image, const int32_t* are
 
 extern "C" b2dgpu_result b2d_pattern_destroy(b2d_pattern* p) {
   if (!p) return B2DGPU_ERROR_INVALID_VALUE;
+  if (--p->refs > 0) return B2DGPU_SUCCESS;
+  b2d_image_destroy(p->image);
   delete p;
   return B2DGPU_SUCCESS;
 }
@@ -842,6 +853,10 @@ struct b2d_context {
   std::vector<b2dgpu_segment> segs;
   std::vector<b2dgpu_geometry_state> states;
   bool state_valid;             // states.back() matches the current transform
+  // Style objects whose memory (LUTs, pixels) the queued FetchData still points to - released after the flush,
+  // like RenderFetchData's reference to its style (renderfetchdata_p.h:43, 181-184).
+  std::vector<b2d_gradient*> kept_gradients;
+  std::vector<b2d_pattern*> kept_patterns;
   bool dirty;                   // device canvas differs from the host image
 };
 
@@ -868,6 +883,17 @@ void update_alpha(b2d_context* c) {
   c->fill_alpha_i = uint32_t(round_to_int(c->global_alpha * 255.0 * c->fill_alpha));
 }
 
+void release_kept(b2d_context* c, bool keep_current) {
+  // The current fill style may still be used by the next batch: keep the most recent object of each kind.
+  b2d_gradient* cur_g = (keep_current && !c->kept_gradients.empty()) ? c->kept_gradients.back() : nullptr;
+  b2d_pattern* cur_p = (keep_current && !c->kept_patterns.empty()) ? c->kept_patterns.back() : nullptr;
+  for (b2d_gradient* g : c->kept_gradients) if (g != cur_g) b2d_gradient_destroy(g);
+  for (b2d_pattern* p : c->kept_patterns) if (p != cur_p) b2d_pattern_destroy(p);
+  c->kept_gradients.clear(); c->kept_patterns.clear();
+  if (cur_g) c->kept_gradients.push_back(cur_g);
+  if (cur_p) c->kept_patterns.push_back(cur_p);
+}
+
 b2dgpu_result flush_batch(b2d_context* c) {
   if (c->cmds.empty()) return B2DGPU_SUCCESS;
   if (c->record_only) return B2DGPU_ERROR_INVALID_STATE;
@@ -879,6 +905,7 @@ b2dgpu_result flush_batch(b2d_context* c) {
   c->state_valid = false;
   c->style.fetch_index = -1;
   c->dirty = true;
+  release_kept(c, true);
   if (r) c->error_flags |= 1;
   return r;
 }
@@ -1104,6 +1131,7 @@ extern "C" b2dgpu_result b2d_context_end(b2d_context* c) { return b2d_context_fl
 extern "C" b2dgpu_result b2d_context_destroy(b2d_context* c) {
   if (!c) return B2DGPU_ERROR_INVALID_VALUE;
   b2dgpu_result r = b2d_context_end(c);
+  release_kept(c, false);
   if (c->target) b2dgpu_target_destroy(c->target);
   if (c->own_rt) b2dgpu_runtime_destroy(c->rt);
   delete c;
@@ -1130,6 +1158,7 @@ extern "C" b2dgpu_result b2d_context_discard_batch(b2d_context* c) {
   if (!c) return B2DGPU_ERROR_INVALID_VALUE;
   c->cmds.clear(); c->fetch.clear(); c->vtx.clear(); c->segs.clear(); c->states.clear();
   c->state_valid = false; c->style.fetch_index = -1;
+  release_kept(c, true);
   return B2DGPU_SUCCESS;
 }
 
@@ -1218,6 +1247,8 @@ extern "C" b2dgpu_result b2d_context_set_fill_style_gradient(b2d_context* c, con
   if (g->type == B2D_GRADIENT_LINEAR) ft = init_linear_gradient(fd.gradient, g->values, g->extend_mode, quality, m);
   else if (g->type == B2D_GRADIENT_RADIAL) ft = init_radial_gradient(fd.gradient, g->values, g->extend_mode, quality, m);
   else ft = init_conic_gradient(fd.gradient, g->values, quality, m);
+  g->refs++;
+  c->kept_gradients.push_back(g);
   return set_non_solid_style(c, ft, g->format, fd);
 }
 
@@ -1232,6 +1263,8 @@ extern "C" b2dgpu_result b2d_context_set_fill_style_pattern(b2d_context* c, cons
   fd.pattern.src.stride = img->stride;
   fd.pattern.src.w = p->area[2]; fd.pattern.src.h = p->area[3];
   uint32_t ft = init_pattern_affine(fd.pattern, p->extend_mode, c->pattern_quality, uint32_t(img->bpp), m);
+  const_cast<b2d_pattern*>(p)->refs++;
+  c->kept_patterns.push_back(const_cast<b2d_pattern*>(p));
   return set_non_solid_style(c, ft, img->format, fd);
 }
 

@@ -260,13 +260,20 @@ struct SmemStore {
   __device__ __forceinline__ void add_carry(int row, uint32_t v) { atomicAdd(carry + row, v); }
 };
 
+// Per-command result of the classification phase.
+struct PreCmd {
+  uint32_t carry[kTileH];    // backdrop of each tile row from the edges entirely left of the tile
+  uint32_t straddlers;       // number of edges that need the rasterizer in this tile
+  uint32_t any_carry;        // OR of carry[]
+};
+
 template<int BPP>
-__global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
+__global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
   __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];
   __shared__ uint32_t s_carry[kTileH];
   __shared__ uint32_t s_list[kTileThreads];
+  __shared__ PreCmd s_pre[kTileThreads];
   __shared__ uint32_t s_wcount[kTileH];
-  __shared__ uint32_t s_any[4];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -277,6 +284,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
   const int ty0 = P.y_begin + tile_y * kTileH;          // absolute y of the tile's first row
   const int px = tx0 + lane * 4;
   const int py = ty0 + row;
+  const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
 
   // Load the destination once.
   uint8_t* dst_row = P.dst + size_t(py - P.y_begin) * P.dst_stride;
@@ -296,10 +304,6 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
   // Zero the coverage scratch.
   *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
   if (tid < kTileH) s_carry[tid] = 0;
-  if (tid < 4) s_any[tid] = 0;
-  __syncthreads();
-
-  uint32_t iter = 0;      // counts analytic commands processed by this CTA (indexes the rotating s_any flags)
 
   for (uint32_t base = 0; base < P.command_count; base += kTileThreads) {
     // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
       hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
     }
     uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+    __syncthreads();                                    // previous chunk is done with s_list / s_pre / s_wcount
     if (lane == 0) s_wcount[row] = __popc(ballot);
     __syncthreads();
     uint32_t wbase = 0, total = 0;
@@ -322,11 +327,46 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
     if (hit) s_list[wbase + __popc(ballot & ((1u << lane) - 1u))] = c;
     __syncthreads();
 
+    // ---- phase 1: classify every (command, edge) against the tile, one warp per command, no block barriers ----
+    for (uint32_t k = row; k < total; k += kTileH) {
+      const uint32_t ci = s_list[k];
+      const uint32_t type = P.commands[ci].type;
+      uint32_t left_acc[kTileH];
+      #pragma unroll
+      for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
+      uint32_t straddlers = 0;
+      if (type >= B2DGPU_CMD_FILL_ANALYTIC) {
+        const uint2 er = P.cmd_edges[ci];
+        for (uint32_t e = lane; e < er.y; e += 32) {
+          int4 ev = __ldg(edges + er.x + e);
+          b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
+          NormEdge ne = normalize_edge(raw);
+          int cls = tile_edge_class(ne, tx0, ty0);
+          if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
+          else if (cls == kEdgeStraddle) straddlers++;
+        }
+      }
+      uint32_t any = 0;
+      #pragma unroll
+      for (int r = 0; r < kTileH; r++) {
+        left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
+        any |= left_acc[r];
+      }
+      straddlers = __reduce_add_sync(0xFFFFFFFFu, straddlers);
+      if (lane == 0) {
+        #pragma unroll
+        for (int r = 0; r < kTileH; r++) s_pre[k].carry[r] = left_acc[r];
+        s_pre[k].straddlers = straddlers;
+        s_pre[k].any_carry = any;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: replay the commands in order ----
     for (uint32_t k = 0; k < total; k++) {
       const uint32_t ci = s_list[k];
       const b2dgpu_command& cmd = P.commands[ci];
       const uint32_t type = cmd.type;
-      const uint32_t sig = cmd.signature;
       const uint32_t alpha = cmd.alpha;
       uint32_t m[4] = { 0, 0, 0, 0 };
 
@@ -343,63 +383,56 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
         for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
       }
       else {
-        // ---- K2: accumulate cover/area cells of this command's edges that touch the tile ----
-        const uint2 er = P.cmd_edges[ci];
-        const uint32_t slot = iter & 3u;
-        iter++;
-        uint32_t touched = 0;
-        uint32_t left_acc[kTileH];
-        #pragma unroll
-        for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
-
-        SmemStore store{ &s_cells[0][0], s_carry };
-        for (uint32_t e = tid; e < er.y; e += kTileThreads) {
-          if (tile_accumulate_edge(P.edges[er.x + e], tx0, ty0, store, left_acc)) touched = 1;
+        const uint32_t straddlers = s_pre[k].straddlers;
+        if (!straddlers) {
+          // No edge inside the tile: coverage is constant along every row (FillAnalytic's CMask spans).
+          if (!s_pre[k].any_carry) continue;
+          const uint32_t mm = calc_mask((256u << 9) + s_pre[k].carry[row], cmd.fill_rule_mask, alpha);
+          m[0] = m[1] = m[2] = m[3] = mm;
         }
+        else {
+          // ---- K2: rasterize the straddling edges into the shared cells ----
+          const uint2 er = P.cmd_edges[ci];
+          SmemStore store{ &s_cells[0][0], s_carry };
+          for (uint32_t e = tid; e < er.y; e += kTileThreads) {
+            int4 ev = __ldg(edges + er.x + e);
+            b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
+            NormEdge ne = normalize_edge(raw);
+            if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle) tile_rasterize_edge(ne, tx0, ty0, store);
+          }
+          __syncthreads();                                            // A: cells complete
 
-        // Warp-aggregate the "entirely left" covers: one shared atomic per warp and row instead of one per edge.
-        #pragma unroll
-        for (int r = 0; r < kTileH; r++) {
-          uint32_t v = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
-          if (v && lane == 0) { atomicAdd(&s_carry[r], v); touched = 1; }
-        }
-        if (touched) s_any[slot] = 1;
-        __syncthreads();                                              // A: cells complete
-
-        if (tid == 0) s_any[(slot + 2) & 3u] = 0;
-        if (!s_any[slot]) continue;                                   // nothing of this command reaches the tile
-
-        // ---- K3 (mask part): prefix-scan the row's cells, re-zero them, derive 8-bit masks ----
-        uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
-        *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
-        const uint32_t carry = s_carry[row];
-        uint32_t s0 = cv.x, s1 = s0 + cv.y, s2 = s1 + cv.z, s3 = s2 + cv.w;
-        uint32_t inc = s3;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-          if (lane >= o) inc += t;
-        }
-        const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
-        const uint32_t rule = cmd.fill_rule_mask;
-        m[0] = calc_mask(cov_base + s0, rule, alpha);
-        m[1] = calc_mask(cov_base + s1, rule, alpha);
-        m[2] = calc_mask(cov_base + s2, rule, alpha);
-        m[3] = calc_mask(cov_base + s3, rule, alpha);
-        // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
-        {
-          const int4 bb = P.cmd_bbox_px[ci];
+          // ---- K3 (mask part): prefix-scan the row's cells, re-zero them, derive 8-bit masks ----
+          uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
+          *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
+          const uint32_t carry = s_carry[row] + s_pre[k].carry[row];
+          uint32_t s0 = cv.x, s1 = s0 + cv.y, s2 = s1 + cv.z, s3 = s2 + cv.w;
+          uint32_t inc = s3;
           #pragma unroll
-          for (int i = 0; i < 4; i++) if (px + i >= bb.z) m[i] = 0;
+          for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += t;
+          }
+          const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
+          const uint32_t rule = cmd.fill_rule_mask;
+          m[0] = calc_mask(cov_base + s0, rule, alpha);
+          m[1] = calc_mask(cov_base + s1, rule, alpha);
+          m[2] = calc_mask(cov_base + s2, rule, alpha);
+          m[3] = calc_mask(cov_base + s3, rule, alpha);
+          __syncwarp();
+          if (lane == 0) s_carry[row] = 0;
+          __syncthreads();                                            // B: cells re-zeroed before the next command
         }
-        __syncwarp();
-        if (lane == 0) s_carry[row] = 0;
-        __syncthreads();                                              // B: cells re-zeroed before the next command
+        // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
+        const int bx1 = P.cmd_bbox_px[ci].z;
+        #pragma unroll
+        for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
       }
 
       // ---- K3 (fetch + composite) ----
       if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
 
+      const uint32_t sig = cmd.signature;
       FetchEnv env;
       env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
       env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
@@ -407,23 +440,17 @@ __global__ void __launch_bounds__(kTileThreads) k_tile_render(TileParams P) {
       env.fd = P.fetch_data + cmd.fetch_index;
       env.bayer = P.bayer;
       env.origin_x = P.origin_x; env.origin_y = P.origin_y;
-      const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
 
-      RowCtx rc;
-      fetch_row_init(env, uint32_t(py), rc);
-
-      #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (m[i]) {
-          uint32_t s = fetch_pixel(env, rc, uint32_t(px + i), uint32_t(py));
-          if (BPP == 1) s = (s >> 24) * 0x01010101u;
-          d[i] = composite(comp_op, d[i], s, m[i]);
-          px_written++;
-        }
+      uint32_t s[4];
+      fetch4(env, uint32_t(px), uint32_t(py), m, s);
+      if (BPP == 1) {
+        #pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
       }
+      composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
+      px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
       dirty = true;
     }
-    __syncthreads();        // s_list is rewritten by the next chunk
   }
 
   if (dirty) {

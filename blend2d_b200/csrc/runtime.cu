@@ -106,6 +106,8 @@ struct b2dgpu_runtime {
   PinnedBuffer image_staging;
 
   b2dgpu_stats stats;
+  bool profiling;
+  std::vector<cudaEvent_t> prof_events;     // triples: start, after build kernels, after tile kernel
 };
 
 struct b2dgpu_target {
@@ -232,6 +234,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->own_stream = false;
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
+  rt->profiling = false;
   memset(&rt->stats, 0, sizeof(rt->stats));
 
   if (info && info->stream) rt->stream = (cudaStream_t)info->stream;
@@ -267,6 +270,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   if (rt->d_scalars) cudaFree(rt->d_scalars);
   if (rt->h_scalars) cudaFreeHost(rt->h_scalars);
   for (int i = 0; i < 2; i++) rt->staging[i].release();
+  for (cudaEvent_t e : rt->prof_events) cudaEventDestroy(e);
   rt->image_staging.release();
   rt->oneshot_block.release();
   rt->oneshot_edges.release();
@@ -291,11 +295,28 @@ extern "C" b2dgpu_result b2dgpu_get_stats(b2dgpu_runtime* rt, b2dgpu_stats* out,
   CU_TRY(cudaStreamSynchronize(rt->stream));
   memcpy(&px, rt->h_scalars + 8, 8);
   rt->stats.pixels_composited = px;
+  for (size_t i = 0; i + 2 < rt->prof_events.size(); i += 3) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, rt->prof_events[i], rt->prof_events[i + 1]);
+    cudaEventElapsedTime(&b, rt->prof_events[i + 1], rt->prof_events[i + 2]);
+    rt->stats.build_kernels_ms += a;
+    rt->stats.tile_kernel_ms += b;
+    rt->stats.tile_kernel_launches += 1;
+  }
+  for (cudaEvent_t e : rt->prof_events) cudaEventDestroy(e);
+  rt->prof_events.clear();
   *out = rt->stats;
   if (reset) {
     memset(&rt->stats, 0, sizeof(rt->stats));
     CU_TRY(cudaMemsetAsync(rt->d_pixel_counter, 0, 8, rt->stream));
   }
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled) {
+  if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_set_profiling: invalid runtime");
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  rt->profiling = enabled != 0;
   return B2DGPU_SUCCESS;
 }
 
@@ -587,6 +608,12 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
   uint32_t* d_seg_counts = reinterpret_cast<uint32_t*>(blk + L.seg_counts);
   uint32_t* d_seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
 
+  cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+  if (rt->profiling) {
+    for (int i = 0; i < 3; i++) CU_TRY(cudaEventCreate(&ev[i]));
+    CU_TRY(cudaEventRecord(ev[0], s));
+  }
+
   launches += launch_init_bbox(d_bbox_fixed, in.command_count, s);
 
   BuildParams B;
@@ -672,7 +699,12 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
   T.origin_x = in.origin_x;
   T.origin_y = in.origin_y;
   T.pixel_counter = rt->d_pixel_counter;
+  if (rt->profiling) CU_TRY(cudaEventRecord(ev[1], s));
   launches += launch_tile_render(T, t->bpp, s);
+  if (rt->profiling) {
+    CU_TRY(cudaEventRecord(ev[2], s));
+    for (int i = 0; i < 3; i++) rt->prof_events.push_back(ev[i]);
+  }
 
   CU_TRY(cudaGetLastError());
   rt->stats.kernel_launches += uint64_t(launches);

@@ -107,6 +107,10 @@ B2DGPU_API b2dgpu_result b2d_context_peek_batch(b2d_context* ctx, b2dgpu_batch_v
 /* Drops the queued commands without rendering them. */
 B2DGPU_API b2dgpu_result b2d_context_discard_batch(b2d_context* ctx);
 
+/* Replays fills [first, first + count) of a flat scene description (include/b2d_scene.h) through the calls above. */
+struct b2d_scene;
+B2DGPU_API b2dgpu_result b2d_scene_replay(b2d_context* ctx, const struct b2d_scene* scene, uint32_t first, uint32_t count);
+
 #ifdef __cplusplus
 }
 #endif

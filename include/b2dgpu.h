@@ -342,8 +342,14 @@ typedef struct b2dgpu_stats {
   uint64_t commands;                          /* commands rendered                                               */
   uint64_t edges;                             /* edges produced by the edge builder + supplied                   */
   uint64_t h2d_bytes, d2h_bytes;
+  /* Device time of OUR kernels, measured with CUDA events on the runtime stream while profiling is enabled
+   * (b2dgpu_set_profiling): the tile compositor (K2+K3) and everything before it (K1 edge builder, scan, finalize). */
+  double tile_kernel_ms, build_kernels_ms;
+  uint64_t tile_kernel_launches;
 } b2dgpu_stats;
 B2DGPU_API b2dgpu_result b2dgpu_get_stats(b2dgpu_runtime* rt, b2dgpu_stats* out, int reset);
+/* Enables (1) / disables (0) per-kernel CUDA-event timing; adds two event records per phase and render. */
+B2DGPU_API b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled);
 
 /* Debug/KAT access used by the parity tests: runs only the edge builder and returns the flattened edges. */
 B2DGPU_API b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dgpu_batch_view* batch,

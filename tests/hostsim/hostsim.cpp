@@ -129,12 +129,25 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
         for (int r = 0; r < kTileH; r++) for (int x = 0; x < kTileW; x++) masks[r][x] = box_u_mask(bu, tx0 + x, ty0 + r);
       }
       else {
+        // Phase 1 (classification): backdrop from the edges entirely left of the tile, and whether any edge straddles.
         uint32_t left_acc[kTileH];
         memset(left_acc, 0, sizeof(left_acc));
         bool touched = false;
-        for (uint32_t e = 0; e < e_count[c]; e++)
-          touched |= tile_accumulate_edge(edges[e_begin[c] + e], tx0, ty0, store, left_acc);
+        uint32_t straddlers = 0;
+        for (uint32_t e = 0; e < e_count[c]; e++) {
+          NormEdge ne = normalize_edge(edges[e_begin[c] + e]);
+          int cls = tile_edge_class(ne, tx0, ty0);
+          if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
+          else if (cls == kEdgeStraddle) straddlers++;
+        }
         for (int r = 0; r < kTileH; r++) if (left_acc[r]) { store.carry[r] += left_acc[r]; touched = true; }
+        // Phase 2: only straddling edges go through the rasterizer.
+        if (straddlers) {
+          for (uint32_t e = 0; e < e_count[c]; e++) {
+            NormEdge ne = normalize_edge(edges[e_begin[c] + e]);
+            if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle) touched |= tile_rasterize_edge(ne, tx0, ty0, store);
+          }
+        }
         if (!touched) continue;
         for (int r = 0; r < kTileH; r++) {
           uint32_t cov = (256u << 9) + store.carry[r];
