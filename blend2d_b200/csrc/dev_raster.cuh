@@ -52,12 +52,30 @@ B2D_HD void err_step_u(uint32_t& acc, int& iter, int step, int correction) {
   iter += mask & correction;
 }
 
+// q = a / b, r = a % b for a < 2^64; takes the 32-bit divider whenever the dividend fits (always the case for
+// canvases up to 65535 px: coordinates are below 2^24 in 24.8 fixed point).
+B2D_HD void udivmod64(uint64_t a, uint32_t b, uint32_t& q, uint32_t& r) {
+  if ((a >> 32) == 0) {
+    uint32_t a32 = uint32_t(a);
+    q = a32 / b;
+    r = a32 - q * b;
+  }
+  else {
+    uint64_t q64 = a / b;
+    q = uint32_t(q64);
+    r = uint32_t(a - q64 * b);
+  }
+}
+
 // `count` steps at once (AnalyticUtils::acc_err_multi_step, :84-100).
 B2D_HD void err_multi_step(int& acc, int& iter, int step, int correction, int count) {
   int64_t i = int64_t(uint32_t(iter));
   i -= int64_t(uint64_t(uint32_t(step)) * uint32_t(count));
   if (i < 0) {
-    int n = int((uint64_t(-i) + uint32_t(correction) - 1u) / uint64_t(uint32_t(correction)));
+    uint64_t num = uint64_t(-i) + uint32_t(correction) - 1u;
+    uint32_t q, r;
+    udivmod64(num, uint32_t(correction), q, r);
+    int n = int(q);
     acc += n;
     i += int64_t(correction) * n;
   }
@@ -99,10 +117,9 @@ B2D_HD bool edge_prepare(EdgeState& s, int x0, int y0, int x1, int y1, uint32_t 
   uint64_t x_base = uint64_t(uint32_t(s.dx)) * kA8Scale;
   uint64_t y_base = uint64_t(uint32_t(s.dy)) * kA8Scale;
 
-  s.x_lift = int(x_base / uint32_t(s.dy));
-  s.x_rem  = int(x_base % uint32_t(s.dy));
-  s.y_lift = int(y_base / uint32_t(s.dx));
-  s.y_rem  = int(y_base % uint32_t(s.dx));
+  uint32_t q, r;
+  udivmod64(x_base, uint32_t(s.dy), q, r); s.x_lift = int(q); s.x_rem = int(r);
+  udivmod64(y_base, uint32_t(s.dx), q, r); s.y_lift = int(q); s.y_rem = int(r);
 
   s.x_dlt = s.dx;
   s.y_dlt = s.dy;
@@ -111,15 +128,17 @@ B2D_HD bool edge_prepare(EdgeState& s, int x0, int y0, int x1, int y1, uint32_t 
 
   if (s.ey0 != s.ey1) {
     uint64_t p = uint64_t(uint32_t(kA8Scale - s.fy0)) * uint32_t(s.dx);
-    s.x_dlt  = int(p / uint32_t(s.dy));
-    s.x_err -= int(p % uint32_t(s.dy));
+    udivmod64(p, uint32_t(s.dy), q, r);
+    s.x_dlt  = int(q);
+    s.x_err -= int(r);
     err_step(s.x_dlt, s.x_err, 0, s.dy);
   }
 
   if (s.ex0 != s.ex1) {
     uint64_t p = uint64_t((s.flags & kEdgeRightToLeft) ? uint32_t(s.fx0) : uint32_t(kA8Scale - s.fx0)) * uint32_t(s.dy);
-    s.y_dlt  = int(p / uint32_t(s.dx));
-    s.y_err -= int(p % uint32_t(s.dx));
+    udivmod64(p, uint32_t(s.dx), q, r);
+    s.y_dlt  = int(q);
+    s.y_err -= int(r);
     err_step(s.y_dlt, s.y_err, 0, s.dx);
   }
 

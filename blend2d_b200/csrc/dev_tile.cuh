@@ -116,6 +116,17 @@ B2D_HD bool tile_rasterize_edge(const NormEdge& ed, int tx0, int ty0, Store& sto
   return sink.touched != 0;
 }
 
+// One scanline `y` (absolute, inside the edge's y-range) of an edge: prepare, closed-form jump, one step.  This is the
+// unit of work of a GPU lane - the reference's own unit test pins that jumping with advanceToY() equals stepping
+// (raster/analyticrasterizer_test.cpp:34-157).
+template<typename Sink>
+B2D_HD void tile_rasterize_edge_row(const NormEdge& ed, int y, Sink& sink) {
+  EdgeState st;
+  if (!edge_prepare(st, ed.x0, ed.y0, ed.x1, ed.y1, ed.sign_bit)) return;
+  edge_advance_to_y(st, y);
+  edge_step_scanline(st, sink);
+}
+
 // Pixel bounding box [x0,x1) x [y0,y1) of a command, clipped to the rows [y_begin, y_end) of a `width`-wide target;
 // all zeros when the command cannot touch it.  `bb_fixed` = 24.8 bounds of an analytic command's edges.
 struct CmdBox { int x0, y0, x1, y1; };

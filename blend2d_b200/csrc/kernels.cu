@@ -252,27 +252,60 @@ __global__ void k_finalize_commands(FinalizeParams P) {
 // K2 + K3 - tile compositor
 // =================================================================================================================
 
-// Shared-memory cell store of one tile (u32 wrap-around adds: order independent).
-struct SmemStore {
-  uint32_t* cells;      // kTileH x kTileW
-  uint32_t* carry;      // kTileH
-  __device__ __forceinline__ void add_cell(int row, int rel, uint32_t v) { atomicAdd(cells + row * kTileW + rel, v); }
-  __device__ __forceinline__ void add_carry(int row, uint32_t v) { atomicAdd(carry + row, v); }
+// Shared-memory cell row used by the slow path (u32 wrap-around adds: order independent).
+struct SmemRowStore {
+  uint32_t* cells;      // kTileW cells of ONE row (warp private)
+  uint32_t* carry;      // that row's backdrop accumulator
+  __device__ __forceinline__ void add_cell(int, int rel, uint32_t v) { atomicAdd(cells + rel, v); }
+  __device__ __forceinline__ void add_carry(int, uint32_t v) { atomicAdd(carry, v); }
 };
 
-// Per-command result of the classification phase.
+// Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
+enum : int { kSubChunk = 64, kEntCap = 8 };
+enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
+
 struct PreCmd {
-  uint32_t carry[kTileH];    // backdrop of each tile row from the edges entirely left of the tile
-  uint32_t straddlers;       // number of edges that need the rasterizer in this tile
-  uint32_t any_carry;        // OR of carry[]
+  uint32_t carry_left[kTileH];      // backdrop per tile row from the edges entirely left of the tile
+  uint32_t carry_st[kTileH];        // backdrop per tile row from straddling edges (their cells left of the tile)
+  uint32_t nent[kTileH];            // number of cell entries appended per row (may exceed kEntCap: overflow)
+  uint32_t flags;
+  uint32_t _pad;
+  uint2 ent[kTileH][kEntCap];       // (cell index relative to the tile, value to add)
 };
+
+// Coverage sink of phase 1: the few cells a straddling edge touches in a row are appended to that row's entry list.
+struct EntrySink {
+  PreCmd* pre;
+  int tx0;
+  int row;
+  __device__ __forceinline__ void put(int x, uint32_t v) {
+    if (!v) return;
+    int rel = x - tx0;
+    if (rel < 0) atomicAdd(&pre->carry_st[row], v);
+    else if (rel < kTileW) {
+      uint32_t idx = atomicAdd(&pre->nent[row], 1u);
+      if (idx < uint32_t(kEntCap)) pre->ent[row][idx] = make_uint2(uint32_t(rel), v);
+      else atomicOr(&pre->flags, kPreOverflow);
+    }
+  }
+  __device__ __forceinline__ void merge(int x, uint32_t cover, uint32_t area) {
+    put(x, (cover << 9) - area);
+    put(x + 1, area);
+  }
+};
+
+__device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, uint32_t index) {
+  int4 ev = __ldg(edges + index);
+  b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
+  return normalize_edge(raw);
+}
 
 template<int BPP>
 __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
-  __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];
+  __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
   __shared__ uint32_t s_carry[kTileH];
   __shared__ uint32_t s_list[kTileThreads];
-  __shared__ PreCmd s_pre[kTileThreads];
+  __shared__ __align__(16) PreCmd s_pre[kSubChunk];
   __shared__ uint32_t s_wcount[kTileH];
 
   const int tid = threadIdx.x;
@@ -301,10 +334,6 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
   bool dirty = false;
   uint32_t px_written = 0;
 
-  // Zero the coverage scratch.
-  *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
-  if (tid < kTileH) s_carry[tid] = 0;
-
   for (uint32_t base = 0; base < P.command_count; base += kTileThreads) {
     // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
     uint32_t c = base + tid;
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
       hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
     }
     uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-    __syncthreads();                                    // previous chunk is done with s_list / s_pre / s_wcount
+    __syncthreads();                                    // the previous chunk is done with s_list / s_wcount
     if (lane == 0) s_wcount[row] = __popc(ballot);
     __syncthreads();
     uint32_t wbase = 0, total = 0;
@@ -325,131 +354,180 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
       total += cnt;
     }
     if (hit) s_list[wbase + __popc(ballot & ((1u << lane) - 1u))] = c;
-    __syncthreads();
 
-    // ---- phase 1: classify every (command, edge) against the tile, one warp per command, no block barriers ----
-    for (uint32_t k = row; k < total; k += kTileH) {
-      const uint32_t ci = s_list[k];
-      const uint32_t type = P.commands[ci].type;
-      uint32_t left_acc[kTileH];
-      #pragma unroll
-      for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
-      uint32_t straddlers = 0;
-      if (type >= B2DGPU_CMD_FILL_ANALYTIC) {
-        const uint2 er = P.cmd_edges[ci];
-        for (uint32_t e = lane; e < er.y; e += 32) {
-          int4 ev = __ldg(edges + er.x + e);
-          b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
-          NormEdge ne = normalize_edge(raw);
-          int cls = tile_edge_class(ne, tx0, ty0);
-          if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
-          else if (cls == kEdgeStraddle) straddlers++;
-        }
-      }
-      uint32_t any = 0;
-      #pragma unroll
-      for (int r = 0; r < kTileH; r++) {
-        left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
-        any |= left_acc[r];
-      }
-      straddlers = __reduce_add_sync(0xFFFFFFFFu, straddlers);
-      if (lane == 0) {
+    for (uint32_t sub = 0; sub < total; sub += kSubChunk) {
+      const uint32_t sub_n = min(uint32_t(kSubChunk), total - sub);
+      __syncthreads();                                  // s_list written / previous sub-chunk's s_pre consumed
+
+      // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
+      //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
+      for (uint32_t k = row; k < sub_n; k += kTileH) {
+        const uint32_t ci = s_list[sub + k];
+        PreCmd* pre = &s_pre[k];
+        if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; }
+        if (lane == 0) pre->flags = 0;
+        __syncwarp();
+
+        uint32_t left_acc[kTileH];
         #pragma unroll
-        for (int r = 0; r < kTileH; r++) s_pre[k].carry[r] = left_acc[r];
-        s_pre[k].straddlers = straddlers;
-        s_pre[k].any_carry = any;
-      }
-    }
-    __syncthreads();
+        for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
+        uint32_t nstr = 0;
 
-    // ---- phase 2: replay the commands in order ----
-    for (uint32_t k = 0; k < total; k++) {
-      const uint32_t ci = s_list[k];
-      const b2dgpu_command& cmd = P.commands[ci];
-      const uint32_t type = cmd.type;
-      const uint32_t alpha = cmd.alpha;
-      uint32_t m[4] = { 0, 0, 0, 0 };
-
-      if (type == B2DGPU_CMD_FILL_BOX_A) {
-        // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
-        if (py >= cmd.box[1] && py < cmd.box[3]) {
+        if (P.commands[ci].type >= B2DGPU_CMD_FILL_ANALYTIC) {
+          const uint2 er = P.cmd_edges[ci];
+          EntrySink sink; sink.pre = pre; sink.tx0 = tx0; sink.row = 0;
+          for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            int cls = kEdgeNone;
+            if (e < er.y) {
+              NormEdge ne = load_edge(edges, er.x + e);
+              cls = tile_edge_class(ne, tx0, ty0);
+              if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
+            }
+            uint32_t sb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle);
+            nstr += __popc(sb);
+            while (sb) {
+              // Up to 4 straddling edges x 8 rows = 32 (edge, row) items, one per lane.
+              int src = -1;
+              #pragma unroll
+              for (int q = 0; q < 4; q++) {
+                int bit = sb ? (__ffs(sb) - 1) : -1;
+                if (sb) sb &= sb - 1;
+                if ((lane >> 3) == q) src = bit;
+              }
+              if (src >= 0) {
+                NormEdge ne = load_edge(edges, er.x + e0 + uint32_t(src));
+                const int r = lane & 7, y = ty0 + r;
+                if (y >= (ne.y0 >> 8) && y <= ((ne.y1 - 1) >> 8)) {
+                  sink.row = r;
+                  tile_rasterize_edge_row(ne, y, sink);
+                }
+              }
+            }
+          }
+        }
+        #pragma unroll
+        for (int r = 0; r < kTileH; r++) left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
+        if (lane == 0) {
           #pragma unroll
-          for (int i = 0; i < 4; i++) m[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
+          for (int r = 0; r < kTileH; r++) pre->carry_left[r] = left_acc[r];
+          if (nstr) atomicOr(&pre->flags, kPreStraddle);
         }
       }
-      else if (type == B2DGPU_CMD_FILL_BOX_U) {
-        BoxUParams bu = box_u_setup(cmd.box, alpha);
-        #pragma unroll
-        for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
-      }
-      else {
-        const uint32_t straddlers = s_pre[k].straddlers;
-        if (!straddlers) {
-          // No edge inside the tile: coverage is constant along every row (FillAnalytic's CMask spans).
-          if (!s_pre[k].any_carry) continue;
-          const uint32_t mm = calc_mask((256u << 9) + s_pre[k].carry[row], cmd.fill_rule_mask, alpha);
-          m[0] = m[1] = m[2] = m[3] = mm;
+      __syncthreads();
+
+      // ---- phase 2 (K3): every warp replays the commands in order for ITS row; warps never wait for each other ----
+      for (uint32_t k = 0; k < sub_n; k++) {
+        const uint32_t ci = s_list[sub + k];
+        const b2dgpu_command& cmd = P.commands[ci];
+        const uint32_t type = cmd.type;
+        const uint32_t alpha = cmd.alpha;
+        uint32_t m[4] = { 0, 0, 0, 0 };
+
+        if (type == B2DGPU_CMD_FILL_BOX_A) {
+          // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
+          if (py >= cmd.box[1] && py < cmd.box[3]) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) m[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
+          }
+        }
+        else if (type == B2DGPU_CMD_FILL_BOX_U) {
+          BoxUParams bu = box_u_setup(cmd.box, alpha);
+          #pragma unroll
+          for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
         }
         else {
-          // ---- K2: rasterize the straddling edges into the shared cells ----
-          const uint2 er = P.cmd_edges[ci];
-          SmemStore store{ &s_cells[0][0], s_carry };
-          for (uint32_t e = tid; e < er.y; e += kTileThreads) {
-            int4 ev = __ldg(edges + er.x + e);
-            b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
-            NormEdge ne = normalize_edge(raw);
-            if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle) tile_rasterize_edge(ne, tx0, ty0, store);
+          const PreCmd& pre = s_pre[k];
+          const uint32_t flags = pre.flags;
+          uint32_t carry = pre.carry_left[row];
+          if (!(flags & kPreStraddle)) {
+            // No edge inside the tile: coverage is constant along the row (FillAnalytic's CMask spans).
+            if (!carry) continue;
+            const uint32_t mm = calc_mask((256u << 9) + carry, cmd.fill_rule_mask, alpha);
+            m[0] = m[1] = m[2] = m[3] = mm;
           }
-          __syncthreads();                                            // A: cells complete
-
-          // ---- K3 (mask part): prefix-scan the row's cells, re-zero them, derive 8-bit masks ----
-          uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
-          *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
-          const uint32_t carry = s_carry[row] + s_pre[k].carry[row];
-          uint32_t s0 = cv.x, s1 = s0 + cv.y, s2 = s1 + cv.z, s3 = s2 + cv.w;
-          uint32_t inc = s3;
+          else {
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            const uint32_t n = pre.nent[row];
+            if (!(flags & kPreOverflow) || n <= uint32_t(kEntCap)) {
+              // Fast path: the row's cells are the handful of entries phase 1 recorded.
+              carry += pre.carry_st[row];
+              #pragma unroll
+              for (int j = 0; j < kEntCap; j++) {
+                if (uint32_t(j) < n) {
+                  const uint2 en = pre.ent[row][j];
+                  if (int(en.x >> 2) == lane) {
+                    const uint32_t sel = en.x & 3u;
+                    c0 += sel == 0 ? en.y : 0u; c1 += sel == 1 ? en.y : 0u;
+                    c2 += sel == 2 ? en.y : 0u; c3 += sel == 3 ? en.y : 0u;
+                  }
+                }
+              }
+            }
+            else {
+              // Slow path (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
+              // rasterizes its own row into its private shared-memory cell row.
+              *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
+              if (lane == 0) s_carry[row] = 0;
+              __syncwarp();
+              const uint2 er = P.cmd_edges[ci];
+              SmemRowStore store{ &s_cells[row][0], &s_carry[row] };
+              TileSink<SmemRowStore> sink(store, tx0);
+              sink.row = row;
+              for (uint32_t e = lane; e < er.y; e += 32) {
+                NormEdge ne = load_edge(edges, er.x + e);
+                if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
+                  tile_rasterize_edge_row(ne, py, sink);
+              }
+              __syncwarp();
+              uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
+              c0 = cv.x; c1 = cv.y; c2 = cv.z; c3 = cv.w;
+              carry += s_carry[row];
+              __syncwarp();
+            }
+            // Prefix-sum of the row's cells (fillgeneric_p.h:285-297) and 8-bit masks.
+            uint32_t s0 = c0, s1 = s0 + c1, s2 = s1 + c2, s3 = s2 + c3;
+            uint32_t inc = s3;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+              if (lane >= o) inc += t;
+            }
+            const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
+            const uint32_t rule = cmd.fill_rule_mask;
+            m[0] = calc_mask(cov_base + s0, rule, alpha);
+            m[1] = calc_mask(cov_base + s1, rule, alpha);
+            m[2] = calc_mask(cov_base + s2, rule, alpha);
+            m[3] = calc_mask(cov_base + s3, rule, alpha);
+          }
+          // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
+          const int bx1 = P.cmd_bbox_px[ci].z;
           #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += t;
-          }
-          const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
-          const uint32_t rule = cmd.fill_rule_mask;
-          m[0] = calc_mask(cov_base + s0, rule, alpha);
-          m[1] = calc_mask(cov_base + s1, rule, alpha);
-          m[2] = calc_mask(cov_base + s2, rule, alpha);
-          m[3] = calc_mask(cov_base + s3, rule, alpha);
-          __syncwarp();
-          if (lane == 0) s_carry[row] = 0;
-          __syncthreads();                                            // B: cells re-zeroed before the next command
+          for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
         }
-        // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
-        const int bx1 = P.cmd_bbox_px[ci].z;
-        #pragma unroll
-        for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
+
+        // ---- fetch + composite ----
+        if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
+
+        const uint32_t sig = cmd.signature;
+        FetchEnv env;
+        env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
+        env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
+        env.solid = cmd.solid_prgb32;
+        env.fd = P.fetch_data + cmd.fetch_index;
+        env.bayer = P.bayer;
+        env.origin_x = P.origin_x; env.origin_y = P.origin_y;
+
+        uint32_t s[4];
+        fetch4(env, uint32_t(px), uint32_t(py), m, s);
+        if (BPP == 1) {
+          #pragma unroll
+          for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+        }
+        composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
+        px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
+        dirty = true;
       }
-
-      // ---- K3 (fetch + composite) ----
-      if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
-
-      const uint32_t sig = cmd.signature;
-      FetchEnv env;
-      env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
-      env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
-      env.solid = cmd.solid_prgb32;
-      env.fd = P.fetch_data + cmd.fetch_index;
-      env.bayer = P.bayer;
-      env.origin_x = P.origin_x; env.origin_y = P.origin_y;
-
-      uint32_t s[4];
-      fetch4(env, uint32_t(px), uint32_t(py), m, s);
-      if (BPP == 1) {
-        #pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
-      }
-      composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
-      px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
-      dirty = true;
     }
   }
 

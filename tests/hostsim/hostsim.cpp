@@ -145,7 +145,12 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
         if (straddlers) {
           for (uint32_t e = 0; e < e_count[c]; e++) {
             NormEdge ne = normalize_edge(edges[e_begin[c] + e]);
-            if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle) touched |= tile_rasterize_edge(ne, tx0, ty0, store);
+            if (tile_edge_class(ne, tx0, ty0) != kEdgeStraddle) continue;
+            // One (edge, row) item at a time, exactly like a GPU lane: prepare + advance_to_y + one step.
+            TileSink<HostStore> sink(store, tx0);
+            const int y_from = tmax(ne.y0 >> 8, ty0), y_to = tmin((ne.y1 - 1) >> 8, ty0 + kTileH - 1);
+            for (int y = y_from; y <= y_to; y++) { sink.row = y - ty0; tile_rasterize_edge_row(ne, y, sink); }
+            touched |= sink.touched != 0;
           }
         }
         if (!touched) continue;
