@@ -320,6 +320,11 @@ def run_gpu(args):
     st2 = {"h2d_bytes": e2e_acc["h2d"], "d2h_bytes": e2e_acc["d2h"]}
     checksum = int(np.bitwise_xor.reduce(img.pixels().ravel()))
 
+    # ---- the bandwidth-bound case: full-canvas SrcOver fills, one command per launch (8 B per pixel) ----
+    full = None
+    if rank == 0 and not args.no_full_canvas:
+        full = measure_full_canvas(G, N, rt, lib, torch, stream, flush_buf)
+
     # ---- reduce over ranks: time = max, work = sum ----
     if world > 1:
         t = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -373,6 +378,10 @@ def run_gpu(args):
                                  "algorithmic bytes (8 B per composited pixel) exceed DRAM traffic by the overdraw factor"},
             "clocks": clocks,
             "pixels_per_step": px_per_step, "canvas_checksum": checksum,
+            "roofline_full_canvas": None if full is None else {
+                k: {"bound": "hbm", "kernel": "k_box_stream<4>", "achieved": v["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": v["gbs"] / peak, "kernel_ms": v["ms"], "algorithmic_bytes_per_launch": v["bytes"],
+                    "workload": v["what"]} for k, v in full.items()},
         }
         if world == 1 and not args.no_cpu_baseline:
             sample = min(n_fills, args.cpu_sample)
@@ -391,6 +400,38 @@ def run_gpu(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_full_canvas(G, N, rt, lib, torch, stream, flush_buf):
+    """One translucent full-canvas SrcOver fill per launch: reads 4 B and writes 4 B per pixel."""
+    out = {}
+    for name, (W, H) in (("4k", (3840, 2160)), ("16k", (16384, 16384))):
+        img = G.Image(W, H, G.FORMAT_PRGB32)
+        rec = G.Context(img, record_only=True)
+        rec.set_fill_style(0x80336699)
+        rec.fill_all()
+        batch = G.ResidentBatch(rt._h, rec.peek_batch())
+        tgt = C.c_void_p()
+        N.check(lib.b2dgpu_target_create(rt._h, W, H, G.FORMAT_PRGB32, C.byref(tgt)), "target_create")
+        for _ in range(3):
+            batch.render(tgt)
+        torch.cuda.synchronize()
+        rt.stats(reset=True)
+        N.check(lib.b2dgpu_set_profiling(rt._h, 1), "set_profiling")
+        reps = 10
+        for _ in range(reps):
+            flush_buf.fill_(7)
+            batch.render(tgt)
+        torch.cuda.synchronize()
+        st = rt.stats(reset=True)
+        N.check(lib.b2dgpu_set_profiling(rt._h, 0), "set_profiling")
+        ms = st["tile_kernel_ms"] / reps
+        nbytes = W * H * 8.0
+        out[name] = {"ms": ms, "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9,
+                     "what": f"full-canvas SrcOver solid fill (alpha 0.5) of a {W}x{H} PRGB32 canvas, L2 flushed between launches"}
+        batch.close()
+        N.check(lib.b2dgpu_target_destroy(tgt), "target_destroy")
+    return out
 
 
 def run_reference_arm(args):
@@ -430,6 +471,7 @@ def main():
     ap.add_argument("--height", type=int, default=H4K)
     ap.add_argument("--cpu-sample", type=int, default=400, help="fills in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-canvas", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

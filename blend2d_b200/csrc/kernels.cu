@@ -269,7 +269,7 @@ struct PreCmd {
   uint32_t carry_st[kTileH];        // backdrop per tile row from straddling edges (their cells left of the tile)
   uint32_t nent[kTileH];            // number of cell entries appended per row (may exceed kEntCap: overflow)
   uint32_t flags;
-  uint32_t _pad;
+  uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
   uint2 ent[kTileH][kEntCap];       // (cell index relative to the tile, value to add)
 };
 
@@ -372,8 +372,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
         #pragma unroll
         for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
         uint32_t nstr = 0;
+        const bool is_box = P.commands[ci].type < B2DGPU_CMD_FILL_ANALYTIC;
 
-        if (P.commands[ci].type >= B2DGPU_CMD_FILL_ANALYTIC) {
+        if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
           EntrySink sink; sink.pre = pre; sink.tx0 = tx0; sink.row = 0;
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
@@ -406,18 +407,26 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
             }
           }
         }
+        uint32_t any_left = 0;
         #pragma unroll
-        for (int r = 0; r < kTileH; r++) left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]);
+        for (int r = 0; r < kTileH; r++) { left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]); any_left |= left_acc[r]; }
         if (lane == 0) {
           #pragma unroll
           for (int r = 0; r < kTileH; r++) pre->carry_left[r] = left_acc[r];
           if (nstr) atomicOr(&pre->flags, kPreStraddle);
+          pre->active = (is_box || nstr || any_left) ? 1u : 0u;
         }
       }
       __syncthreads();
 
       // ---- phase 2 (K3): every warp replays the commands in order for ITS row; warps never wait for each other ----
-      for (uint32_t k = 0; k < sub_n; k++) {
+      // Commands that leave the tile untouched (bounding box hit only) are compacted away first.
+      uint32_t act_lo = __ballot_sync(0xFFFFFFFFu, uint32_t(lane) < sub_n && s_pre[lane].active != 0);
+      uint32_t act_hi = __ballot_sync(0xFFFFFFFFu, uint32_t(lane + 32) < sub_n && s_pre[lane + 32].active != 0);
+      while (act_lo | act_hi) {
+        uint32_t k;
+        if (act_lo) { k = uint32_t(__ffs(act_lo) - 1); act_lo &= act_lo - 1; }
+        else { k = 32u + uint32_t(__ffs(act_hi) - 1); act_hi &= act_hi - 1; }
         const uint32_t ci = s_list[sub + k];
         const b2dgpu_command& cmd = P.commands[ci];
         const uint32_t type = cmd.type;
@@ -452,16 +461,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
             if (!(flags & kPreOverflow) || n <= uint32_t(kEntCap)) {
               // Fast path: the row's cells are the handful of entries phase 1 recorded.
               carry += pre.carry_st[row];
-              #pragma unroll
-              for (int j = 0; j < kEntCap; j++) {
-                if (uint32_t(j) < n) {
-                  const uint2 en = pre.ent[row][j];
-                  if (int(en.x >> 2) == lane) {
-                    const uint32_t sel = en.x & 3u;
-                    c0 += sel == 0 ? en.y : 0u; c1 += sel == 1 ? en.y : 0u;
-                    c2 += sel == 2 ? en.y : 0u; c3 += sel == 3 ? en.y : 0u;
-                  }
-                }
+              for (uint32_t j = 0; j < n; j++) {
+                const uint2 en = pre.ent[row][j];
+                const uint32_t v = (int(en.x >> 2) == lane) ? en.y : 0u;
+                const uint32_t sel = en.x & 3u;
+                c0 += sel == 0 ? v : 0u; c1 += sel == 1 ? v : 0u;
+                c2 += sel == 2 ? v : 0u; c3 += sel == 3 ? v : 0u;
               }
             }
             else {
@@ -546,6 +551,94 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
 }
 
 // =================================================================================================================
+// K3s - streaming compositor for batches that only hold a few box fills (fill_all / clear_all / large rectangles).
+//
+// Such batches are pure HBM streaming (8 B per pixel for SrcOver): there is no coverage to accumulate and
+// nothing to order across tiles, so instead of one short-lived CTA per tile a persistent grid walks the canvas in
+// 16-byte chunks with four independent vector loads in flight per thread before any of them is consumed.
+// =================================================================================================================
+enum : int { kStreamMaxCmds = 8, kStreamUnroll = 4 };
+
+template<int BPP>
+__device__ __forceinline__ void stream_chunk(const TileParams& P, const b2dgpu_command* cmds, int ncmd, int x, int y, uint32_t* d, uint32_t& written) {
+  for (int k = 0; k < ncmd; k++) {
+    const b2dgpu_command& cmd = cmds[k];
+    uint32_t m[4];
+    if (cmd.type == B2DGPU_CMD_FILL_BOX_A) {
+      const bool in_y = y >= cmd.box[1] && y < cmd.box[3];
+      #pragma unroll
+      for (int i = 0; i < 4; i++) m[i] = (in_y && x + i >= cmd.box[0] && x + i < cmd.box[2]) ? cmd.alpha : 0u;
+    }
+    else {
+      BoxUParams bu = box_u_setup(cmd.box, cmd.alpha);
+      #pragma unroll
+      for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, x + i, y);
+    }
+    if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
+    const uint32_t sig = cmd.signature;
+    FetchEnv env;
+    env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
+    env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
+    env.solid = cmd.solid_prgb32;
+    env.fd = P.fetch_data + cmd.fetch_index;
+    env.bayer = P.bayer;
+    env.origin_x = P.origin_x; env.origin_y = P.origin_y;
+    uint32_t s[4];
+    fetch4(env, uint32_t(x), uint32_t(y), m, s);
+    if (BPP == 1) {
+      #pragma unroll
+      for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+    }
+    composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
+    written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
+  }
+}
+
+template<int BPP>
+__global__ void __launch_bounds__(256) k_box_stream(TileParams P, int rows, int y0r, int x0c, int chunks_per_row) {
+  __shared__ b2dgpu_command s_cmds[kStreamMaxCmds];
+  const int ncmd = int(P.command_count);
+  for (int i = threadIdx.x; i < ncmd * int(sizeof(b2dgpu_command) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(s_cmds)[i] = reinterpret_cast<const uint32_t*>(P.commands)[i];
+  __syncthreads();
+
+  // The dirty region [x0c*4, ...) x [y0r, y0r + rows) in 4-pixel chunks; chunk -> (row, column) without division in
+  // the inner loop would need 2-D indexing, the 64-bit divide below costs less than 1% of the memory time.
+  const long long total = (long long)rows * chunks_per_row;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  uint32_t written = 0;
+  for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * kStreamUnroll) {
+    uint4 v[kStreamUnroll];
+    int xs[kStreamUnroll], ys[kStreamUnroll];
+    uint8_t* ptr[kStreamUnroll];
+    #pragma unroll
+    for (int u = 0; u < kStreamUnroll; u++) {
+      long long c = c0 + stride * u;
+      bool ok = c < total;
+      int r = ok ? int(c / chunks_per_row) : 0;
+      int cc = ok ? int(c - (long long)r * chunks_per_row) : 0;
+      ys[u] = y0r + r;
+      xs[u] = (x0c + cc) * 4;
+      ptr[u] = ok ? P.dst + size_t(ys[u] - P.y_begin) * P.dst_stride + size_t(xs[u]) * BPP : nullptr;
+      if (ok) {
+        if (BPP == 4) v[u] = *reinterpret_cast<const uint4*>(ptr[u]);
+        else { uint32_t b = *reinterpret_cast<const uint32_t*>(ptr[u]); v[u] = make_uint4((b & 0xFFu) * 0x01010101u, ((b >> 8) & 0xFFu) * 0x01010101u, ((b >> 16) & 0xFFu) * 0x01010101u, (b >> 24) * 0x01010101u); }
+      }
+    }
+    #pragma unroll
+    for (int u = 0; u < kStreamUnroll; u++) {
+      if (!ptr[u]) continue;
+      uint32_t d[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
+      stream_chunk<BPP>(P, s_cmds, ncmd, xs[u], ys[u], d, written);
+      if (BPP == 4) *reinterpret_cast<uint4*>(ptr[u]) = make_uint4(d[0], d[1], d[2], d[3]);
+      else *reinterpret_cast<uint32_t*>(ptr[u]) = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
+    }
+  }
+  written = __reduce_add_sync(0xFFFFFFFFu, written);
+  if ((threadIdx.x & 31) == 0 && written) atomicAdd(P.pixel_counter, (unsigned long long)written);
+}
+
+// =================================================================================================================
 // Launchers (host)
 // =================================================================================================================
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -605,6 +698,21 @@ int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s) {
   if (!P.command_count) return 0;
   k_finalize_commands<<<div_up(P.command_count, 256), 256, 0, s>>>(P);
+  return 1;
+}
+
+// Streaming path: `box` = union of the commands' pixel boxes (already clipped to the target), in pixels.
+int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s) {
+  int x0c = box[0] / 4, x1c = (box[2] + 3) / 4;
+  int rows = box[3] - box[1];
+  int chunks_per_row = x1c - x0c;
+  if (rows <= 0 || chunks_per_row <= 0) return 0;
+  long long total = (long long)rows * chunks_per_row;
+  long long want = (total + 256LL * kStreamUnroll - 1) / (256LL * kStreamUnroll);
+  int grid = int(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
+  if (grid < 1) grid = 1;
+  if (bpp == 4) k_box_stream<4><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
+  else k_box_stream<1><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
   return 1;
 }
 

@@ -59,5 +59,6 @@ int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
 int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
 int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s);
+int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
 
 } // namespace b2d

@@ -107,6 +107,7 @@ struct b2dgpu_runtime {
 
   b2dgpu_stats stats;
   bool profiling;
+  int sm_count;
   std::vector<cudaEvent_t> prof_events;     // triples: start, after build kernels, after tile kernel
 };
 
@@ -140,6 +141,8 @@ struct b2dgpu_batch {
   uint32_t built_edges;                     // known after the first render
   bool built_known;
   bool edges_staged;                        // supplied edges already copied into `edges`
+  bool stream_ok;
+  int stream_box[4];
 };
 
 static const uint32_t kRuntimeMagic = 0xB2D09B00u;
@@ -235,6 +238,8 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
   rt->profiling = false;
+  rt->sm_count = 148;
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) rt->sm_count = v; }
   memset(&rt->stats, 0, sizeof(rt->stats));
 
   if (info && info->stream) rt->stream = (cudaStream_t)info->stream;
@@ -543,6 +548,8 @@ struct PreparedBatch {
   std::vector<FetchUse> uses;
   std::vector<size_t> fetch_blob;
   bool has_analytic;
+  bool stream_ok;
+  int stream_box[4];
 };
 
 static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb) {
@@ -554,6 +561,19 @@ static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb
   plan_layout(v, blob_bytes, pb.lay);
   pb.has_analytic = false;
   for (uint32_t i = 0; i < v->command_count; i++) if (v->commands[i].type == B2DGPU_CMD_FILL_ANALYTIC) pb.has_analytic = true;
+  pb.stream_ok = v->command_count >= 1 && v->command_count <= 8;
+  pb.stream_box[0] = pb.stream_box[1] = INT_MAX; pb.stream_box[2] = pb.stream_box[3] = INT_MIN;
+  for (uint32_t i = 0; i < v->command_count && pb.stream_ok; i++) {
+    const b2dgpu_command& c = v->commands[i];
+    int b[4];
+    if (c.type == B2DGPU_CMD_FILL_BOX_A) { b[0] = c.box[0]; b[1] = c.box[1]; b[2] = c.box[2]; b[3] = c.box[3]; }
+    else if (c.type == B2DGPU_CMD_FILL_BOX_U) { b[0] = c.box[0] >> 8; b[1] = c.box[1] >> 8; b[2] = (c.box[2] + 0xFF) >> 8; b[3] = (c.box[3] + 0xFF) >> 8; }
+    else { pb.stream_ok = false; break; }
+    if (b[0] < pb.stream_box[0]) pb.stream_box[0] = b[0];
+    if (b[1] < pb.stream_box[1]) pb.stream_box[1] = b[1];
+    if (b[2] > pb.stream_box[2]) pb.stream_box[2] = b[2];
+    if (b[3] > pb.stream_box[3]) pb.stream_box[3] = b[3];
+  }
   return B2DGPU_SUCCESS;
 }
 
@@ -595,6 +615,8 @@ struct RenderInput {
   bool built_known;
   uint32_t built_edges;
   bool edges_staged;
+  bool stream_ok;                 // only box fills, few of them: eligible for the streaming compositor
+  int stream_box[4];              // union of their boxes in pixels
 };
 
 static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderInput& in) {
@@ -700,7 +722,17 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
   T.origin_y = in.origin_y;
   T.pixel_counter = rt->d_pixel_counter;
   if (rt->profiling) CU_TRY(cudaEventRecord(ev[1], s));
-  launches += launch_tile_render(T, t->bpp, s);
+  bool streamed = false;
+  if (in.stream_ok) {
+    int box[4] = { in.stream_box[0] < 0 ? 0 : in.stream_box[0], in.stream_box[1] < t->y0 ? t->y0 : in.stream_box[1],
+                   in.stream_box[2] > t->w ? t->w : in.stream_box[2], in.stream_box[3] > t->y0 + t->h ? t->y0 + t->h : in.stream_box[3] };
+    // Large dirty regions only: small boxes are latency bound either way and the tile path culls them well.
+    if (box[0] < box[2] && box[1] < box[3] && (long long)(box[2] - box[0]) * (box[3] - box[1]) >= (1 << 20)) {
+      launches += launch_box_stream(T, t->bpp, box, rt->sm_count, s);
+      streamed = true;
+    }
+  }
+  if (!streamed) launches += launch_tile_render(T, t->bpp, s);
   if (rt->profiling) {
     CU_TRY(cudaEventRecord(ev[2], s));
     for (int i = 0; i < 3; i++) rt->prof_events.push_back(ev[i]);
@@ -737,6 +769,7 @@ extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target
   in.origin_x = view->pixel_origin_x; in.origin_y = view->pixel_origin_y;
   in.has_analytic = pb.has_analytic;
   in.built_known = false; in.built_edges = 0; in.edges_staged = false;
+  in.stream_ok = pb.stream_ok; memcpy(in.stream_box, pb.stream_box, sizeof(in.stream_box));
   return render_block(rt, target, in);
 }
 
@@ -763,6 +796,7 @@ extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_ba
   cudaError_t e = b->block.ensure(pb.lay.total_bytes);
   if (e != cudaSuccess) { delete b; return cuda_fail(e, "b2dgpu_batch_upload: cudaMalloc(block)"); }
   b->edges_staged = false;
+  b->stream_ok = pb.stream_ok; memcpy(b->stream_box, pb.stream_box, sizeof(b->stream_box));
   r = upload_block(rt, view, pb, static_cast<uint8_t*>(b->block.ptr));
   if (r) { b->block.release(); b->edges.release(); delete b; return r; }
   *out = b;
@@ -791,6 +825,7 @@ extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* 
   in.origin_x = b->origin_x; in.origin_y = b->origin_y;
   in.has_analytic = b->has_analytic;
   in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged;
+  in.stream_ok = b->stream_ok; memcpy(in.stream_box, b->stream_box, sizeof(in.stream_box));
   // The whole path (K1 count, scan, K1 write, finalize, K2+K3) re-runs on every render; only the host read-back of the
   // edge total is skipped after the first time because the geometry of a resident batch cannot change.
   b2dgpu_result r = render_block(rt, target, in);

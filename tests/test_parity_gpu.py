@@ -73,3 +73,32 @@ def test_4k_config1_slice(ref, gpu):
     W, H = 3840, 2160
     compare(ref, gpu, S.curve_paths("quad", 40, W, H, 0, "linear"), W, H)
     compare(ref, gpu, S.polygons(500, 256, 20, W, H, 1, "radial", 1), W, H)
+
+
+def big_box_scene(style, op):
+    """A batch that only holds a few large box fills: exercises the streaming compositor (k_box_stream)."""
+    def scene(api, ctx, rng):
+        W, H = ctx.image.w, ctx.image.h
+        ctx.set_comp_op(op)
+        if style == "solid":
+            ctx.set_fill_style(0x80FF8040)
+        else:
+            ctx.set_gradient_quality(2)
+            ctx.set_fill_style(S.make_gradient(api, rng, {"linear": 0, "radial": 1, "conic": 2}[style], 1, 100.0, 50.0, 700.0, 500.0))
+        ctx.fill_all()
+        ctx.flush()
+        ctx.set_fill_style(0x60102030)
+        ctx.fill_rect_d(10.25, 20.5, W - 30.75, H - 41.125)
+        ctx.fill_rect_i(5, 7, W - 11, H - 13)
+        ctx.flush()
+        ctx.clear_all()
+        ctx.set_fill_style(S.rand_rgba32(rng))
+        ctx.fill_rect_d(0.5, 0.5, W - 1.0, H - 1.0)
+    return scene
+
+
+@pytest.mark.parametrize("style,tol", [("solid", 0), ("linear", 0), ("radial", 0), ("conic", 1)])
+@pytest.mark.parametrize("fmt", [1, 3])
+@pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
+def test_streaming_box_fills(ref, gpu, style, tol, fmt, op):
+    compare(ref, gpu, big_box_scene(style, op), 1403, 1001, fmt, max_diff=tol)
