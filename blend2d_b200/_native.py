@@ -82,7 +82,7 @@ class GradientStop(C.Structure):
 class ContextCreateInfo(C.Structure):
     _fields_ = [("flags", C.c_uint32), ("thread_count", C.c_uint32), ("pixel_origin_x", C.c_int32),
                 ("pixel_origin_y", C.c_int32), ("device", C.c_int32), ("command_queue_limit", C.c_uint32),
-                ("runtime", C.c_void_p), ("stream", C.c_void_p)]
+                ("runtime", C.c_void_p), ("stream", C.c_void_p), ("slab_y0", C.c_int32), ("slab_y1", C.c_int32)]
 
 
 # Every symbol declared in include/b2dgpu.h and include/b2d_host.h (tests/test_abi.py checks the list against the headers).

@@ -179,10 +179,11 @@ class Context:
     """BLContext bound to an Image; rendering happens on the GPU when the batch is flushed."""
 
     def __init__(self, image, device=0, pixel_origin=(0, 0), command_queue_limit=0, runtime=None, stream=None,
-                 record_only=False):
+                 record_only=False, slab=None):
         self.image = image
+        y0, y1 = slab if slab is not None else (0, 0)
         info = N.ContextCreateInfo(0x40000000 if record_only else 0, 0, pixel_origin[0], pixel_origin[1], device, command_queue_limit,
-                                   runtime._h if runtime is not None else None, stream)
+                                   runtime._h if runtime is not None else None, stream, y0, y1)
         self._h = C.c_void_p()
         check(lib.b2d_context_create(image._h, C.byref(info), C.byref(self._h)), "b2d_context_create")
         self._keep = []

@@ -1077,7 +1077,11 @@ extern "C" b2dgpu_result b2d_context_create(b2d_image* target, const b2d_context
     if (r) { delete c; return r; }
     c->own_rt = true;
   }
-  if (!c->record_only) r = b2dgpu_target_create(c->rt, target->w, target->h, target->format, &c->target);
+  if (!c->record_only) {
+    int y0 = 0, y1 = target->h;
+    if (info && (info->slab_y0 || info->slab_y1)) { y0 = info->slab_y0; y1 = info->slab_y1; }
+    r = b2dgpu_target_create_slab(c->rt, target->w, target->h, y0, y1, target->format, &c->target);
+  }
   if (!r && !c->record_only) {
     b2dgpu_image_data id; b2d_image_get_data(target, &id);
     r = b2dgpu_target_upload(c->target, &id);

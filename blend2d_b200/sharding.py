@@ -1,0 +1,77 @@
+"""Multi-GPU sharding of the render path: one process per GPU, no collective while rendering.
+
+Two partitions, both taken from the reference's own threading model:
+
+  band sharding   One big canvas.  Rank r owns a contiguous slab of rows, rounded to the tile height, and replays EVERY
+                  command clipped to its slab - exactly what a reference worker does with its bands
+                  (raster/workerproc.cpp:260-299, rendercommandprocasync_p.h:153-174).  The only exchange is one gather of
+                  the slabs when a single contiguous image is needed (`gather_canvas`), NCCL over NVLink on the GPU box.
+  frame sharding  Many independent canvases.  Frame i belongs to rank i mod world; nothing is exchanged.
+
+`torch.distributed` is plumbing here (process group + the final gather); rendering never goes through it.
+"""
+import ctypes as C
+
+TILE_ROWS = 8          # kTileH in csrc/dev_common.cuh: slabs are cut on tile boundaries so no tile is shared by two ranks
+
+
+def slab_table(height, world, align=TILE_ROWS):
+    """[(y0, y1)] per rank: contiguous, disjoint, covering [0, height), every boundary a multiple of `align`.
+    Ranks that would get nothing (more ranks than row groups) receive an empty slab (y0 == y1)."""
+    if height <= 0 or world <= 0:
+        raise ValueError("height and world must be positive")
+    groups = (height + align - 1) // align
+    table, g0 = [], 0
+    for r in range(world):
+        g1 = g0 + groups // world + (1 if r < groups % world else 0)
+        table.append((min(g0 * align, height), min(g1 * align, height)))
+        g0 = g1
+    return table
+
+
+def slab_rows(height, world, rank, align=TILE_ROWS):
+    return slab_table(height, world, align)[rank]
+
+
+def frames_of(rank, world, frame_count):
+    """Indices of the frames rank `rank` renders (round robin, like scene i -> GPU i mod G)."""
+    return range(rank, frame_count, world)
+
+
+def canvas_tensor(ctx):
+    """The context's device canvas slab as a torch uint8 tensor [padded rows, stride bytes] (no copy).
+    Rows beyond the slab height and bytes beyond width * bpp are padding."""
+    import torch
+    from . import _native as N
+    ptr, stride, pw, ph = C.c_void_p(), C.c_ssize_t(), C.c_int32(), C.c_int32()
+    N.check(N.lib.b2dgpu_target_device_view(ctx.target_handle(), C.byref(ptr), C.byref(stride), C.byref(pw), C.byref(ph)),
+            "b2dgpu_target_device_view")
+
+    class _Mem:
+        pass
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": (ph.value, stride.value), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+    return torch.as_tensor(m, device=torch.device("cuda", torch.cuda.current_device()))
+
+
+def gather_canvas(local_rows, height, dst=0, group=None):
+    """Gathers per-rank row slabs into the full image on rank `dst`.
+
+    local_rows: torch tensor [rows of this rank's slab, row_bytes] (uint8; CUDA with NCCL, CPU with gloo).
+    Returns the [height, row_bytes] tensor on `dst`, None elsewhere.  Slabs are padded to the tallest slab for the
+    collective and trimmed afterwards."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    table = slab_table(height, world)
+    y0, y1 = table[rank]
+    if local_rows.shape[0] < y1 - y0:
+        raise ValueError("local slab has fewer rows than the partition assigns to this rank")
+    tallest = max(b - a for a, b in table)
+    send = torch.zeros((tallest, local_rows.shape[1]), dtype=local_rows.dtype, device=local_rows.device)
+    send[: y1 - y0].copy_(local_rows[: y1 - y0])
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([recv[r][: b - a] for r, (a, b) in enumerate(table)], dim=0)

@@ -69,6 +69,10 @@ typedef struct b2d_context_create_info {      /* BLContextCreateInfo (core/conte
   uint32_t command_queue_limit;               /* commands per batch before an implicit flush (0 = default)       */
   void*    runtime;                           /* optional shared b2dgpu_runtime*                                  */
   void*    stream;                            /* optional cudaStream_t for a runtime created by this context     */
+  int32_t  slab_y0, slab_y1;                  /* band sharding: this context owns image rows [slab_y0, slab_y1) only;
+                                                 0,0 = the whole image.  Mirrors the reference's worker/band model,
+                                                 where every worker replays all commands clipped to its own bands
+                                                 (raster/workerproc.cpp:260-299).                                   */
 } b2d_context_create_info;
 
 B2DGPU_API b2dgpu_result b2d_context_create(b2d_image* target, const b2d_context_create_info* info, b2d_context** out);

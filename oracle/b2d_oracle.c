@@ -1,0 +1,597 @@
+/*
+ * b2d_oracle.c - CPU restatement (plain C) of the reference's pixel path, written for CHECKING, not for speed.
+ *
+ * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may build, load or call
+ * this file.  Nothing under blend2d_b200/ does; the product has no CPU path.
+ *
+ * What is restated (each function cites the reference lines it follows, relative to /root/reference):
+ *   - composition operators on premultiplied PRGB32 and on A8      pipeline/reference/compopgeneric_p.h:24-81,
+ *                                                                  pipeline/reference/pixelgeneric_p.h:292-405
+ *     plus Multiply / Screen, which only exist in the JIT          pipeline/jit/compoppart.cpp:4325-4461, 4591-4640
+ *   - coverage accumulator -> mask                                 pipeline/reference/fillgeneric_p.h:381-387
+ *   - FillAnalytic scanline walk over dense cells                  pipeline/reference/fillgeneric_p.h:174-379
+ *   - axis-unaligned box -> mask-command program and its walker    pipeline/pipedefs_p.h:644-815,
+ *                                                                  pipeline/reference/fillgeneric_p.h:67-162
+ *   - the analytic rasterizer in its ORIGINAL whole-edge (non-banded, multi-scanline) form
+ *                                                                  raster/analyticrasterizer_p.h:289-360, 466-1165
+ *   - unclipped polygon -> 24.8 edges                              raster/edgebuilder_p.h:1136-1152
+ *   - linear gradient fetch (incremental form)                     pipeline/reference/fetchgeneric_p.h:939-1011
+ *
+ * PINNING: every restated piece that the reference itself can execute (SrcOver, SrcCopy, masks, rasterizer, BoxU,
+ * linear gradient) is checked against the UNMODIFIED reference binary (oracle/_ref/libblend2d_ref.so) in
+ * tests/test_oracle.py and against the committed fixtures in tests/golden/.  The reference ships no golden images
+ * (SURVEY.md section 4), so "outputs of the reference itself run here" are the golden vectors.
+ * Plus / Multiply / Screen: PARITY UNPINNED - the reference's portable pipeline rejects them
+ * (pipeline/reference/fixedpiperuntime.cpp:254) and its JIT cannot be built here (asmjit is not vendored); they are
+ * restated from the JIT source and only their inputs (masks, source pixels) come from the reference binary.
+ *
+ * NOT restated here: curve flattening / clipping and the radial, conic and pattern fetchers.  Those are checked
+ * directly against the reference binary (tests/test_parity_gpu.py, tests/test_hostsim_parity.py).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Pixel arithmetic: 4 x 16-bit lanes in one 64-bit word, laid out [.3.1.2.0] like U32_8888 (pixelgeneric_p.h:292-296).
+ * ---------------------------------------------------------------------------------------------------------------- */
+static uint64_t orc_rep(uint32_t v) { uint64_t x = v | (v << 16); return x | (x << 32); }                 /* Repeat::u16x4 */
+static uint64_t orc_unpack(uint32_t p) { return (uint64_t)(p & 0x00FF00FFu) | ((uint64_t)(p & 0xFF00FF00u) << 24); }
+static uint32_t orc_pack(uint64_t u) { return (uint32_t)(((u >> 24) | u) & 0xFFFFFFFFu); }
+static uint64_t orc_div255(uint64_t u) {                                                                  /* :390-393 */
+  u += orc_rep(0x80u);
+  return ((u + ((u >> 8) & orc_rep(0xFFu))) >> 8) & orc_rep(0xFFu);
+}
+static uint64_t orc_addus8(uint64_t a, uint64_t b) {                                                       /* :399-403 */
+  uint64_t val = a + b;
+  uint64_t msk = ((val >> 8) & orc_rep(0x1u)) * 0xFFu;
+  return (val | msk) & orc_rep(0xFFu);
+}
+
+/* CompOp_SrcCopy_Op::op_prgb32_prgb32(d, s, m)                                      compopgeneric_p.h:38-40 */
+static uint32_t orc_src_copy(uint32_t d, uint32_t s, uint32_t m) {
+  return orc_pack(orc_div255(orc_unpack(d) * (m ^ 0xFFu) + orc_unpack(s) * m));
+}
+/* CompOp_SrcOver_Op::op_prgb32_prgb32(d, s, m)                                      compopgeneric_p.h:54-62 */
+static uint32_t orc_src_over(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t sm = orc_pack(orc_div255(orc_unpack(s) * m));
+  return sm + orc_pack(orc_div255(orc_unpack(d) * ((sm >> 24) ^ 0xFFu)));
+}
+/* CompOp_Plus_Op::op_prgb32_prgb32(d, s, m)                                         compopgeneric_p.h:78-80 */
+static uint32_t orc_plus(uint32_t d, uint32_t s, uint32_t m) {
+  return orc_pack(orc_addus8(orc_unpack(d), orc_div255(orc_unpack(s) * m)));
+}
+
+/* 16-bit SIMD lane helpers of the JIT: v_mul_u16 (pmullw), v_add_i16 (paddw), v_div255_u16 = paddw 0x80; pmulhuw 0x101
+ * (pipeline/jit/pipecompiler_p.h:84-95), packing with unsigned saturation (packuswb). */
+static uint32_t jit_mul16(uint32_t a, uint32_t b) { return (a * b) & 0xFFFFu; }
+static uint32_t jit_add16(uint32_t a, uint32_t b) { return (a + b) & 0xFFFFu; }
+static uint32_t jit_div255(uint32_t x) { return (((x + 0x80u) & 0xFFFFu) * 0x101u) >> 16; }
+static uint32_t jit_packus(uint32_t x) { int16_t v = (int16_t)x; return v < 0 ? 0u : v > 255 ? 255u : (uint32_t)v; }
+
+/* Multiply, masked, Da and Sa used                                                  compoppart.cpp:4408-4441
+ *   S = div255(S * m);  D' = div255(D * (S + (255 - Sa)) + S * (255 - Da))   per channel, alpha included. */
+static uint32_t orc_multiply(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t sv[4], dv[4], out = 0;
+  for (int i = 0; i < 4; i++) { sv[i] = jit_div255(jit_mul16((s >> (i * 8)) & 0xFFu, m)); dv[i] = (d >> (i * 8)) & 0xFFu; }
+  uint32_t isa = 255u - sv[3], ida = 255u - dv[3];                                                        /* v_inv255_u16 */
+  for (int i = 0; i < 4; i++) {
+    uint32_t y = jit_add16(isa, sv[i]);
+    uint32_t v = jit_add16(jit_mul16(dv[i], y), jit_mul16(ida, sv[i]));
+    out |= jit_packus(jit_div255(v)) << (i * 8);
+  }
+  return out;
+}
+/* Screen, masked                                                                    compoppart.cpp:4614-4630
+ *   S = div255(S * m);  D' = div255(D * (255 - S)) + S */
+static uint32_t orc_screen(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t out = 0;
+  for (int i = 0; i < 4; i++) {
+    uint32_t sc = jit_div255(jit_mul16((s >> (i * 8)) & 0xFFu, m));
+    uint32_t dc = (d >> (i * 8)) & 0xFFu;
+    out |= jit_packus(jit_add16(jit_div255(jit_mul16(dc, 255u - sc)), sc)) << (i * 8);
+  }
+  return out;
+}
+
+/* A8 pixels (P8_Alpha / U8_Alpha, pixelgeneric_p.h:85-200): one 16-bit lane, packed adds wrap at 8 bits. */
+static uint32_t a8_div255(uint32_t u) { u = (u + 0x80u) & 0xFFFFu; return ((u + ((u >> 8) & 0xFFu)) >> 8) & 0xFFu; }
+static uint32_t orc_a8_src_copy(uint32_t d, uint32_t s, uint32_t m) { return a8_div255(d * (m ^ 0xFFu) + s * m); }
+static uint32_t orc_a8_src_over(uint32_t d, uint32_t s, uint32_t m) {
+  uint32_t sm = a8_div255(s * m);
+  return (sm + a8_div255(d * (sm ^ 0xFFu))) & 0xFFu;
+}
+
+enum { ORC_SRC_OVER = 0, ORC_SRC_COPY = 1, ORC_PLUS = 12, ORC_MULTIPLY = 15, ORC_SCREEN = 16 };
+
+ORC_API uint32_t orc_composite_prgb32(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
+  if (m == 0) return d;                      /* the fillers never call the compositor with a zero mask ... except in  */
+  switch (op) {                              /* VMask runs, where every operator below is the identity for m == 0.    */
+    case ORC_SRC_OVER: return orc_src_over(d, s, m);
+    case ORC_SRC_COPY: return orc_src_copy(d, s, m);
+    case ORC_PLUS: return orc_plus(d, s, m);
+    case ORC_MULTIPLY: return orc_multiply(d, s, m);
+    default: return orc_screen(d, s, m);
+  }
+}
+
+/* dst[i] = op(dst[i], src[i], mask[i]) over a plane of n pixels; src_stride 0 means a solid source. */
+ORC_API void orc_composite_plane_prgb32(uint32_t op, uint32_t* dst, const uint32_t* src, int src_is_solid, const uint8_t* mask, size_t n) {
+  for (size_t i = 0; i < n; i++) dst[i] = orc_composite_prgb32(op, dst[i], src[src_is_solid ? 0 : i], mask[i]);
+}
+
+ORC_API void orc_composite_plane_a8(uint32_t op, uint8_t* dst, const uint8_t* src, int src_is_solid, const uint8_t* mask, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t m = mask[i], s = src[src_is_solid ? 0 : i];
+    if (!m) continue;
+    dst[i] = (uint8_t)(op == ORC_SRC_COPY ? orc_a8_src_copy(dst[i], s, m) : orc_a8_src_over(dst[i], s, m));
+  }
+}
+
+/* FillAnalytic_Base::calc_mask                                                      fillgeneric_p.h:381-387 */
+ORC_API uint32_t orc_calc_mask(uint32_t cov, uint32_t fill_rule_mask, uint32_t global_alpha) {
+  uint32_t c = 256;
+  uint32_t m = ((uint32_t)(((int32_t)cov) >> 9) & fill_rule_mask) - c;
+  int32_t mi = (int32_t)m;
+  uint32_t a = (uint32_t)(mi < 0 ? -mi : mi);
+  if (a > c) a = c;
+  return (a * global_alpha) >> 8;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Analytic rasterizer, whole-edge form (rasterize<> without kOptionBandingMode).  Cells: u32 cells[h][stride],
+ * stride >= w + 2.  The bit vectors of the reference only accelerate the later scan and are not modelled.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int ex0, ey0, ex1, ey1, fx0, fy0, fx1, fy1;
+  int xErr, yErr, xDlt, yDlt, xRem, yRem, xLift, yLift, dx, dy, savedFy1;
+  uint32_t flags, sign_mask;
+} OrcRas;
+
+enum { ORC_INITIAL = 1, ORC_VERT_OR_SINGLE = 2, ORC_RTL = 4 };
+
+static void orc_err_step(int* acc, int* iter, int step, int correction) {                                 /* :71-82 */
+  *iter -= step;
+  if (*iter < 0) { (*acc)++; *iter += correction; }
+}
+static uint32_t orc_sign(const OrcRas* r, uint32_t v) { return (v ^ r->sign_mask) - r->sign_mask; }        /* :56-60 */
+static void orc_merge(uint32_t* row, int x, uint32_t cover, uint32_t area) {                               /* :1202-1210 */
+  row[x] += (cover << 9) - area;
+  row[x + 1] += area;
+}
+
+static int orc_prepare(OrcRas* r, int x0, int y0, int x1, int y1) {                                        /* :289-360 */
+  if (y0 == y1) return 0;
+  r->dx = x1 - x0; r->dy = y1 - y0; r->flags = ORC_INITIAL;
+  if (r->dx < 0) { r->flags |= ORC_RTL; r->dx = -r->dx; }
+  r->ex0 = x0 >> 8; r->ey0 = y0 >> 8; r->ex1 = x1 >> 8; r->ey1 = (y1 - 1) >> 8;
+  r->fx0 = x0 & 255; r->fy0 = y0 & 255; r->fx1 = x1 & 255; r->fy1 = ((y1 - 1) & 255) + 1;
+  r->savedFy1 = r->fy1;
+  if (r->ey0 != r->ey1) r->fy1 = 256;
+  r->xErr = r->yErr = r->xDlt = r->yDlt = r->xRem = r->yRem = r->xLift = r->yLift = 0;
+  if (r->ex0 == r->ex1 && (r->ey0 == r->ey1 || r->dx == 0)) { r->flags |= ORC_VERT_OR_SINGLE; return 1; }
+  uint64_t x_base = (uint64_t)(uint32_t)r->dx * 256, y_base = (uint64_t)(uint32_t)r->dy * 256;
+  r->xLift = (int)(x_base / (unsigned)r->dy); r->xRem = (int)(x_base % (unsigned)r->dy);
+  r->yLift = (int)(y_base / (unsigned)r->dx); r->yRem = (int)(y_base % (unsigned)r->dx);
+  r->xDlt = r->dx; r->yDlt = r->dy;
+  r->xErr = (r->dy >> 1) - 1; r->yErr = (r->dx >> 1) - 1;
+  if (r->ey0 != r->ey1) {
+    uint64_t p = (uint64_t)(256 - (uint32_t)r->fy0) * (uint32_t)r->dx;
+    r->xDlt = (int)(p / (unsigned)r->dy); r->xErr -= (int)(p % (unsigned)r->dy);
+    orc_err_step(&r->xDlt, &r->xErr, 0, r->dy);
+  }
+  if (r->ex0 != r->ex1) {
+    uint64_t p = (uint64_t)((r->flags & ORC_RTL) ? (uint32_t)r->fx0 : 256 - (uint32_t)r->fx0) * (uint32_t)r->dy;
+    r->yDlt = (int)(p / (unsigned)r->dx); r->yErr -= (int)(p % (unsigned)r->dx);
+    orc_err_step(&r->yDlt, &r->yErr, 0, r->dx);
+  }
+  r->yDlt += r->fy0;
+  return 1;
+}
+
+/* One whole edge, top to bottom (rasterize<0>, :466-1165 with every kOptionBandingMode branch removed). */
+static void orc_rasterize(OrcRas* r, uint32_t* cells, size_t stride) {
+  size_t i = (size_t)(r->ey1 - r->ey0);
+  uint32_t* row = cells + (size_t)r->ey0 * stride;
+  const uint32_t full = orc_sign(r, 256);
+
+  if (r->flags & ORC_VERT_OR_SINGLE) {                                                                      /* :493-571 */
+    uint32_t area = (uint32_t)r->fx0 + (uint32_t)r->fx1;
+    uint32_t cover = orc_sign(r, (uint32_t)(r->fy1 - r->fy0));
+    orc_merge(row, r->ex0, cover, cover * area);
+    if (!i) return;
+    row += stride;
+    cover = full;
+    while (--i) { orc_merge(row, r->ex0, cover, cover * area); row += stride; }
+    cover = orc_sign(r, (uint32_t)r->savedFy1);
+    orc_merge(row, r->ex0, cover, cover * area);
+    return;
+  }
+
+  if (r->dy >= r->dx) {                                                                                     /* :572-869 */
+    for (;;) {
+      uint32_t area = (uint32_t)r->fx0, cov;
+      if (r->flags & ORC_RTL) {
+        r->fx0 -= r->xDlt;
+        if (r->fx0 < 0) {
+          r->ex0--; r->fx0 += 256; r->yDlt &= 255;
+          if (!area) {
+            area = 256;
+            orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); r->yDlt += r->yLift;
+            cov = orc_sign(r, (uint32_t)(r->fy1 - r->fy0));
+            orc_merge(row, r->ex0, cov, cov * (area + (uint32_t)r->fx0));
+          }
+          else {
+            cov = orc_sign(r, (uint32_t)(r->yDlt - r->fy0));
+            orc_merge(row, r->ex0 + 1, cov, cov * area);
+            cov = orc_sign(r, (uint32_t)(r->fy1 - r->yDlt));
+            orc_merge(row, r->ex0, cov, cov * ((uint32_t)r->fx0 + 256));
+            orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); r->yDlt += r->yLift;
+          }
+        }
+        else {
+          cov = orc_sign(r, (uint32_t)(r->fy1 - r->fy0));
+          orc_merge(row, r->ex0, cov, cov * (area + (uint32_t)r->fx0));
+        }
+      }
+      else {
+        r->fx0 += r->xDlt;
+        if (r->fx0 <= 256) {
+          cov = orc_sign(r, (uint32_t)(r->fy1 - r->fy0));
+          orc_merge(row, r->ex0, cov, cov * (area + (uint32_t)r->fx0));
+          if (r->fx0 == 256) { r->ex0++; r->fx0 = 0; r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); }
+        }
+        else {
+          r->ex0++; r->fx0 &= 255; r->yDlt &= 255;
+          cov = orc_sign(r, (uint32_t)(r->yDlt - r->fy0));
+          orc_merge(row, r->ex0 - 1, cov, cov * (area + 256));
+          cov = orc_sign(r, (uint32_t)(r->fy1 - r->yDlt));
+          orc_merge(row, r->ex0, cov, cov * (uint32_t)r->fx0);
+          r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx);
+        }
+      }
+      r->fy0 = 0;
+      row += stride;
+      if (!i) return;
+
+      /* scanlines strictly between the first and the last one: full cover, x advances by the DDA step */
+      while (--i) {
+        r->xDlt = r->xLift; orc_err_step(&r->xDlt, &r->xErr, r->xRem, r->dy);
+        r->fy1 = 256;
+        area = (uint32_t)r->fx0;
+        if (r->flags & ORC_RTL) {
+          r->fx0 -= r->xDlt;
+          if (r->fx0 < 0) {
+            r->ex0--; r->fx0 += 256; r->yDlt &= 255;
+            if (!area) {
+              area = 256;
+              orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); r->yDlt += r->yLift;
+              orc_merge(row, r->ex0, full, full * (area + (uint32_t)r->fx0));
+            }
+            else {
+              uint32_t c1 = orc_sign(r, (uint32_t)r->yDlt);
+              orc_merge(row, r->ex0 + 1, c1, c1 * area);
+              uint32_t c0 = full - c1;
+              orc_merge(row, r->ex0, c0, c0 * ((uint32_t)r->fx0 + 256));
+              orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); r->yDlt += r->yLift;
+            }
+          }
+          else orc_merge(row, r->ex0, full, full * (area + (uint32_t)r->fx0));
+        }
+        else {
+          r->fx0 += r->xDlt;
+          if (r->fx0 <= 256) {
+            orc_merge(row, r->ex0, full, full * (area + (uint32_t)r->fx0));
+            if (r->fx0 == 256) { r->ex0++; r->fx0 = 0; r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); }
+          }
+          else {
+            r->fx0 &= 255; r->yDlt &= 255;
+            uint32_t c0 = orc_sign(r, (uint32_t)r->yDlt);
+            orc_merge(row, r->ex0, c0, c0 * (area + 256));
+            r->ex0++;
+            uint32_t c1 = orc_sign(r, 256 - (uint32_t)r->yDlt);
+            orc_merge(row, r->ex0, c1, c1 * (uint32_t)r->fx0);
+            r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx);
+          }
+        }
+        row += stride;
+      }
+
+      /* prepare the last scanline (:862-866 / :717-722) and run the first-scanline code once more */
+      r->fy1 = r->savedFy1;
+      r->xDlt = (r->flags & ORC_RTL) ? ((r->ex0 - r->ex1) << 8) + r->fx0 - r->fx1 : ((r->ex1 - r->ex0) << 8) + r->fx1 - r->fx0;
+      i = 0;
+    }
+  }
+
+  /* shallow edge: a run of cells per scanline (:870-1164) */
+  {
+    size_t j = 1;
+    int x_local = (r->ex0 << 8) + r->fx0;
+    uint32_t cover, area;
+    const int rtl = (r->flags & ORC_RTL) != 0;
+    int skip_to_inside = 0;
+
+    if (r->flags & ORC_INITIAL) {
+      r->flags &= ~ORC_INITIAL;
+      j = i; i = 1;
+      cover = orc_sign(r, (uint32_t)(r->yDlt - r->fy0));
+      if (rtl ? (r->fx0 - r->xDlt < 0) : (r->fx0 + r->xDlt > 256)) skip_to_inside = 1;
+      else {
+        if (rtl) x_local -= r->xDlt; else x_local += r->xDlt;
+        cover = orc_sign(r, (uint32_t)(r->fy1 - r->fy0));
+        area = rtl ? cover * (uint32_t)(r->fx0 * 2 - r->xDlt) : cover * ((uint32_t)r->fx0 * 2 + (uint32_t)r->xDlt);
+        orc_merge(row, r->ex0, cover, area);
+        if (rtl ? ((x_local & 255) == 0) : (r->fx0 + r->xDlt == 256)) { r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); }
+        r->xDlt = r->xLift; orc_err_step(&r->xDlt, &r->xErr, r->xRem, r->dy);
+        row += stride;
+        i--;
+      }
+    }
+    else cover = 0;
+
+    for (;;) {
+      while (i) {
+        if (!skip_to_inside) {
+          if (rtl) { r->ex0 = (x_local - 1) >> 8; r->fx0 = ((x_local - 1) & 255) + 1; }
+          else { r->ex0 = x_local >> 8; r->fx0 = x_local & 255; }
+          r->yDlt -= 256;
+          cover = orc_sign(r, (uint32_t)r->yDlt);
+        }
+        skip_to_inside = 0;
+
+        if (rtl) {
+          x_local -= r->xDlt;
+          int ex_local = x_local >> 8, fx_local = x_local & 255;
+          area = cover * (uint32_t)r->fx0;
+          while (r->ex0 != ex_local) {
+            orc_merge(row, r->ex0, cover, area);
+            int cv = r->yLift; orc_err_step(&cv, &r->yErr, r->yRem, r->dx);
+            r->yDlt += cv;
+            cover = orc_sign(r, (uint32_t)cv);
+            area = cover * 256;
+            r->ex0--;
+          }
+          cover += orc_sign(r, (uint32_t)(r->fy1 - r->yDlt));
+          area = cover * ((uint32_t)fx_local + 256);
+          orc_merge(row, r->ex0, cover, area);
+          if (fx_local == 0) { r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); }
+        }
+        else {
+          x_local += r->xDlt;
+          int ex_local = (x_local - 1) >> 8, fx_local = ((x_local - 1) & 255) + 1;
+          area = cover * ((uint32_t)r->fx0 + 256);
+          while (r->ex0 != ex_local) {
+            orc_merge(row, r->ex0, cover, area);
+            int cv = r->yLift; orc_err_step(&cv, &r->yErr, r->yRem, r->dx);
+            r->yDlt += cv;
+            cover = orc_sign(r, (uint32_t)cv);
+            area = cover * 256;
+            r->ex0++;
+          }
+          cover += orc_sign(r, (uint32_t)(r->fy1 - r->yDlt));
+          area = cover * (uint32_t)fx_local;
+          orc_merge(row, r->ex0, cover, area);
+          if (fx_local == 256) { r->yDlt += r->yLift; orc_err_step(&r->yDlt, &r->yErr, r->yRem, r->dx); }
+        }
+        r->xDlt = r->xLift; orc_err_step(&r->xDlt, &r->xErr, r->xRem, r->dy);
+        row += stride;
+        i--;
+      }
+
+      r->fy0 = 0; r->fy1 = 256;
+      if (!j) return;
+      i = j - 1; j = 1;
+      if (!i) {
+        /* last scanline (:993-1017 / :1136-1160) */
+        i = 1; j = 0;
+        r->fy1 = r->savedFy1;
+        if (rtl) {
+          r->xDlt = x_local - ((r->ex1 << 8) + r->fx1);
+          r->ex0 = (x_local - 1) >> 8; r->fx0 = ((x_local - 1) & 255) + 1;
+          if (r->fx0 - r->xDlt >= 0) {
+            cover = orc_sign(r, (uint32_t)r->fy1);
+            orc_merge(row, r->ex0, cover, cover * (uint32_t)(r->fx0 * 2 - r->xDlt));
+            return;
+          }
+        }
+        else {
+          r->xDlt = ((r->ex1 << 8) + r->fx1) - x_local;
+          r->ex0 = x_local >> 8; r->fx0 = x_local & 255;
+          if (r->fx0 + r->xDlt <= 256) {
+            cover = orc_sign(r, (uint32_t)r->fy1);
+            orc_merge(row, r->ex0, cover, cover * ((uint32_t)r->fx0 * 2 + (uint32_t)r->xDlt));
+            return;
+          }
+        }
+        r->yDlt -= 256;
+        cover = orc_sign(r, (uint32_t)r->yDlt);
+        skip_to_inside = 1;
+      }
+    }
+  }
+}
+
+/* Accumulates `n` edges (x0,y0,x1,y1 in 24.8, ORIGINAL direction: y0 > y1 means sign bit set) into zeroed cells. */
+ORC_API void orc_rasterize_edges(const int32_t* edges, size_t n, uint32_t* cells, size_t stride) {
+  for (size_t k = 0; k < n; k++) {
+    int x0 = edges[k * 4], y0 = edges[k * 4 + 1], x1 = edges[k * 4 + 2], y1 = edges[k * 4 + 3];
+    OrcRas r;
+    r.sign_mask = 0;
+    if (y0 > y1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; r.sign_mask = 0xFFFFFFFFu; }
+    if (!orc_prepare(&r, x0, y0, x1, y1)) continue;
+    orc_rasterize(&r, cells, stride);
+  }
+}
+
+/* Cells -> 8-bit masks for rows [0, h): mask[y][x] = calc_mask(256 << 9 + sum of cells[y][0..x]).  This is what
+ * FillAnalytic_Base's VMask / CMask walk (fillgeneric_p.h:207-378) computes for every pixel it composites; pixels it
+ * skips have mask 0 in this formulation as well. */
+ORC_API void orc_cells_to_masks(const uint32_t* cells, size_t stride, int w, int h, uint32_t fill_rule_mask, uint32_t alpha, uint8_t* masks) {
+  for (int y = 0; y < h; y++) {
+    uint32_t cov = 256u << 9;
+    for (int x = 0; x < w; x++) {
+      cov += cells[(size_t)y * stride + (size_t)x];
+      masks[(size_t)y * (size_t)w + (size_t)x] = (uint8_t)orc_calc_mask(cov, fill_rule_mask, alpha);
+    }
+  }
+}
+
+/* Unclipped polygon -> edges: every vertex is truncated to 24.8 (Math::trunc_to_int) and consecutive points form a line
+ * when their fixed y differ (edgebuilder_p.h:1142-1152, 1282-1294); the polygon is implicitly closed (:1058-1062).
+ * pts are already in 24.8 UNITS as doubles (i.e. multiplied by 256).  Returns the number of edges written. */
+ORC_API size_t orc_polygon_edges(const double* pts, size_t n, int32_t* edges_out) {
+  size_t ne = 0;
+  for (size_t k = 0; k < n; k++) {
+    size_t k1 = (k + 1) % n;
+    int x0 = (int)pts[k * 2], y0 = (int)pts[k * 2 + 1], x1 = (int)pts[k1 * 2], y1 = (int)pts[k1 * 2 + 1];
+    if (y0 == y1) continue;
+    edges_out[ne * 4] = x0; edges_out[ne * 4 + 1] = y0; edges_out[ne * 4 + 2] = x1; edges_out[ne * 4 + 3] = y1;
+    ne++;
+  }
+  return ne;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Axis-unaligned box: FillData::init_box_u_8bpc_24x8 builds a small program of mask commands (pipedefs_p.h:644-815)
+ * and FillMask_Base interprets it with repeat counters (fillgeneric_p.h:67-162).  Both are restated; the result is the
+ * mask of every pixel of the box's outer pixel rectangle.  Returns 0 when the reference would draw nothing.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct { uint32_t x0, x1, type; uint32_t value; const uint8_t* ptr; } OrcMaskCmd;   /* type 0 end/repeat, 1 CMask, 2 VMask */
+
+static void orc_cmask(OrcMaskCmd* c, uint32_t x0, uint32_t x1, uint32_t v) { c->x0 = x0; c->x1 = x1; c->type = 1; c->value = v; c->ptr = 0; }
+static void orc_vmask(OrcMaskCmd* c, uint32_t x0, uint32_t x1, const uint8_t* p) { c->x0 = x0; c->x1 = x1; c->type = 2; c->value = 0; c->ptr = p; }
+static void orc_end(OrcMaskCmd* c, uint32_t repeat) { c->x0 = repeat; c->x1 = 0; c->type = 0; c->value = 0; c->ptr = 0; }
+
+static void orc_write_mask_row(uint8_t* dst, uint32_t m) { memset(dst, 0, 4); memset(dst + 4, (int)m, 28); }     /* :520-539 */
+
+/* box = x0,y0,x1,y1 in 24.8; out_box = outer pixel box; masks = (out_box h) x (out_box w) bytes, row major. */
+ORC_API int orc_box_u_masks(const int32_t* box, uint32_t alpha, int32_t* out_box, uint8_t* masks, size_t masks_capacity) {
+  int x0 = box[0], y0 = box[1], x1 = box[2], y1 = box[3];
+  uint32_t ax0 = (uint32_t)x0 >> 8, ay0 = (uint32_t)y0 >> 8, ax1 = (uint32_t)(x1 + 0xFF) >> 8, ay1 = (uint32_t)(y1 + 0xFF) >> 8;
+  uint32_t fx0 = (uint32_t)x0 & 0xFF, fy0 = (uint32_t)y0 & 0xFF;
+  uint32_t fx1 = ((uint32_t)(x1 - 1) & 0xFF) + 1, fy1 = ((uint32_t)(y1 - 1) & 0xFF) + 1;
+  uint32_t w = ax1 - ax0, h = ay1 - ay0;
+  out_box[0] = (int)ax0; out_box[1] = (int)ay0; out_box[2] = (int)ax1; out_box[3] = (int)ay1;
+  if ((size_t)w * h > masks_capacity) return -1;
+  memset(masks, 0, (size_t)w * h);
+
+  fy0 = (h == 1 ? fy1 : 256u) - fy0;
+  uint32_t fy0_a = fy0 * alpha, fy1_a = fy1 * alpha;
+
+  OrcMaskCmd cmds[12];
+  uint8_t mask_data[96];
+  OrcMaskCmd* mc = cmds;
+  uint8_t* mp = mask_data;
+  int by0 = (int)ay0, by1 = (int)(ay0 + h);
+  int draw;
+  uint32_t span_x0 = ax0;                       /* left end of the spans (moves left when the mask run is padded) */
+
+  if (w == 1) {
+    fx0 = fx1 - fx0;
+    uint32_t m0 = (fx0 * fy0_a) >> 16;
+    orc_cmask(&mc[0], ax0, ax1, m0); orc_end(&mc[1], 1);
+    if (h == 1) draw = m0 != 0;
+    else {
+      mc += m0 ? 2 : 0; by0 += (m0 == 0);
+      uint32_t m1 = (fx0 * alpha) >> 8;
+      orc_cmask(&mc[0], ax0, ax1, m1); orc_end(&mc[1], h - 2);
+      mc += h > 2 ? 2 : 0;
+      uint32_t m2 = (fx0 * fy1_a) >> 16;
+      orc_cmask(&mc[0], ax0, ax1, m2); orc_end(&mc[1], 1);
+      by1 -= (m2 == 0);
+      draw = by0 < by1 && m1 != 0;
+    }
+  }
+  else {
+    uint32_t m0x1 = fy0_a >> 8, m1x1 = alpha, m2x1 = fy1_a >> 8;
+    fx0 = 256 - fx0;
+    if ((fx0 & fx1) == 256) {
+      orc_cmask(&mc[0], ax0, ax1, m0x1); orc_end(&mc[1], 1); mc += m0x1 ? 2 : 0; by0 += (m0x1 == 0);
+      orc_cmask(&mc[0], ax0, ax1, m1x1); orc_end(&mc[1], h - 2); mc += h > 2 ? 2 : 0;
+      orc_cmask(&mc[0], ax0, ax1, m2x1); orc_end(&mc[1], 1); by1 -= (m2x1 == 0);
+      draw = by0 < by1;
+    }
+    else {
+      uint32_t m0x0 = (fx0 * fy0_a) >> 16, m0x2 = (fx1 * fy0_a) >> 16;
+      uint32_t m1x0 = (fx0 * alpha) >> 8, m1x2 = (fx1 * alpha) >> 8;
+      uint32_t m2x0 = (fx0 * fy1_a) >> 16, m2x2 = (fx1 * fy1_a) >> 16;
+      orc_write_mask_row(mp + 0, m0x1); mp[0 + 4] = (uint8_t)m0x0;
+      orc_write_mask_row(mp + 32, m1x1); mp[32 + 4] = (uint8_t)m1x0;
+      orc_write_mask_row(mp + 64, m2x1); mp[64 + 4] = (uint8_t)m2x0;
+      mp += 4;
+      uint32_t w_align = (4u - (w & 3u)) & 3u;                                  /* IntOps::align_up_diff(w, 4) */
+      if (w_align > ax0) w_align = 0;
+      span_x0 = ax0 - w_align; w += w_align; mp -= w_align;
+      if (w <= 20) {
+        mp[0 + w - 1] = (uint8_t)m0x2; mp[32 + w - 1] = (uint8_t)m1x2; mp[64 + w - 1] = (uint8_t)m2x2;
+        orc_vmask(&mc[0], span_x0, ax1, mp + 0); orc_end(&mc[1], 1); mc += m0x1 ? 2 : 0; by0 += (m0x1 == 0);
+        orc_vmask(&mc[0], span_x0, ax1, mp + 32); orc_end(&mc[1], h - 2); mc += h > 2 ? 2 : 0;
+        orc_vmask(&mc[0], span_x0, ax1, mp + 64); orc_end(&mc[1], 1); by1 -= (m2x1 == 0);
+      }
+      else {
+        uint32_t inner_width = (w - 5) & ~7u;
+        uint32_t inner_end = span_x0 + 4 + inner_width;
+        uint32_t tail_width = ax1 - inner_end;
+        const uint8_t* tail = mp + 16 - tail_width;
+        mp[0 + 15] = (uint8_t)m0x2; mp[32 + 15] = (uint8_t)m1x2; mp[64 + 15] = (uint8_t)m2x2;
+        for (int rowk = 0; rowk < 3; rowk++) {
+          uint32_t inner = rowk == 0 ? m0x1 : rowk == 1 ? m1x1 : m2x1;
+          orc_vmask(&mc[0], span_x0, span_x0 + 4, mp + 32 * rowk);
+          orc_cmask(&mc[1], span_x0 + 4, inner_end, inner);
+          orc_vmask(&mc[2], inner_end, ax1, tail + 32 * rowk);
+          orc_end(&mc[3], rowk == 1 ? h - 2 : 1);
+          if (rowk == 0) { mc += m0x1 ? 4 : 0; by0 += (m0x1 == 0); }
+          else if (rowk == 1) mc += h > 2 ? 4 : 0;
+          else by1 -= (m2x1 == 0);
+        }
+      }
+      draw = by0 < by1;
+    }
+  }
+  if (!draw) return 0;
+
+  /* FillMask_Base::fill_func: walk the program for rows [by0, by1). */
+  OrcMaskCmd* cmd = cmds;
+  uint32_t rows_left = (uint32_t)(by1 - by0);
+  int y = by0;
+  for (;;) {
+    OrcMaskCmd* begin = cmd;
+    while (cmd->type != 0) {
+      for (uint32_t x = cmd->x0; x < cmd->x1; x++) {
+        uint32_t m = cmd->type == 1 ? cmd->value : cmd->ptr[x - cmd->x0];
+        if (x >= ax0) masks[(size_t)(y - (int)ay0) * (ax1 - ax0) + (x - ax0)] = (uint8_t)m;
+      }
+      cmd++;
+    }
+    uint32_t repeat = cmd->x0;
+    if (--rows_left == 0) break;
+    cmd++; y++;
+    repeat--;
+    cmd[-1].x0 = repeat;
+    if (repeat != 0) cmd = begin;
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Linear gradient, incremental form: spanInitY / spanStartX / fetch / advance_y (fetchgeneric_p.h:951-1010).
+ * Fills out[h][w] for the pixel rectangle starting at (x0, y0).  lut: u32[lut_size].
+ * ---------------------------------------------------------------------------------------------------------------- */
+ORC_API void orc_linear_gradient_rect(uint64_t pt0, uint64_t dy, uint64_t dt, uint32_t maxi, uint32_t rori, int is_pad,
+                                      const uint32_t* lut, int x0, int y0, int w, int h, uint32_t* out) {
+  uint64_t py = pt0 + (uint64_t)(uint32_t)y0 * dy;
+  for (int y = 0; y < h; y++) {
+    uint64_t pt = py + (uint64_t)(uint32_t)x0 * dt;
+    for (int x = 0; x < w; x++) {
+      uint32_t idx = (uint32_t)(pt >> 32);
+      if (is_pad) { int32_t v = (int32_t)idx; idx = (uint32_t)(v < 0 ? 0 : v > (int32_t)maxi ? (int32_t)maxi : v); }
+      else { uint32_t a = idx & maxi, b = (idx & maxi) ^ rori; idx = b < a ? b : a; }
+      pt += dt;
+      out[(size_t)y * (size_t)w + (size_t)x] = lut[idx];
+    }
+    py += dy;
+  }
+}

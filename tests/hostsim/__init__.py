@@ -55,3 +55,15 @@ def build_edges(ctx):
     lib().hostsim_build_edges(C.byref(view), edges, n, begins)
     arr = np.frombuffer(edges, dtype=np.int32).reshape(-1, 4)[:n].copy()
     return arr, np.frombuffer(begins, dtype=np.uint32).copy()
+
+
+def draw(scene, W, H, fmt=1, seed=1):
+    """Draws `scene` with the blend2d_b200 host frontend in record-only mode and renders the batch on the CPU simulator."""
+    import blend2d_b200 as G
+    img = G.Image(W, H, fmt)
+    ctx = G.Context(img, record_only=True)
+    scene(G, ctx, np.random.default_rng(seed))
+    render(ctx, img)
+    out = img.to_numpy().copy()
+    ctx.close()
+    return out

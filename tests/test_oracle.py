@@ -1,0 +1,217 @@
+"""Pins oracle/b2d_oracle.c (the C restatement) against the unmodified reference: first against committed vectors the
+reference produced (tests/golden/oracle_vectors.npz), then - where oracle/_ref is present - against the reference binary
+on a wider random sweep.  Finally uses the pinned oracle as the checker for the operators the reference build cannot
+execute (Plus / Multiply / Screen): host simulator here, the CUDA path under `-m gpu`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as O
+from tests import scenes as S
+
+V = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_vectors.npz"))
+W, H = 96, 64
+
+
+def fixed_box(x, y, w, h):
+    """The context converts a rect to 24.8 by truncating x * 256 (Math::trunc_to_int on the scaled coordinates)."""
+    return [int(x * 256), int(y * 256), int((x + w) * 256), int((y + h) * 256)]
+
+
+def alpha8(a):
+    return int(np.floor(a * 255 + 0.5))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# committed vectors
+# ---------------------------------------------------------------------------------------------------------------------
+def test_calc_mask_known_answers():
+    l = O.lib()
+    full = 0xFFFFFFFF
+    assert l.orc_calc_mask(256 << 9, full, 255) == 0            # empty accumulator
+    assert l.orc_calc_mask((256 << 9) + (256 << 9), full, 255) == 255
+    assert l.orc_calc_mask((256 << 9) - (256 << 9), full, 255) == 255   # negative winding
+    assert l.orc_calc_mask((256 << 9) + (128 << 9), full, 255) == 127
+    assert l.orc_calc_mask((256 << 9) + (512 << 9), full, 255) == 255   # non-zero saturates
+    assert l.orc_calc_mask((256 << 9) + (512 << 9), 0x1FF, 255) == 0    # even-odd wraps
+    assert l.orc_calc_mask((256 << 9) + (256 << 9), full, 128) == 128
+
+
+def test_polygon_masks_match_reference_vectors():
+    for pts, rule, mask in zip(V["poly_pts"], V["poly_rule"], V["poly_mask"]):
+        got = O.polygon_masks(pts, W, H, 0xFFFFFFFF if rule == 0 else 0x1FF)
+        assert np.array_equal(got, mask)
+
+
+def test_box_masks_match_reference_vectors():
+    for (x, y, w, h), a, mask in zip(V["box_rect"], V["box_alpha"], V["box_mask"]):
+        got = O.box_u_masks(fixed_box(x, y, w, h), alpha8(a), W, H)
+        assert np.array_equal(got, mask)
+
+
+@pytest.mark.parametrize("op", [O.SRC_OVER, O.SRC_COPY])
+def test_composite_matches_reference_vectors(op):
+    mask = V["comp_mask"]
+    assert np.array_equal(mask, O.polygon_masks(V["comp_pts"], W, H, alpha=alpha8(0.7)))
+    solid = int(V["comp_solid_prgb32"][0])
+    assert np.array_equal(O.composite_prgb32(op, V["comp_dst"], solid, mask), V[f"comp_out_op{op}_fmt1"])
+    assert np.array_equal(O.composite_a8(op, V["comp_dst8"], solid >> 24, mask), V[f"comp_out_op{op}_fmt3"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# live sweep against the reference binary
+# ---------------------------------------------------------------------------------------------------------------------
+def ref_mask(R, draw, w, h, alpha=1.0, rule=0):
+    img = R.Image(w, h, 3)
+    ctx = R.Context(img)
+    ctx.set_comp_op(1); ctx.set_fill_style(0xFFFFFFFF); ctx.set_global_alpha(alpha); ctx.set_fill_rule(rule)
+    draw(ctx); ctx.end()
+    return img.to_numpy().copy()
+
+
+def test_rasterizer_sweep_against_reference(ref):
+    rng = np.random.default_rng(77)
+    w, h = 200, 150
+    for it in range(200):
+        n = int(rng.integers(3, 14))
+        pts = rng.uniform(0, 1, (n, 2)) * [w, h]
+        if it % 3 == 0:
+            pts = np.round(pts * 4) / 4                  # many vertical / horizontal / pixel-aligned edges
+        if it % 7 == 0:
+            pts[:, 1] = np.round(pts[:, 1])              # shallow edges that end on scanline boundaries
+        rule = it & 1
+        a = 1.0 if it % 5 else 0.37
+        want = ref_mask(ref, lambda c: c.fill_polygon(pts.reshape(-1).tolist()), w, h, a, rule)
+        got = O.polygon_masks(pts, w, h, 0xFFFFFFFF if rule == 0 else 0x1FF, alpha8(a))
+        assert np.array_equal(want, got), f"polygon {it}"
+
+
+def test_box_u_sweep_against_reference(ref):
+    rng = np.random.default_rng(78)
+    w, h = 200, 150
+    for it in range(400):
+        x, y = rng.uniform(0, w - 60), rng.uniform(0, h - 60)
+        bw, bh = rng.uniform(0.01, 58), rng.uniform(0.01, 58)
+        if it % 4 == 0: bw = rng.uniform(0.01, 1.5)
+        if it % 5 == 0: bh = rng.uniform(0.01, 1.5)
+        if it % 7 == 0: x, bw = float(int(x)), float(int(bw) + 1)
+        a = 1.0 if it % 2 else float(rng.uniform(0, 1))
+        box = fixed_box(x, y, bw, bh)
+        if box[0] >= box[2] or box[1] >= box[3] or not ((box[0] | box[1] | box[2] | box[3]) & 0xFF):
+            continue
+        want = ref_mask(ref, lambda c: c.fill_rect_d(x, y, bw, bh), w, h, a)
+        assert np.array_equal(want, O.box_u_masks(box, alpha8(a), w, h)), f"box {it}"
+
+
+def linear_fetch_data(gpu, gtype_values, extend, stops, w, h):
+    """FetchData of a linear gradient as the blend2d_b200 host frontend initialises it (record-only context)."""
+    img = gpu.Image(w, h, 1)
+    ctx = gpu.Context(img, record_only=True)
+    g = gpu.Gradient(0, gtype_values, extend, stops)
+    ctx.set_comp_op(1); ctx.set_fill_style(g); ctx.fill_all()
+    view = ctx.peek_batch()
+    raw = bytes((C.c_uint8 * 176).from_address(view.fetch_data))
+    lut_ptr, lut_size = np.frombuffer(raw[:12], dtype=np.uint64, count=1)[0], np.frombuffer(raw[8:12], dtype=np.uint32)[0]
+    lut = np.ctypeslib.as_array((C.c_uint32 * int(lut_size)).from_address(int(lut_ptr))).copy()
+    pt0, _pt1, dy, dt = np.frombuffer(raw[16:48], dtype=np.uint64)
+    maxi, rori = np.frombuffer(raw[48:56], dtype=np.uint32)
+    ctx.close()
+    return int(pt0), int(dy), int(dt), int(maxi), int(rori), lut
+
+
+@pytest.mark.parametrize("extend", [0, 1, 2])
+def test_linear_gradient_against_reference(ref, extend):
+    import blend2d_b200 as G
+    w, h = 120, 90
+    stops = [(0.0, 0xFF102030), (0.4, 0x80FF8000), (1.0, 0xFF00C0FF)]
+    vals = [20.5, 10.25, 90.0, 70.75]
+    pt0, dy, dt, maxi, rori, lut = linear_fetch_data(G, vals, extend, stops, w, h)
+    got = O.linear_gradient_rect(pt0, dy, dt, maxi, rori, extend == 0, lut, 0, 0, w, h)
+    img = ref.Image(w, h, 1)
+    ctx = ref.Context(img)
+    ctx.set_comp_op(1); ctx.set_fill_style(ref.Gradient(0, vals, extend, stops)); ctx.fill_all(); ctx.end()
+    assert np.array_equal(got, img.to_numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Plus / Multiply / Screen: the oracle is the checker (unpinned against the reference - see oracle/b2d_oracle.c)
+# ---------------------------------------------------------------------------------------------------------------------
+def premul(rng, shape):
+    a = rng.integers(0, 256, shape).astype(np.uint32)
+    ch = [(rng.integers(0, 256, shape) * a // 255).astype(np.uint32) for _ in range(3)]
+    return (a << 24) | (ch[0] << 16) | (ch[1] << 8) | ch[2]
+
+
+def premultiply_rgba32(c):
+    """RgbaInternal: rgba32 -> premultiplied via udiv255 per channel (pixelops/scalar_p.h:34, 118-131)."""
+    a = c >> 24
+    f = lambda v: ((v * a + 0x80) * 0x101) >> 16
+    return (a << 24) | (f((c >> 16) & 0xFF) << 16) | (f((c >> 8) & 0xFF) << 8) | f(c & 0xFF)
+
+
+def jit_only_scene(op, backdrop, shapes):
+    def scene(api, ctx, rng):
+        ctx.image.from_numpy(backdrop) if hasattr(ctx, "image") else None
+        ctx.set_comp_op(op)
+        for pts, color, alpha in shapes:
+            ctx.set_fill_style(color); ctx.set_global_alpha(alpha)
+            ctx.fill_polygon(pts.reshape(-1).tolist())
+    return scene
+
+
+def expected_jit_only(op, backdrop, shapes, w, h):
+    out = backdrop.copy()
+    for pts, color, alpha in shapes:
+        mask = O.polygon_masks(pts, w, h, alpha=alpha8(alpha))
+        out = O.composite_prgb32(op, out, premultiply_rgba32(color), mask)
+    return out
+
+
+def make_shapes(seed, w, h, n=12):
+    rng = np.random.default_rng(seed)
+    backdrop = premul(rng, (h, w))
+    shapes = [(rng.uniform(0, 1, (7, 2)) * [w, h], int(rng.integers(0, 2 ** 32)), float(rng.choice([1.0, 0.8, 0.33])))
+              for _ in range(n)]
+    return backdrop, shapes
+
+
+@pytest.mark.parametrize("op", [O.SRC_OVER, O.SRC_COPY, O.PLUS, O.MULTIPLY, O.SCREEN])
+def test_hostsim_operators_against_oracle(op):
+    import blend2d_b200 as G
+    from tests import hostsim
+    w, h = 150, 100
+    backdrop, shapes = make_shapes(300 + op, w, h)
+    img = G.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = G.Context(img, record_only=True)
+    jit_only_scene(op, backdrop, shapes)(G, ctx, None)
+    hostsim.render(ctx, img)
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_jit_only(op, backdrop, shapes, w, h))
+
+
+def test_plus_saturates_and_screen_multiply_identities():
+    one = lambda op, d, s, m: int(O.lib().orc_composite_prgb32(op, d, s, m))
+    assert one(O.PLUS, 0xF0F0F0F0, 0x20202020, 255) == 0xFFFFFFFF
+    assert one(O.PLUS, 0x10203040, 0x01010101, 255) == 0x11213141
+    assert one(O.SCREEN, 0x00000000, 0x80402010, 255) == 0x80402010
+    assert one(O.SCREEN, 0xFFFFFFFF, 0x80402010, 255) == 0xFFFFFFFF
+    assert one(O.MULTIPLY, 0xFFFFFFFF, 0xFF804020, 255) == 0xFF804020       # white backdrop, opaque source: D*S
+    assert one(O.MULTIPLY, 0x00000000, 0xFF804020, 255) == 0xFF804020       # transparent backdrop: source shows
+    for op in (O.PLUS, O.SCREEN, O.MULTIPLY, O.SRC_OVER, O.SRC_COPY):
+        assert one(op, 0x80112233, 0xFF445566, 0) == 0x80112233
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", [O.SRC_OVER, O.SRC_COPY, O.PLUS, O.MULTIPLY, O.SCREEN])
+def test_gpu_operators_against_oracle(gpu, op):
+    w, h = 300, 200
+    backdrop, shapes = make_shapes(400 + op, w, h, 30)
+    img = gpu.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = gpu.Context(img)
+    jit_only_scene(op, backdrop, shapes)(gpu, ctx, None)
+    ctx.end()
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_jit_only(op, backdrop, shapes, w, h))
