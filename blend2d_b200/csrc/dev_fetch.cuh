@@ -307,6 +307,14 @@ B2D_HD uint32_t fetch_pixel(const FetchEnv& env, const RowCtx& rc, uint32_t x, u
   }
 }
 
+// Everything that is not a solid colour or a nearest-neighbour gradient (dithered gradients, all patterns): kept out of
+// line so that the compositor's hot loop stays small (see B2D_HD_COLD).
+B2D_HD_COLD uint32_t fetch_pixel_cold(const FetchEnv& env, uint32_t x, uint32_t y) {
+  RowCtx rc;
+  fetch_row_init(env, y, rc);
+  return fetch_pixel(env, rc, x, y);
+}
+
 // Fetches the (up to) 4 consecutive pixels x..x+3 of row y whose mask is non-zero.  The fetch-type dispatch is hoisted
 // out of the pixel loop: a command is uniform over the whole CTA, so every warp takes the same branch.
 B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* m, uint32_t* s) {
@@ -315,56 +323,51 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     s[0] = s[1] = s[2] = s[3] = env.solid;
     return;
   }
-  if (ft >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD && ft <= B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_ROR) {
+  if (ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD || ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_ROR) {
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
     const b2dgpu_gradient_linear& l = g.linear;
-    const bool pad = (ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD) || (ft == B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_PAD);
-    const bool dither = ft >= B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_PAD;
-    uint64_t pt = l.pt[0].u64 + uint64_t(y) * l.dy.u64 + uint64_t(x) * l.dt.u64;
+    const bool pad = ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD;
+    const uint32_t maxi = l.maxi, rori = l.rori;
+    const uint64_t dt = l.dt.u64;
+    uint64_t pt = l.pt[0].u64 + uint64_t(y) * l.dy.u64 + uint64_t(x) * dt;
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (m[i]) {
         uint32_t idx = uint32_t(pt >> 32);
-        idx = pad ? grad_index_pad(idx, l.maxi) : grad_index_ror(idx, l.maxi, l.rori);
-        s[i] = dither ? lut_fetch_dither(env, g, idx, x + i, y) : lut_fetch_nn(g, idx);
+        idx = pad ? grad_index_pad(idx, maxi) : grad_index_ror(idx, maxi, rori);
+        s[i] = lut_fetch_nn(g, idx);
       }
-      pt += l.dt.u64;
+      pt += dt;
     }
     return;
   }
-  if (ft >= B2DGPU_FETCH_GRADIENT_RADIAL_NN_PAD && ft <= B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_ROR) {
+  if (ft == B2DGPU_FETCH_GRADIENT_RADIAL_NN_PAD || ft == B2DGPU_FETCH_GRADIENT_RADIAL_NN_ROR) {
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
     const b2dgpu_gradient_radial& r = g.radial;
-    const bool pad = (ft == B2DGPU_FETCH_GRADIENT_RADIAL_NN_PAD) || (ft == B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_PAD);
-    const bool dither = ft >= B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_PAD;
+    const bool pad = ft == B2DGPU_FETCH_GRADIENT_RADIAL_NN_PAD;
     const RadialRow row = radial_row(r, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (m[i]) {
         uint32_t idx = radial_index(r, row, x + i);
         idx = pad ? grad_index_pad(idx, r.maxi) : grad_index_ror(idx, r.maxi, r.rori);
-        s[i] = dither ? lut_fetch_dither(env, g, idx, x + i, y) : lut_fetch_nn(g, idx);
+        s[i] = lut_fetch_nn(g, idx);
       }
     }
     return;
   }
-  if (ft >= B2DGPU_FETCH_GRADIENT_CONIC_NN) {
+  if (ft == B2DGPU_FETCH_GRADIENT_CONIC_NN) {
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
-    const bool dither = ft == B2DGPU_FETCH_GRADIENT_CONIC_DITHER;
     const ConicRow row = conic_row(g.conic, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (m[i]) {
-        uint32_t idx = conic_index(g.conic, row, x + i);
-        s[i] = dither ? lut_fetch_dither(env, g, idx, x + i, y) : lut_fetch_nn(g, idx);
-      }
+      if (m[i]) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
     }
     return;
   }
-  RowCtx rc;
-  #pragma unroll
+  #pragma unroll 1
   for (int i = 0; i < 4; i++)
-    if (m[i]) s[i] = fetch_pixel(env, rc, x + i, y);
+    if (m[i]) s[i] = fetch_pixel_cold(env, x + i, y);
 }
 
 } // namespace b2d

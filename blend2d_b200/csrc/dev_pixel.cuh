@@ -15,13 +15,39 @@ namespace b2d {
 // Two 16-bit lanes in one 32-bit word.
 struct Lanes2 { uint32_t rb, ag; };
 
-B2D_HD Lanes2 unpack(uint32_t p) { return Lanes2{ p & 0x00FF00FFu, (p >> 8) & 0x00FF00FFu }; }
-B2D_HD uint32_t pack(Lanes2 u) { return (u.rb & 0x00FF00FFu) | ((u.ag & 0x00FF00FFu) << 8); }
+// (u >> 8) & 0x00FF00FF: the high byte of each 16-bit lane.  One PRMT on the GPU instead of shift + mask.
+B2D_HD uint32_t lanes_hi(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(u, 0u, 0x4341);
+#else
+  return (u >> 8) & 0x00FF00FFu;
+#endif
+}
+
+B2D_HD Lanes2 unpack(uint32_t p) { return Lanes2{ p & 0x00FF00FFu, lanes_hi(p) }; }
+B2D_HD uint32_t pack(Lanes2 u) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(u.rb, u.ag, 0x6240);                 // bytes {rb.0, ag.0, rb.2, ag.2}; high lane bytes are dropped
+#else
+  return (u.rb & 0x00FF00FFu) | ((u.ag & 0x00FF00FFu) << 8);
+#endif
+}
 
 // ((x + 128) + ((x + 128) >> 8)) >> 8 on each 16-bit lane; exact for lane values <= 65025 + 254.
 B2D_HD uint32_t div255_2(uint32_t x) {
   uint32_t u = x + 0x00800080u;
-  return ((u + ((u >> 8) & 0x00FF00FFu)) >> 8) & 0x00FF00FFu;
+  return lanes_hi(u + lanes_hi(u));
+}
+
+// pack(div255(a)) with the final ">> 8 & mask" of both lane pairs folded into the packing permute.
+B2D_HD uint32_t pack_div255(Lanes2 a) {
+  uint32_t u0 = a.rb + 0x00800080u, u1 = a.ag + 0x00800080u;
+  uint32_t t0 = u0 + lanes_hi(u0), t1 = u1 + lanes_hi(u1);
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(t0, t1, 0x7351);                     // bytes {t0.1, t1.1, t0.3, t1.3}
+#else
+  return ((t0 >> 8) & 0x00FF00FFu) | (t1 & 0xFF00FF00u);
+#endif
 }
 B2D_HD uint32_t div256_2(uint32_t x) { return (x >> 8) & 0x00FF00FFu; }
 
@@ -51,15 +77,21 @@ B2D_HD uint32_t jit_div255_u16(uint32_t x) { return (((x + 0x80u) & 0xFFFFu) * 0
 B2D_HD uint32_t comp_src_copy(uint32_t d, uint32_t s, uint32_t m) {
   Lanes2 du = unpack(d), su = unpack(s);
   uint32_t im = m ^ 0xFFu;
-  return pack(div255(add(mul(du, im), mul(su, m))));
+  return pack_div255(add(mul(du, im), mul(su, m)));
 }
 
 // SrcOver: s' = (s*m).div255(); d' = s' + (d*(255 - s'.a)).div255()        compopgeneric_p.h:54-62
 // The final "+" is a plain 32-bit add of packed pixels in the reference; kept as such.
 B2D_HD uint32_t comp_src_over(uint32_t d, uint32_t s, uint32_t m) {
-  uint32_t sm = pack(div255(mul(unpack(s), m)));
+  uint32_t sm = pack_div255(mul(unpack(s), m));
   uint32_t ia = (sm >> 24) ^ 0xFFu;
-  return sm + pack(div255(mul(unpack(d), ia)));
+  return sm + pack_div255(mul(unpack(d), ia));
+}
+
+// The same operator at m == 255: div255(s * 255) == s for every 8-bit s, so the first half is the identity.
+B2D_HD uint32_t comp_src_over_opaque_mask(uint32_t d, uint32_t s) {
+  uint32_t ia = (s >> 24) ^ 0xFFu;
+  return s + pack_div255(mul(unpack(d), ia));
 }
 
 // Plus: addus8(d, (s*m).div255())                                          compopgeneric_p.h:74-80
@@ -114,29 +146,41 @@ B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) 
   }
 }
 
-// d[i] = op(d[i], s[i], m[i]) for the pixels whose mask is non-zero; operator dispatch hoisted out of the loop.
-B2D_HD void composite4(uint32_t comp_op, uint32_t* d, const uint32_t* s, const uint32_t* m) {
+// The operators outside the hot loop's instruction footprint (see B2D_HD_COLD).
+B2D_HD_COLD uint32_t composite_cold(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) {
   switch (comp_op) {
-    case kOpSrcOver:
+    case kOpPlus:     return comp_plus(d, s, m);
+    case kOpMultiply: return comp_multiply(d, s, m);
+    default:          return comp_screen(d, s, m);
+  }
+}
+
+// d[i] = op(d[i], s[i], m[i]) for the pixels whose mask is non-zero; operator dispatch hoisted out of the loop.
+// `all_opaque`: every non-zero m[i] the caller passes is 255 (decided per warp, so the branch never diverges).
+B2D_HD void composite4(uint32_t comp_op, uint32_t* d, const uint32_t* s, const uint32_t* m, bool all_opaque = false) {
+  if (comp_op == kOpSrcOver) {
+    if (all_opaque) {
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_over_opaque_mask(d[i], s[i]);
+    }
+    else {
       #pragma unroll
       for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_over(d[i], s[i], m[i]);
-      break;
-    case kOpSrcCopy:
+    }
+  }
+  else if (comp_op == kOpSrcCopy) {
+    if (all_opaque) {
+      #pragma unroll
+      for (int i = 0; i < 4; i++) if (m[i]) d[i] = s[i];                 // div255(s * 255) == s
+    }
+    else {
       #pragma unroll
       for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_copy(d[i], s[i], m[i]);
-      break;
-    case kOpPlus:
-      #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_plus(d[i], s[i], m[i]);
-      break;
-    case kOpMultiply:
-      #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_multiply(d[i], s[i], m[i]);
-      break;
-    default:
-      #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_screen(d[i], s[i], m[i]);
-      break;
+    }
+  }
+  else {
+    #pragma unroll 1
+    for (int i = 0; i < 4; i++) if (m[i]) d[i] = composite_cold(comp_op, d[i], s[i], m[i]);
   }
 }
 

@@ -54,6 +54,8 @@ B2D_HD void err_step_u(uint32_t& acc, int& iter, int step, int correction) {
 
 // q = a / b, r = a % b for a < 2^64; takes the 32-bit divider whenever the dividend fits (always the case for
 // canvases up to 65535 px: coordinates are below 2^24 in 24.8 fixed point).
+B2D_HD_COLD uint64_t udiv64_wide(uint64_t a, uint32_t b) { return a / b; }
+
 B2D_HD void udivmod64(uint64_t a, uint32_t b, uint32_t& q, uint32_t& r) {
   if ((a >> 32) == 0) {
     uint32_t a32 = uint32_t(a);
@@ -61,7 +63,7 @@ B2D_HD void udivmod64(uint64_t a, uint32_t b, uint32_t& q, uint32_t& r) {
     r = a32 - q * b;
   }
   else {
-    uint64_t q64 = a / b;
+    uint64_t q64 = udiv64_wide(a, b);
     q = uint32_t(q64);
     r = uint32_t(a - q64 * b);
   }

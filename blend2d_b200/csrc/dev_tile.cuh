@@ -100,6 +100,19 @@ B2D_HD void tile_left_cover(const NormEdge& ed, int ty0, uint32_t* left_acc) {
   }
 }
 
+// Columns an edge can touch inside the band of rows [band_y, band_y + kTileH): cells [min >> 8, (max >> 8) + 1]
+// (cell_merge writes x and x + 1) of the edge's part inside the band, with one more column of slack on each side for
+// the DDA's rounding.  Used by k_band_extents to cull (tile, command) pairs; must never be too tight.
+B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi) {
+  const long long dx = (long long)ed.x1 - ed.x0, dy = (long long)ed.y1 - ed.y0;
+  const int ya = tmax(ed.y0, band_y << 8);
+  const int yb = tmin(ed.y1, (band_y + kTileH) << 8);
+  const int xa = ed.x0 + int(dx * (ya - ed.y0) / dy);
+  const int xb = ed.x0 + int(dx * (yb - ed.y0) / dy);
+  lo = tmax((tmin(xa, xb) >> 8) - 1, 0);
+  hi = tmax((tmax(xa, xb) >> 8) + 2, 0);
+}
+
 // Rasterizes the tile's rows of a straddling edge through `store`.  Returns true when anything was written.
 template<typename Store>
 B2D_HD bool tile_rasterize_edge(const NormEdge& ed, int tx0, int ty0, Store& store) {

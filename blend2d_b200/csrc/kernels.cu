@@ -249,6 +249,52 @@ __global__ void k_finalize_commands(FinalizeParams P) {
 }
 
 // =================================================================================================================
+// K1d - per (command, band) x-extents
+//
+// A band is one tile row (kTileH scanlines).  For every band a command's bounding box covers, the columns its edges
+// can touch inside that band are recorded as (min cell x, ~max cell x).  The compositor culls (tile, command) pairs
+// with it: a tile left of the extent sees nothing, a tile right of it sees every edge of the band on its left, and
+// the covers of a closed outline sum to zero on every scanline (EdgeBuilder closes figures and keeps clipped parts as
+// border lines, edgebuilder_p.h:1058-1062, 2546-2622) - so both are skipped.  This replaces the reference's per-band
+// edge lists (edgestorage_p.h:38-178) as the structure that keeps work proportional to the shape, not to its box.
+// =================================================================================================================
+__device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, uint32_t index) {
+  int4 ev = __ldg(edges + index);
+  b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
+  return normalize_edge(raw);
+}
+
+__global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __restrict__ band_ext) {
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (c >= P.command_count) return;
+  const int4 bb = P.cmd_bbox_px[c];
+  if (bb.x >= bb.z || bb.y >= bb.w) return;
+  const int band0 = (bb.y - P.y_begin) >> 3, band1 = (bb.w - 1 - P.y_begin) >> 3;
+  uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
+  if (P.commands[c].type < B2DGPU_CMD_FILL_ANALYTIC) {
+    for (int b = band0 + int(lane); b <= band1; b += 32)
+      band_ext[size_t(b) * P.command_count + c] = make_uint2(0u, 0u);               // every column
+    return;
+  }
+  const uint2 er = P.cmd_edges[c];
+  const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
+  for (uint32_t e = lane; e < er.y; e += 32) {
+    const NormEdge ne = load_edge(edges, er.x + e);
+    if (ne.y0 == ne.y1) continue;
+    const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
+    if (row_first > row_last) continue;
+    for (int b = (row_first - P.y_begin) >> 3; b <= ((row_last - P.y_begin) >> 3); b++) {
+      int lo, hi;
+      band_edge_extent(ne, P.y_begin + b * kTileH, lo, hi);
+      uint32_t* cell = ext + (size_t(b) * P.command_count + c) * 2;
+      atomicMin(cell, uint32_t(lo));
+      atomicMin(cell + 1, ~uint32_t(hi));
+    }
+  }
+}
+
+// =================================================================================================================
 // K2 + K3 - tile compositor
 // =================================================================================================================
 
@@ -261,7 +307,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 64, kEntCap = 8 };
+enum : int { kSubChunk = 64, kEntCap = 8, kRing = 512 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 
 struct PreCmd {
@@ -294,17 +340,30 @@ struct EntrySink {
   }
 };
 
-__device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, uint32_t index) {
-  int4 ev = __ldg(edges + index);
-  b2dgpu_edge raw; raw.x0 = ev.x; raw.y0 = ev.y; raw.x1 = ev.z; raw.y1 = ev.w;
-  return normalize_edge(raw);
+// Slow path of the replay (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
+// rasterizes its own row into its private shared-memory cell row.  Out of line: it is rare and large.
+__device__ __noinline__ uint4 slow_row_cells(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int py, int row,
+                                             int lane, uint32_t* cells_row, uint32_t* carry_row) {
+  *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(0, 0, 0, 0);
+  if (lane == 0) *carry_row = 0;
+  __syncwarp();
+  SmemRowStore store{ cells_row, carry_row };
+  TileSink<SmemRowStore> sink(store, tx0);
+  sink.row = row;
+  for (uint32_t e = lane; e < er.y; e += 32) {
+    NormEdge ne = load_edge(edges, er.x + e);
+    if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
+      tile_rasterize_edge_row(ne, py, sink);
+  }
+  __syncwarp();
+  return *reinterpret_cast<uint4*>(cells_row + lane * 4);
 }
 
 template<int BPP>
 __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
   __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
   __shared__ uint32_t s_carry[kTileH];
-  __shared__ uint32_t s_list[kTileThreads];
+  __shared__ uint32_t s_list[kRing];
   __shared__ __align__(16) PreCmd s_pre[kSubChunk];
   __shared__ uint32_t s_wcount[kTileH];
 
@@ -334,35 +393,48 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
   bool dirty = false;
   uint32_t px_written = 0;
 
-  for (uint32_t base = 0; base < P.command_count; base += kTileThreads) {
+  // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSubChunk of them are
+  // pending (or the command list ends) they are classified (phase 1) and replayed (phase 2).
+  uint32_t ring_head = 0, ring_tail = 0;                // block-uniform
+  for (uint32_t base = 0; base < P.command_count || ring_head != ring_tail; base += kTileThreads) {
     // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
-    uint32_t c = base + tid;
-    bool hit = false;
-    if (c < P.command_count) {
-      int4 bb = P.cmd_bbox_px[c];
-      hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
+    if (base < P.command_count) {
+      uint32_t c = base + tid;
+      bool hit = false;
+      if (c < P.command_count) {
+        int4 bb = P.cmd_bbox_px[c];
+        hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
+        if (hit && P.band_ext) {
+          const uint2 ex = P.band_ext[size_t(tile_y) * P.command_count + c];
+          hit = uint32_t(tx0 + kTileW) > ex.x && uint32_t(tx0) <= ~ex.y;
+        }
+      }
+      uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+      __syncthreads();                                  // everybody is done reading s_wcount of the previous chunk
+      if (lane == 0) s_wcount[row] = __popc(ballot);
+      __syncthreads();
+      uint32_t wbase = 0, total = 0;
+      #pragma unroll
+      for (int w = 0; w < kTileH; w++) {
+        uint32_t cnt = s_wcount[w];
+        if (w < row) wbase += cnt;
+        total += cnt;
+      }
+      if (hit) s_list[(ring_tail + wbase + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1)] = c;
+      ring_tail += total;
     }
-    uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-    __syncthreads();                                    // the previous chunk is done with s_list / s_wcount
-    if (lane == 0) s_wcount[row] = __popc(ballot);
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
-    #pragma unroll
-    for (int w = 0; w < kTileH; w++) {
-      uint32_t cnt = s_wcount[w];
-      if (w < row) wbase += cnt;
-      total += cnt;
-    }
-    if (hit) s_list[wbase + __popc(ballot & ((1u << lane) - 1u))] = c;
+    const bool last = base + kTileThreads >= P.command_count;
 
-    for (uint32_t sub = 0; sub < total; sub += kSubChunk) {
-      const uint32_t sub_n = min(uint32_t(kSubChunk), total - sub);
-      __syncthreads();                                  // s_list written / previous sub-chunk's s_pre consumed
+    while (ring_tail - ring_head >= uint32_t(kSubChunk) || (last && ring_tail != ring_head)) {
+      const uint32_t sub = ring_head;
+      const uint32_t sub_n = min(uint32_t(kSubChunk), ring_tail - ring_head);
+      ring_head += sub_n;
+      __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
       for (uint32_t k = row; k < sub_n; k += kTileH) {
-        const uint32_t ci = s_list[sub + k];
+        const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
         if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; }
         if (lane == 0) pre->flags = 0;
@@ -427,7 +499,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
         uint32_t k;
         if (act_lo) { k = uint32_t(__ffs(act_lo) - 1); act_lo &= act_lo - 1; }
         else { k = 32u + uint32_t(__ffs(act_hi) - 1); act_hi &= act_hi - 1; }
-        const uint32_t ci = s_list[sub + k];
+        const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         const b2dgpu_command& cmd = P.commands[ci];
         const uint32_t type = cmd.type;
         const uint32_t alpha = cmd.alpha;
@@ -470,22 +542,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
               }
             }
             else {
-              // Slow path (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
-              // rasterizes its own row into its private shared-memory cell row.
-              *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]) = make_uint4(0, 0, 0, 0);
-              if (lane == 0) s_carry[row] = 0;
-              __syncwarp();
-              const uint2 er = P.cmd_edges[ci];
-              SmemRowStore store{ &s_cells[row][0], &s_carry[row] };
-              TileSink<SmemRowStore> sink(store, tx0);
-              sink.row = row;
-              for (uint32_t e = lane; e < er.y; e += 32) {
-                NormEdge ne = load_edge(edges, er.x + e);
-                if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
-                  tile_rasterize_edge_row(ne, py, sink);
-              }
-              __syncwarp();
-              uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
+              uint4 cv = slow_row_cells(edges, P.cmd_edges[ci], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
               c0 = cv.x; c1 = cv.y; c2 = cv.z; c3 = cv.w;
               carry += s_carry[row];
               __syncwarp();
@@ -512,7 +569,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
         }
 
         // ---- fetch + composite ----
-        if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
+        // Warp-uniform exit: the lanes stay converged for the votes / shuffles of this and the next iteration.
+        if (!__any_sync(0xFFFFFFFFu, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
 
         const uint32_t sig = cmd.signature;
         FetchEnv env;
@@ -529,7 +587,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
           #pragma unroll
           for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
         }
-        composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
+        const bool opaque = __all_sync(0xFFFFFFFFu, ((m[0] + 1u) & 0xFEu) + ((m[1] + 1u) & 0xFEu) + ((m[2] + 1u) & 0xFEu) + ((m[3] + 1u) & 0xFEu) == 0u);
+        composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m, opaque);
         px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
         dirty = true;
       }
@@ -713,6 +772,12 @@ int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count
   if (grid < 1) grid = 1;
   if (bpp == 4) k_box_stream<4><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
   else k_box_stream<1><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
+  return 1;
+}
+
+int launch_band_extents(const TileParams& P, uint2* band_ext, cudaStream_t s) {
+  if (!P.command_count) return 0;
+  k_band_extents<<<div_up(P.command_count * 32, 256), 256, 0, s>>>(P, band_ext);
   return 1;
 }
 

@@ -43,6 +43,8 @@ struct TileParams {
   uint32_t command_count;
   const int4* cmd_bbox_px;
   const uint2* cmd_edges;
+  const uint2* band_ext;                  // [tile row][command]: (min cell x, ~max cell x) of the command's edges in that
+                                          // band of 8 rows; nullptr = not built (cull by bounding box only)
   const b2dgpu_edge* edges;
   const b2dgpu_fetch_data* fetch_data;
   const uint8_t* bayer;
@@ -58,6 +60,7 @@ int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_
 int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
 int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
+int launch_band_extents(const TileParams& P, uint2* band_ext, cudaStream_t s);
 int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s);
 int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
 

@@ -103,6 +103,7 @@ struct b2dgpu_runtime {
   int staging_next;
   DevBuffer oneshot_block;                  // device block reused by b2dgpu_submit()
   DevBuffer oneshot_edges;
+  DevBuffer band_ext;                       // [tile row][command] x-extents (k_band_extents), rebuilt by every render
   PinnedBuffer image_staging;
 
   b2dgpu_stats stats;
@@ -279,6 +280,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   rt->image_staging.release();
   rt->oneshot_block.release();
   rt->oneshot_edges.release();
+  rt->band_ext.release();
   if (rt->own_stream) cudaStreamDestroy(rt->stream);
   rt->magic = 0;
   delete rt;
@@ -721,6 +723,20 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
   T.origin_x = in.origin_x;
   T.origin_y = in.origin_y;
   T.pixel_counter = rt->d_pixel_counter;
+  T.band_ext = nullptr;
+  // Per (band, command) x-extents: only worth building when some command has edges (a box's bounding box is exact) and
+  // while the table stays small (8 B per cell; 10 000 commands on a 4K canvas = 21.6 MB).
+  const size_t band_cells = size_t(in.command_count) * size_t(T.tiles_y);
+  if ((in.has_analytic || in.segment_count) && band_cells <= (size_t(64) << 20)) {
+    const size_t need = band_cells * sizeof(uint2);
+    if (need > rt->band_ext.cap) {
+      CU_TRY(cudaStreamSynchronize(s));
+      CU_TRY(rt->band_ext.ensure(need + need / 4));
+    }
+    CU_TRY(cudaMemsetAsync(rt->band_ext.ptr, 0xFF, need, s));
+    launches += launch_band_extents(T, static_cast<uint2*>(rt->band_ext.ptr), s);
+    T.band_ext = static_cast<const uint2*>(rt->band_ext.ptr);
+  }
   if (rt->profiling) CU_TRY(cudaEventRecord(ev[1], s));
   bool streamed = false;
   if (in.stream_ok) {

@@ -106,6 +106,29 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
   }
 
   const int tiles_x = (w + kTileW - 1) / kTileW, tiles_y = (h + kTileH - 1) / kTileH;
+
+  // K1d (k_band_extents): columns each command's edges can touch per band of kTileH rows.
+  std::vector<int> ext_lo(size_t(tiles_y) * B->command_count, INT_MAX), ext_hi(size_t(tiles_y) * B->command_count, -1);
+  for (uint32_t c = 0; c < B->command_count; c++) {
+    const CmdBox& bb = boxes[c];
+    if (bb.x0 >= bb.x1 || bb.y0 >= bb.y1) continue;
+    if (B->commands[c].type < B2DGPU_CMD_FILL_ANALYTIC) {
+      for (int b = bb.y0 >> 3; b <= (bb.y1 - 1) >> 3; b++) { ext_lo[size_t(b) * B->command_count + c] = 0; ext_hi[size_t(b) * B->command_count + c] = INT_MAX; }
+      continue;
+    }
+    for (uint32_t e = 0; e < e_count[c]; e++) {
+      NormEdge ne = normalize_edge(edges[e_begin[c] + e]);
+      if (ne.y0 == ne.y1) continue;
+      const int row_first = tmax(ne.y0 >> 8, bb.y0), row_last = tmin((ne.y1 - 1) >> 8, bb.y1 - 1);
+      for (int b = row_first >> 3; row_first <= row_last && b <= (row_last >> 3); b++) {
+        int lo, hi;
+        band_edge_extent(ne, b * kTileH, lo, hi);
+        int& l = ext_lo[size_t(b) * B->command_count + c]; l = tmin(l, lo);
+        int& hh = ext_hi[size_t(b) * B->command_count + c]; hh = tmax(hh, hi);
+      }
+    }
+  }
+
   static HostStore store;
   for (int ty = 0; ty < tiles_y; ty++) for (int tx = 0; tx < tiles_x; tx++) {
     const int tx0 = tx * kTileW, ty0 = ty * kTileH;
@@ -113,6 +136,7 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
     for (uint32_t c = 0; c < B->command_count; c++) {
       const CmdBox& bb = boxes[c];
       if (!(bb.x0 < tx0 + kTileW && bb.x1 > tx0 && bb.y0 < ty0 + kTileH && bb.y1 > ty0)) continue;
+      if (!(tx0 + kTileW > ext_lo[size_t(ty) * B->command_count + c] && tx0 <= ext_hi[size_t(ty) * B->command_count + c])) continue;
       const b2dgpu_command& cmd = B->commands[c];
       const uint32_t sig = cmd.signature, alpha = cmd.alpha;
       uint32_t masks[kTileH][kTileW];
