@@ -379,7 +379,7 @@ def run_gpu(args):
             "clocks": clocks,
             "pixels_per_step": px_per_step, "canvas_checksum": checksum,
             "roofline_full_canvas": None if full is None else {
-                k: {"bound": "hbm", "kernel": "k_box_stream<4>", "achieved": v["gbs"], "peak": peak, "unit": "GB/s",
+                k: {"bound": "hbm", "kernel": "k_stream_solid<SrcOver>", "achieved": v["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": v["gbs"] / peak, "kernel_ms": v["ms"], "algorithmic_bytes_per_launch": v["bytes"],
                     "workload": v["what"]} for k, v in full.items()},
         }

@@ -698,6 +698,79 @@ __global__ void __launch_bounds__(256) k_box_stream(TileParams P, int rows, int 
 }
 
 // =================================================================================================================
+// K3f - one solid box fill over a large region: FillBoxA + FetchSolid + SrcOver / SrcCopy (compositeCSpan of
+// compopgeneric_p.h:104-122 with a constant source and a constant mask).
+//
+// Everything that does not depend on the destination is folded on the host side of the launch into two constants:
+//   SrcOver  d' = sm + div255(d * ia)          sm = div255(s * m), ia = 255 - sm.a
+//   SrcCopy  d' = div255(d * (255 - m) + s*m)  (m == 255: d' = s, the destination is not even read)
+// which leaves ~11 integer instructions per pixel, few registers (full occupancy) and four 16-byte loads in flight
+// per thread: the kernel is bound by HBM (8 B per pixel, 4 B for the store-only case).  An A8 target is processed as
+// 32-bit words of four pixels: the per-byte arithmetic of SrcOver / SrcCopy is the same for a channel and for an A8
+// pixel (pixelgeneric_p.h:85-200 vs :292-405), and no byte ever overflows into its neighbour.
+// =================================================================================================================
+enum : int { kSolidUnroll = 4 };
+
+template<int MODE>
+__device__ __forceinline__ uint32_t solid_word(uint32_t d, uint32_t k0, uint32_t k1, uint32_t k2) {
+  if (MODE == 0) return k0 + pack_div255(mul(unpack(d), k1));                              // k0 = sm, k1 = ia
+  return pack_div255(Lanes2{ (d & 0x00FF00FFu) * k2 + k0, lanes_hi(d) * k2 + k1 });        // k0/k1 = s*m lanes, k2 = 255 - m
+}
+
+template<int MODE>
+__global__ void __launch_bounds__(256) k_stream_solid(SolidStreamParams P, int chunks_per_row, int c0, int step_r, int step_c) {
+  // Constants of the fill.
+  uint32_t k0, k1, k2 = 0;
+  if (MODE == 0) { k0 = pack_div255(mul(unpack(P.src), P.mask)); k1 = (k0 >> 24) ^ 0xFFu; }
+  else { Lanes2 sm = mul(unpack(P.src), P.mask); k0 = sm.rb; k1 = sm.ag; k2 = P.mask ^ 0xFFu; }
+  if (MODE == 2) k0 = P.src;
+
+  // Chunk = four 32-bit words.  The linear chunk index advances by a fixed stride; (row, column) follow it without
+  // a division: stride = step_r rows + step_c columns (computed by the launcher).
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int r = int(tid / chunks_per_row);
+  int c = int(tid - (long long)r * chunks_per_row);
+  const int rows = P.y1 - P.y0;
+
+  while (r < rows) {
+    uint4 v[kSolidUnroll];
+    uint4* ptr[kSolidUnroll];
+    int cw[kSolidUnroll];
+    #pragma unroll
+    for (int u = 0; u < kSolidUnroll; u++) {
+      ptr[u] = nullptr;
+      if (r < rows) {
+        cw[u] = (c0 + c) * 4;
+        ptr[u] = reinterpret_cast<uint4*>(P.dst + size_t(P.y0 + r) * P.dst_stride) + (c0 + c);
+        if (MODE != 2 || cw[u] < P.x0w || cw[u] + 4 > P.x1w) v[u] = *ptr[u];
+      }
+      c += step_c; r += step_r;
+      if (c >= chunks_per_row) { c -= chunks_per_row; r++; }
+    }
+    #pragma unroll
+    for (int u = 0; u < kSolidUnroll; u++) {
+      if (!ptr[u]) continue;
+      uint4 o;
+      if (cw[u] >= P.x0w && cw[u] + 4 <= P.x1w) {
+        if (MODE == 2) o = make_uint4(k0, k0, k0, k0);
+        else o = make_uint4(solid_word<MODE>(v[u].x, k0, k1, k2), solid_word<MODE>(v[u].y, k0, k1, k2),
+                            solid_word<MODE>(v[u].z, k0, k1, k2), solid_word<MODE>(v[u].w, k0, k1, k2));
+      }
+      else {
+        // chunk cut by the left / right end of the box
+        o = v[u];
+        if (cw[u] + 0 >= P.x0w && cw[u] + 0 < P.x1w) o.x = MODE == 2 ? k0 : solid_word<MODE>(o.x, k0, k1, k2);
+        if (cw[u] + 1 >= P.x0w && cw[u] + 1 < P.x1w) o.y = MODE == 2 ? k0 : solid_word<MODE>(o.y, k0, k1, k2);
+        if (cw[u] + 2 >= P.x0w && cw[u] + 2 < P.x1w) o.z = MODE == 2 ? k0 : solid_word<MODE>(o.z, k0, k1, k2);
+        if (cw[u] + 3 >= P.x0w && cw[u] + 3 < P.x1w) o.w = MODE == 2 ? k0 : solid_word<MODE>(o.w, k0, k1, k2);
+      }
+      *ptr[u] = o;
+    }
+  }
+  if (tid == 0) atomicAdd(P.pixel_counter, P.pixels);
+}
+
+// =================================================================================================================
 // Launchers (host)
 // =================================================================================================================
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -772,6 +845,30 @@ int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count
   if (grid < 1) grid = 1;
   if (bpp == 4) k_box_stream<4><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
   else k_box_stream<1><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
+  return 1;
+}
+
+int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s) {
+  const int c0 = P.x0w / 4, c1 = (P.x1w + 3) / 4;
+  const int chunks_per_row = c1 - c0, rows = P.y1 - P.y0;
+  if (chunks_per_row <= 0 || rows <= 0) return 0;
+  const long long total = (long long)rows * chunks_per_row;
+  // Persistent grid: exactly the CTAs that are resident at once (one wave, no tail).
+  static int per_sm[3] = { 0, 0, 0 };
+  if (!per_sm[P.mode]) {
+    int n = 0;
+    const void* fn = P.mode == 0 ? (const void*)k_stream_solid<0> : P.mode == 1 ? (const void*)k_stream_solid<1> : (const void*)k_stream_solid<2>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0) != cudaSuccess || n < 1) n = 4;
+    per_sm[P.mode] = n;
+  }
+  long long want = (total + 256LL * kSolidUnroll - 1) / (256LL * kSolidUnroll);
+  const long long cap = (long long)sm_count * per_sm[P.mode];
+  const int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
+  const long long stride = (long long)grid * 256;
+  const int step_r = int(stride / chunks_per_row), step_c = int(stride - (long long)step_r * chunks_per_row);
+  if (P.mode == 0) k_stream_solid<0><<<grid, 256, 0, s>>>(P, chunks_per_row, c0, step_r, step_c);
+  else if (P.mode == 1) k_stream_solid<1><<<grid, 256, 0, s>>>(P, chunks_per_row, c0, step_r, step_c);
+  else k_stream_solid<2><<<grid, 256, 0, s>>>(P, chunks_per_row, c0, step_r, step_c);
   return 1;
 }
 

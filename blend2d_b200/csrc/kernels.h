@@ -52,6 +52,19 @@ struct TileParams {
   unsigned long long* pixel_counter;
 };
 
+// One solid box fill over a large region (fill_all / clear_all / big FillRectA): pure streaming, see k_stream_solid.
+struct SolidStreamParams {
+  uint8_t* dst;                           // first byte of row `y_begin` of the target
+  intptr_t dst_stride;
+  int x0w, x1w;                           // 32-bit words per row to touch: pixels for 32-bpp targets, 4-pixel groups for A8
+  int y0, y1;                             // rows, relative to the first row held by the target
+  uint32_t mode;                          // 0 SrcOver, 1 SrcCopy with m < 255, 2 SrcCopy with m == 255 (store only)
+  uint32_t src;                           // premultiplied source pixel (A8: alpha replicated into the four bytes)
+  uint32_t mask;                          // 1..255
+  unsigned long long pixels;              // pixels the fill composites (added to the counter by one thread)
+  unsigned long long* pixel_counter;
+};
+
 // Each launcher returns the number of kernels it launched.
 int launch_count_edges(const BuildParams& P, cudaStream_t s);
 int launch_write_edges(const BuildParams& P, cudaStream_t s);
@@ -63,5 +76,6 @@ int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
 int launch_band_extents(const TileParams& P, uint2* band_ext, cudaStream_t s);
 int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s);
 int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
+int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s);
 
 } // namespace b2d

@@ -131,6 +131,9 @@ struct BlockLayout {
   size_t total_bytes;
 };
 
+// A batch that is a single solid box fill (fill_all, clear_all, one big FillRectA).
+struct SolidFill { bool ok; int box[4]; uint32_t comp_op, alpha, prgb32; };
+
 struct b2dgpu_batch {
   b2dgpu_runtime* rt;
   DevBuffer block;
@@ -144,6 +147,7 @@ struct b2dgpu_batch {
   bool edges_staged;                        // supplied edges already copied into `edges`
   bool stream_ok;
   int stream_box[4];
+  SolidFill solid;
 };
 
 static const uint32_t kRuntimeMagic = 0xB2D09B00u;
@@ -428,6 +432,19 @@ extern "C" b2dgpu_result b2dgpu_target_download(b2dgpu_target* t, const b2dgpu_i
 // ---------------------------------------------------------------------------------------------------------------
 struct BlobRef { const void* host; size_t bytes; size_t offset; };
 
+
+static SolidFill detect_solid_fill(const b2dgpu_batch_view* v) {
+  SolidFill f; memset(&f, 0, sizeof(f));
+  if (v->command_count != 1) return f;
+  const b2dgpu_command& c = v->commands[0];
+  const uint32_t op = B2DGPU_SIG_COMP_OP(c.signature);
+  if (c.type != B2DGPU_CMD_FILL_BOX_A || B2DGPU_SIG_FETCH_TYPE(c.signature) != B2DGPU_FETCH_SOLID) return f;
+  if (op != 0u /* SrcOver */ && op != 1u /* SrcCopy */) return f;
+  if (c.alpha == 0) return f;
+  f.ok = true; memcpy(f.box, c.box, sizeof(f.box)); f.comp_op = op; f.alpha = c.alpha; f.prgb32 = c.solid_prgb32;
+  return f;
+}
+
 struct FetchUse { uint32_t fetch_type; uint32_t src_format; bool used; };
 
 static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
@@ -552,6 +569,7 @@ struct PreparedBatch {
   bool has_analytic;
   bool stream_ok;
   int stream_box[4];
+  SolidFill solid;
 };
 
 static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb) {
@@ -563,6 +581,7 @@ static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb
   plan_layout(v, blob_bytes, pb.lay);
   pb.has_analytic = false;
   for (uint32_t i = 0; i < v->command_count; i++) if (v->commands[i].type == B2DGPU_CMD_FILL_ANALYTIC) pb.has_analytic = true;
+  pb.solid = detect_solid_fill(v);
   pb.stream_ok = v->command_count >= 1 && v->command_count <= 8;
   pb.stream_box[0] = pb.stream_box[1] = INT_MAX; pb.stream_box[2] = pb.stream_box[3] = INT_MIN;
   for (uint32_t i = 0; i < v->command_count && pb.stream_ok; i++) {
@@ -608,6 +627,7 @@ static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v
 // Rendering
 // ---------------------------------------------------------------------------------------------------------------
 struct RenderInput {
+  SolidFill solid;                // the batch is ONE solid FillBoxA with SrcOver / SrcCopy: k_stream_solid
   uint8_t* block;
   const BlockLayout* lay;
   DevBuffer* edges;
@@ -744,7 +764,23 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
                    in.stream_box[2] > t->w ? t->w : in.stream_box[2], in.stream_box[3] > t->y0 + t->h ? t->y0 + t->h : in.stream_box[3] };
     // Large dirty regions only: small boxes are latency bound either way and the tile path culls them well.
     if (box[0] < box[2] && box[1] < box[3] && (long long)(box[2] - box[0]) * (box[3] - box[1]) >= (1 << 20)) {
-      launches += launch_box_stream(T, t->bpp, box, rt->sm_count, s);
+      // A8 targets are streamed as words of four pixels: the box has to start on a word and end on one (or at the
+      // right edge of the image, where the rest of the word is row padding).
+      const bool words_ok = t->bpp == 4 || ((box[0] & 3) == 0 && ((box[2] & 3) == 0 || box[2] == t->w));
+      if (in.solid.ok && words_ok) {
+        SolidStreamParams S;
+        S.dst = t->d_pixels; S.dst_stride = intptr_t(t->stride);
+        S.x0w = t->bpp == 4 ? box[0] : box[0] / 4;
+        S.x1w = t->bpp == 4 ? box[2] : (box[2] + 3) / 4;
+        S.y0 = box[1] - t->y0; S.y1 = box[3] - t->y0;
+        S.mode = in.solid.comp_op == 0u ? 0u : (in.solid.alpha == 255u ? 2u : 1u);
+        S.src = t->bpp == 4 ? in.solid.prgb32 : (in.solid.prgb32 >> 24) * 0x01010101u;
+        S.mask = in.solid.alpha;
+        S.pixels = (unsigned long long)(box[2] - box[0]) * (unsigned long long)(box[3] - box[1]);
+        S.pixel_counter = rt->d_pixel_counter;
+        launches += launch_stream_solid(S, rt->sm_count, s);
+      }
+      else launches += launch_box_stream(T, t->bpp, box, rt->sm_count, s);
       streamed = true;
     }
   }
@@ -786,6 +822,7 @@ extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target
   in.has_analytic = pb.has_analytic;
   in.built_known = false; in.built_edges = 0; in.edges_staged = false;
   in.stream_ok = pb.stream_ok; memcpy(in.stream_box, pb.stream_box, sizeof(in.stream_box));
+  in.solid = pb.solid;
   return render_block(rt, target, in);
 }
 
@@ -813,6 +850,7 @@ extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_ba
   if (e != cudaSuccess) { delete b; return cuda_fail(e, "b2dgpu_batch_upload: cudaMalloc(block)"); }
   b->edges_staged = false;
   b->stream_ok = pb.stream_ok; memcpy(b->stream_box, pb.stream_box, sizeof(b->stream_box));
+  b->solid = pb.solid;
   r = upload_block(rt, view, pb, static_cast<uint8_t*>(b->block.ptr));
   if (r) { b->block.release(); b->edges.release(); delete b; return r; }
   *out = b;
@@ -842,6 +880,7 @@ extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* 
   in.has_analytic = b->has_analytic;
   in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged;
   in.stream_ok = b->stream_ok; memcpy(in.stream_box, b->stream_box, sizeof(in.stream_box));
+  in.solid = b->solid;
   // The whole path (K1 count, scan, K1 write, finalize, K2+K3) re-runs on every render; only the host read-back of the
   // edge total is skipped after the first time because the geometry of a resident batch cannot change.
   b2dgpu_result r = render_block(rt, target, in);

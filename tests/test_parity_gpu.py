@@ -102,3 +102,29 @@ def big_box_scene(style, op):
 @pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
 def test_streaming_box_fills(ref, gpu, style, tol, fmt, op):
     compare(ref, gpu, big_box_scene(style, op), 1403, 1001, fmt, max_diff=tol)
+
+
+def solid_stream_scene(op, alpha, rect):
+    """Batches of ONE solid box fill over > 1 Mpx, flushed one by one: the streaming solid kernel (k_stream_solid)."""
+    def scene(api, ctx, rng):
+        W, H = ctx.image.w, ctx.image.h
+        ctx.set_fill_style(0xFFFFFFFF); ctx.fill_rect_i(3, 5, W - 9, H - 11); ctx.flush()         # opaque SrcOver -> SrcCopy store
+        ctx.set_fill_style(0xC0204060); ctx.fill_all(); ctx.flush()                                # translucent SrcOver
+        ctx.set_comp_op(op); ctx.set_global_alpha(alpha)
+        ctx.set_fill_style(S.rand_rgba32(rng))
+        if rect == "all":
+            ctx.fill_all()
+        else:
+            ctx.fill_rect_i(*rect)
+        ctx.flush()
+        ctx.set_global_alpha(1.0)
+        ctx.set_fill_style(0x40808080); ctx.fill_rect_i(1, 2, W - 2, H - 3)                        # goes with end()
+    return scene
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+@pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
+@pytest.mark.parametrize("alpha", [1.0, 0.4])
+@pytest.mark.parametrize("rect", ["all", (8, 1, 1392, 990), (5, 3, 1391, 995)])
+def test_streaming_solid_fill(ref, gpu, fmt, op, alpha, rect):
+    compare(ref, gpu, solid_stream_scene(op, alpha, rect), 1403, 1001, fmt)
