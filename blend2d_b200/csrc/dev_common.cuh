@@ -27,7 +27,7 @@ enum : int { kA8Shift = 8, kA8Scale = 256, kA8Mask = 255 };
 
 // Tile geometry of the compositor (see DESIGN.md "Data layout in HBM").
 enum : int {
-  kTileW = 128,            // pixels per tile row  (one warp, 4 px per lane -> 512 B of PRGB32 per row)
+  kTileW = 256,            // pixels per tile row  (one warp, 8 px per lane -> 1 KiB of PRGB32 per row)
   kTileH = 8,              // rows per tile        (one warp per row)
   kTileThreads = 32 * kTileH
 };

@@ -323,6 +323,10 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     s[0] = s[1] = s[2] = s[3] = env.solid;
     return;
   }
+  // Nearest-neighbour gradients are evaluated for all four pixels without looking at the masks: the table index is
+  // always in range (pad clamps, repeat / reflect mask it), so the loads are safe, and straight-line code with four
+  // independent dependency chains is what the instruction front end and the LSU want.  The compositor ignores the
+  // result where the mask is zero.
   if (ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD || ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_ROR) {
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
     const b2dgpu_gradient_linear& l = g.linear;
@@ -332,11 +336,9 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     uint64_t pt = l.pt[0].u64 + uint64_t(y) * l.dy.u64 + uint64_t(x) * dt;
     #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (m[i]) {
-        uint32_t idx = uint32_t(pt >> 32);
-        idx = pad ? grad_index_pad(idx, maxi) : grad_index_ror(idx, maxi, rori);
-        s[i] = lut_fetch_nn(g, idx);
-      }
+      uint32_t idx = uint32_t(pt >> 32);
+      idx = pad ? grad_index_pad(idx, maxi) : grad_index_ror(idx, maxi, rori);
+      s[i] = lut_fetch_nn(g, idx);
       pt += dt;
     }
     return;
@@ -348,11 +350,9 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     const RadialRow row = radial_row(r, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) {
-      if (m[i]) {
-        uint32_t idx = radial_index(r, row, x + i);
-        idx = pad ? grad_index_pad(idx, r.maxi) : grad_index_ror(idx, r.maxi, r.rori);
-        s[i] = lut_fetch_nn(g, idx);
-      }
+      uint32_t idx = radial_index(r, row, x + i);
+      idx = pad ? grad_index_pad(idx, r.maxi) : grad_index_ror(idx, r.maxi, r.rori);
+      s[i] = lut_fetch_nn(g, idx);
     }
     return;
   }
@@ -360,9 +360,7 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
     const ConicRow row = conic_row(g.conic, y);
     #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (m[i]) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
-    }
+    for (int i = 0; i < 4; i++) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
     return;
   }
   #pragma unroll 1

@@ -158,24 +158,26 @@ B2D_HD_COLD uint32_t composite_cold(uint32_t comp_op, uint32_t d, uint32_t s, ui
 // d[i] = op(d[i], s[i], m[i]) for the pixels whose mask is non-zero; operator dispatch hoisted out of the loop.
 // `all_opaque`: every non-zero m[i] the caller passes is 255 (decided per warp, so the branch never diverges).
 B2D_HD void composite4(uint32_t comp_op, uint32_t* d, const uint32_t* s, const uint32_t* m, bool all_opaque = false) {
+  // SrcOver and SrcCopy are the identity at m == 0, so the general variants run unguarded (no branch per pixel); the
+  // m == 255 variants select.
   if (comp_op == kOpSrcOver) {
     if (all_opaque) {
       #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_over_opaque_mask(d[i], s[i]);
+      for (int i = 0; i < 4; i++) { uint32_t v = comp_src_over_opaque_mask(d[i], s[i]); d[i] = m[i] ? v : d[i]; }
     }
     else {
       #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_over(d[i], s[i], m[i]);
+      for (int i = 0; i < 4; i++) d[i] = comp_src_over(d[i], s[i], m[i]);
     }
   }
   else if (comp_op == kOpSrcCopy) {
     if (all_opaque) {
       #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = s[i];                 // div255(s * 255) == s
+      for (int i = 0; i < 4; i++) d[i] = m[i] ? s[i] : d[i];              // div255(s * 255) == s
     }
     else {
       #pragma unroll
-      for (int i = 0; i < 4; i++) if (m[i]) d[i] = comp_src_copy(d[i], s[i], m[i]);
+      for (int i = 0; i < 4; i++) d[i] = comp_src_copy(d[i], s[i], m[i]);
     }
   }
   else {

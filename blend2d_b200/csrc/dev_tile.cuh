@@ -81,12 +81,35 @@ B2D_HD NormEdge normalize_edge(b2dgpu_edge ed) {
   return n;
 }
 
+// Columns an edge can touch inside the band of rows [band_y, band_y + kTileH): cells [min >> 8, (max >> 8) + 1]
+// (cell_merge writes x and x + 1) of the edge's part inside the band, with one more column of slack on each side for
+// the DDA's rounding.  Used by k_band_extents to cull (tile, command) pairs; must never be too tight.
+B2D_HD_COLD long long sdiv64(long long a, long long b) { return a / b; }      // out of line: ~100 instructions on the GPU
+
+B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi) {
+  const long long dx = (long long)ed.x1 - ed.x0, dy = (long long)ed.y1 - ed.y0;
+  const int ya = tmax(ed.y0, band_y << 8);
+  const int yb = tmin(ed.y1, (band_y + kTileH) << 8);
+  const int xa = ed.x0 + int(sdiv64(dx * (ya - ed.y0), dy));
+  const int xb = ed.x0 + int(sdiv64(dx * (yb - ed.y0), dy));
+  lo = tmax((tmin(xa, xb) >> 8) - 1, 0);
+  hi = tmax((tmax(xa, xb) >> 8) + 2, 0);
+}
+
 B2D_HD int tile_edge_class(const NormEdge& ed, int tx0, int ty0) {
   const int ey_first = ed.y0 >> 8, ey_last = (ed.y1 - 1) >> 8;
   if (ey_last < ty0 || ey_first >= ty0 + kTileH) return kEdgeNone;
-  const int cx_min = tmin(ed.x0, ed.x1) >> 8, cx_max = tmax(ed.x0, ed.x1) >> 8;
+  int cx_min = tmin(ed.x0, ed.x1) >> 8, cx_max = (tmax(ed.x0, ed.x1) >> 8) + 1;
   if (cx_min >= tx0 + kTileW) return kEdgeNone;
-  return (cx_max + 1 < tx0) ? kEdgeLeft : kEdgeStraddle;
+  if (cx_max < tx0) return kEdgeLeft;
+  // A long edge (a closing chord can span the whole canvas) only touches a few columns inside this tile's rows:
+  // classify by the part of the edge inside the band, conservatively rounded outwards (band_edge_extent).
+  if (cx_max - cx_min >= 16) {
+    band_edge_extent(ed, ty0, cx_min, cx_max);
+    if (cx_min >= tx0 + kTileW) return kEdgeNone;
+    if (cx_max < tx0) return kEdgeLeft;
+  }
+  return kEdgeStraddle;
 }
 
 // Every scanline's cells of an edge sum to (cover << 9), cover = signed y-extent inside the row: that is all a tile
@@ -98,19 +121,6 @@ B2D_HD void tile_left_cover(const NormEdge& ed, int ty0, uint32_t* left_acc) {
     int cov = tmin(ed.y1, yt + 256) - tmax(ed.y0, yt);
     if (cov > 0) left_acc[r] += uint32_t(ed.sign_bit ? -cov : cov) << 9;
   }
-}
-
-// Columns an edge can touch inside the band of rows [band_y, band_y + kTileH): cells [min >> 8, (max >> 8) + 1]
-// (cell_merge writes x and x + 1) of the edge's part inside the band, with one more column of slack on each side for
-// the DDA's rounding.  Used by k_band_extents to cull (tile, command) pairs; must never be too tight.
-B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi) {
-  const long long dx = (long long)ed.x1 - ed.x0, dy = (long long)ed.y1 - ed.y0;
-  const int ya = tmax(ed.y0, band_y << 8);
-  const int yb = tmin(ed.y1, (band_y + kTileH) << 8);
-  const int xa = ed.x0 + int(dx * (ya - ed.y0) / dy);
-  const int xb = ed.x0 + int(dx * (yb - ed.y0) / dy);
-  lo = tmax((tmin(xa, xb) >> 8) - 1, 0);
-  hi = tmax((tmax(xa, xb) >> 8) + 2, 0);
 }
 
 // Rasterizes the tile's rows of a straddling edge through `store`.  Returns true when anything was written.

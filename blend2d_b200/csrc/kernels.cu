@@ -15,6 +15,7 @@
 //
 // No tensor cores: nothing on this path is a dense contraction.  Compile with -fmad=false (see dev_flatten.cuh).
 #include "kernels.h"
+#include <stdlib.h>
 #include "dev_pixel.cuh"
 #include "dev_raster.cuh"
 #include "dev_flatten.cuh"
@@ -307,7 +308,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 64, kEntCap = 8, kRing = 512 };
+enum : int { kSubChunk = 48, kEntCap = 10, kRing = 512, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 
 struct PreCmd {
@@ -342,9 +343,11 @@ struct EntrySink {
 
 // Slow path of the replay (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
 // rasterizes its own row into its private shared-memory cell row.  Out of line: it is rare and large.
-__device__ __noinline__ uint4 slow_row_cells(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int py, int row,
-                                             int lane, uint32_t* cells_row, uint32_t* carry_row) {
-  *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(0, 0, 0, 0);
+__device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int py, int row,
+                                            int lane, uint32_t* cells_row, uint32_t* carry_row) {
+  #pragma unroll
+  for (int i = 0; i < kLanePx / 4; i++)
+    *reinterpret_cast<uint4*>(cells_row + lane * kLanePx + i * 4) = make_uint4(0, 0, 0, 0);
   if (lane == 0) *carry_row = 0;
   __syncwarp();
   SmemRowStore store{ cells_row, carry_row };
@@ -356,7 +359,6 @@ __device__ __noinline__ uint4 slow_row_cells(const int4* __restrict__ edges, uin
       tile_rasterize_edge_row(ne, py, sink);
   }
   __syncwarp();
-  return *reinterpret_cast<uint4*>(cells_row + lane * 4);
 }
 
 template<int BPP>
@@ -374,21 +376,27 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
   const int tile_y = blockIdx.x / P.tiles_x;
   const int tx0 = tile_x * kTileW;
   const int ty0 = P.y_begin + tile_y * kTileH;          // absolute y of the tile's first row
-  const int px = tx0 + lane * 4;
+  const int px = tx0 + lane * kLanePx;
   const int py = ty0 + row;
   const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
 
-  // Load the destination once.
+  // Load the destination once: kLanePx (8) consecutive pixels per lane, kept in registers for the whole command list.
+  // `lo` = pixels 0..3, `hi` = pixels 4..7.
   uint8_t* dst_row = P.dst + size_t(py - P.y_begin) * P.dst_stride;
-  uint32_t d[4];
+  uint32_t d_lo[4], d_hi[4];
   if (BPP == 4) {
-    uint4 v = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    uint4 v0 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
+    uint4 v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4 + 16);
+    d_lo[0] = v0.x; d_lo[1] = v0.y; d_lo[2] = v0.z; d_lo[3] = v0.w;
+    d_hi[0] = v1.x; d_hi[1] = v1.y; d_hi[2] = v1.z; d_hi[3] = v1.w;
   }
   else {
-    uint32_t v = *reinterpret_cast<const uint32_t*>(dst_row + px);
-    d[0] = (v & 0xFFu) * 0x01010101u; d[1] = ((v >> 8) & 0xFFu) * 0x01010101u;
-    d[2] = ((v >> 16) & 0xFFu) * 0x01010101u; d[3] = (v >> 24) * 0x01010101u;
+    uint2 v = *reinterpret_cast<const uint2*>(dst_row + px);
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+      d_lo[i] = ((v.x >> (8 * i)) & 0xFFu) * 0x01010101u;
+      d_hi[i] = ((v.y >> (8 * i)) & 0xFFu) * 0x01010101u;
+    }
   }
   bool dirty = false;
   uint32_t px_written = 0;
@@ -503,19 +511,22 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
         const b2dgpu_command& cmd = P.commands[ci];
         const uint32_t type = cmd.type;
         const uint32_t alpha = cmd.alpha;
-        uint32_t m[4] = { 0, 0, 0, 0 };
+        uint32_t m_lo[4] = { 0, 0, 0, 0 }, m_hi[4] = { 0, 0, 0, 0 };
 
         if (type == B2DGPU_CMD_FILL_BOX_A) {
           // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
           if (py >= cmd.box[1] && py < cmd.box[3]) {
             #pragma unroll
-            for (int i = 0; i < 4; i++) m[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
+            for (int i = 0; i < 4; i++) {
+              m_lo[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
+              m_hi[i] = (px + 4 + i >= cmd.box[0] && px + 4 + i < cmd.box[2]) ? alpha : 0u;
+            }
           }
         }
         else if (type == B2DGPU_CMD_FILL_BOX_U) {
           BoxUParams bu = box_u_setup(cmd.box, alpha);
           #pragma unroll
-          for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
+          for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + 4 + i, py); }
         }
         else {
           const PreCmd& pre = s_pre[k];
@@ -525,52 +536,64 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
             // No edge inside the tile: coverage is constant along the row (FillAnalytic's CMask spans).
             if (!carry) continue;
             const uint32_t mm = calc_mask((256u << 9) + carry, cmd.fill_rule_mask, alpha);
-            m[0] = m[1] = m[2] = m[3] = mm;
+            #pragma unroll
+            for (int i = 0; i < 4; i++) { m_lo[i] = mm; m_hi[i] = mm; }
           }
           else {
-            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            uint32_t c[kLanePx];
+            #pragma unroll
+            for (int i = 0; i < kLanePx; i++) c[i] = 0;
             const uint32_t n = pre.nent[row];
             if (!(flags & kPreOverflow) || n <= uint32_t(kEntCap)) {
               // Fast path: the row's cells are the handful of entries phase 1 recorded.
               carry += pre.carry_st[row];
               for (uint32_t j = 0; j < n; j++) {
                 const uint2 en = pre.ent[row][j];
-                const uint32_t v = (int(en.x >> 2) == lane) ? en.y : 0u;
-                const uint32_t sel = en.x & 3u;
-                c0 += sel == 0 ? v : 0u; c1 += sel == 1 ? v : 0u;
-                c2 += sel == 2 ? v : 0u; c3 += sel == 3 ? v : 0u;
+                const uint32_t v = (int(en.x >> 3) == lane) ? en.y : 0u;
+                const uint32_t sel = en.x & 7u;
+                #pragma unroll
+                for (int i = 0; i < kLanePx; i++) c[i] += sel == uint32_t(i) ? v : 0u;
               }
             }
             else {
-              uint4 cv = slow_row_cells(edges, P.cmd_edges[ci], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
-              c0 = cv.x; c1 = cv.y; c2 = cv.z; c3 = cv.w;
+              slow_row_cells(edges, P.cmd_edges[ci], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
+              #pragma unroll
+              for (int i = 0; i < kLanePx / 4; i++) {
+                uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * kLanePx + i * 4]);
+                c[i * 4 + 0] = cv.x; c[i * 4 + 1] = cv.y; c[i * 4 + 2] = cv.z; c[i * 4 + 3] = cv.w;
+              }
               carry += s_carry[row];
               __syncwarp();
             }
             // Prefix-sum of the row's cells (fillgeneric_p.h:285-297) and 8-bit masks.
-            uint32_t s0 = c0, s1 = s0 + c1, s2 = s1 + c2, s3 = s2 + c3;
-            uint32_t inc = s3;
+            #pragma unroll
+            for (int i = 1; i < kLanePx; i++) c[i] += c[i - 1];
+            uint32_t inc = c[kLanePx - 1];
             #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
               uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
               if (lane >= o) inc += t;
             }
-            const uint32_t cov_base = (256u << 9) + carry + (inc - s3);
+            const uint32_t cov_base = (256u << 9) + carry + (inc - c[kLanePx - 1]);
             const uint32_t rule = cmd.fill_rule_mask;
-            m[0] = calc_mask(cov_base + s0, rule, alpha);
-            m[1] = calc_mask(cov_base + s1, rule, alpha);
-            m[2] = calc_mask(cov_base + s2, rule, alpha);
-            m[3] = calc_mask(cov_base + s3, rule, alpha);
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+              m_lo[i] = calc_mask(cov_base + c[i], rule, alpha);
+              m_hi[i] = calc_mask(cov_base + c[4 + i], rule, alpha);
+            }
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
           const int bx1 = P.cmd_bbox_px[ci].z;
-          #pragma unroll
-          for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
+          if (bx1 < tx0 + kTileW) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + 4 + i >= bx1) m_hi[i] = 0; }
+          }
         }
 
         // ---- fetch + composite ----
         // Warp-uniform exit: the lanes stay converged for the votes / shuffles of this and the next iteration.
-        if (!__any_sync(0xFFFFFFFFu, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
+        const uint32_t any_m = m_lo[0] | m_lo[1] | m_lo[2] | m_lo[3] | m_hi[0] | m_hi[1] | m_hi[2] | m_hi[3];
+        if (!__any_sync(0xFFFFFFFFu, any_m != 0u)) continue;
 
         const uint32_t sig = cmd.signature;
         FetchEnv env;
@@ -580,16 +603,31 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
         env.fd = P.fetch_data + cmd.fetch_index;
         env.bayer = P.bayer;
         env.origin_x = P.origin_x; env.origin_y = P.origin_y;
+        const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
 
-        uint32_t s[4];
-        fetch4(env, uint32_t(px), uint32_t(py), m, s);
-        if (BPP == 1) {
+        uint32_t not_opaque = 0;
+        #pragma unroll
+        for (int i = 0; i < 4; i++) not_opaque |= ((m_lo[i] + 1u) | (m_hi[i] + 1u)) & 0xFEu;
+        const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
+
+        // The two halves of the lane's 8 pixels go through ONE copy of the fetch / composite code (the loop is not
+        // unrolled; lo and hi swap places after each pass and are back where they started after the second).
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+          uint32_t s[4] = { 0, 0, 0, 0 };
+          fetch4(env, uint32_t(px + 4 * h), uint32_t(py), m_lo, s);
+          if (BPP == 1) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+          }
+          composite4(comp_op, d_lo, s, m_lo, opaque);
+          px_written += (m_lo[0] != 0) + (m_lo[1] != 0) + (m_lo[2] != 0) + (m_lo[3] != 0);
           #pragma unroll
-          for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+          for (int i = 0; i < 4; i++) {
+            uint32_t t = d_lo[i]; d_lo[i] = d_hi[i]; d_hi[i] = t;
+            t = m_lo[i]; m_lo[i] = m_hi[i]; m_hi[i] = t;
+          }
         }
-        const bool opaque = __all_sync(0xFFFFFFFFu, ((m[0] + 1u) & 0xFEu) + ((m[1] + 1u) & 0xFEu) + ((m[2] + 1u) & 0xFEu) + ((m[3] + 1u) & 0xFEu) == 0u);
-        composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m, opaque);
-        px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
         dirty = true;
       }
     }
@@ -597,11 +635,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
 
   if (dirty) {
     if (BPP == 4) {
-      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d_lo[0], d_lo[1], d_lo[2], d_lo[3]);
+      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4 + 16) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
     }
     else {
-      uint32_t v = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
-      *reinterpret_cast<uint32_t*>(dst_row + px) = v;
+      uint2 v;
+      v.x = (d_lo[0] >> 24) | ((d_lo[1] >> 24) << 8) | ((d_lo[2] >> 24) << 16) | ((d_lo[3] >> 24) << 24);
+      v.y = (d_hi[0] >> 24) | ((d_hi[1] >> 24) << 8) | ((d_hi[2] >> 24) << 16) | ((d_hi[3] >> 24) << 24);
+      *reinterpret_cast<uint2*>(dst_row + px) = v;
     }
   }
 
@@ -642,7 +683,7 @@ __device__ __forceinline__ void stream_chunk(const TileParams& P, const b2dgpu_c
     env.fd = P.fetch_data + cmd.fetch_index;
     env.bayer = P.bayer;
     env.origin_x = P.origin_x; env.origin_y = P.origin_y;
-    uint32_t s[4];
+    uint32_t s[4] = { 0, 0, 0, 0 };
     fetch4(env, uint32_t(x), uint32_t(y), m, s);
     if (BPP == 1) {
       #pragma unroll
@@ -882,8 +923,17 @@ int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
   if (!P.command_count) return 0;
   uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
   if (!tiles) return 0;
-  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, 0, s>>>(P);
-  else k_tile_render<1><<<tiles, kTileThreads, 0, s>>>(P);
+  static int exp_dyn = -1;
+  if (exp_dyn < 0) {
+    const char* e = getenv("B2D_EXP_DYNSMEM");
+    exp_dyn = e ? atoi(e) : 0;
+    if (exp_dyn) {
+      cudaFuncSetAttribute(k_tile_render<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, exp_dyn);
+      cudaFuncSetAttribute(k_tile_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, exp_dyn);
+    }
+  }
+  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, exp_dyn, s>>>(P);
+  else k_tile_render<1><<<tiles, kTileThreads, exp_dyn, s>>>(P);
   return 1;
 }
 
