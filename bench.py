@@ -73,6 +73,8 @@ def make_config1_scene(n_fills, W, H, seed):
         f.fill_rule = (i // 3) % 2
         f.comp_op = 0
         f.style = 1 + (i % 3 + i // 7) % 3
+        if os.environ.get("B2D_BENCH_STYLE"):            # experiment knob: force one gradient type (1 linear, 2 radial, 3 conic)
+            f.style = int(os.environ["B2D_BENCH_STYLE"])
         f.extend = (i // 5) % 3
         f.quality = 0
         f.vtx_offset = len(vtx)
@@ -244,7 +246,8 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)
     rt = G.Runtime(device=local_rank, stream=stream.cuda_stream)
     img = G.Image(W, H, G.FORMAT_PRGB32)
-    ctx = G.Context(img, device=local_rank, runtime=rt)
+    # The e2e context flushes every `--queue-limit` commands: batch k renders while the host builds batch k + 1.
+    ctx = G.Context(img, device=local_rank, runtime=rt, command_queue_limit=args.queue_limit)
     lib = N.lib
     G_check = N.check
 
@@ -463,6 +466,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--queue-limit", type=int, default=1024, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

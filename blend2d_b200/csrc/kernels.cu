@@ -362,7 +362,7 @@ __device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint
 }
 
 template<int BPP>
-__global__ void __launch_bounds__(kTileThreads, 3) k_tile_render(TileParams P) {
+__global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
   __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
   __shared__ uint32_t s_carry[kTileH];
   __shared__ uint32_t s_list[kRing];

@@ -101,7 +101,14 @@ struct b2dgpu_runtime {
 
   PinnedBuffer staging[2];
   int staging_next;
-  DevBuffer oneshot_block;                  // device block reused by b2dgpu_submit()
+  // b2dgpu_submit() is pipelined: batch k + 1 is uploaded, counted and scanned on `prep_stream` (its edge total is
+  // read back there) while batch k is still rendering on `stream`.  Two device blocks alternate.
+  cudaStream_t prep_stream;
+  DevBuffer oneshot_block[2];
+  cudaEvent_t slot_done[2];                 // recorded on `stream` after the render that reads oneshot_block[i]
+  bool slot_busy[2];
+  int slot_next;
+  cudaEvent_t prep_ready;
   DevBuffer oneshot_edges;
   DevBuffer band_ext;                       // [tile row][command] x-extents (k_band_extents), rebuilt by every render
   PinnedBuffer image_staging;
@@ -240,6 +247,8 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->device = device;
   rt->stream = nullptr;
   rt->own_stream = false;
+  rt->prep_stream = nullptr; rt->prep_ready = nullptr; rt->slot_next = 0;
+  rt->slot_done[0] = rt->slot_done[1] = nullptr; rt->slot_busy[0] = rt->slot_busy[1] = false;
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
   rt->profiling = false;
@@ -267,6 +276,16 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
     return cuda_fail(e, "b2dgpu_runtime_create: device allocation");
   }
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
+  {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&rt->prep_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) {
+      b2dgpu_runtime_destroy(rt);
+      return cuda_fail(e, "b2dgpu_runtime_create: cudaStreamCreate(prep)");
+    }
+  }
   *out = rt;
   return B2DGPU_SUCCESS;
 }
@@ -275,6 +294,9 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_destroy: invalid runtime");
   cudaSetDevice(rt->device);
   cudaStreamSynchronize(rt->stream);
+  if (rt->prep_stream) { cudaStreamSynchronize(rt->prep_stream); cudaStreamDestroy(rt->prep_stream); }
+  for (int i = 0; i < 2; i++) if (rt->slot_done[i]) cudaEventDestroy(rt->slot_done[i]);
+  if (rt->prep_ready) cudaEventDestroy(rt->prep_ready);
   if (rt->d_bayer) cudaFree(rt->d_bayer);
   if (rt->d_pixel_counter) cudaFree(rt->d_pixel_counter);
   if (rt->d_scalars) cudaFree(rt->d_scalars);
@@ -282,7 +304,8 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   for (int i = 0; i < 2; i++) rt->staging[i].release();
   for (cudaEvent_t e : rt->prof_events) cudaEventDestroy(e);
   rt->image_staging.release();
-  rt->oneshot_block.release();
+  rt->oneshot_block[0].release();
+  rt->oneshot_block[1].release();
   rt->oneshot_edges.release();
   rt->band_ext.release();
   if (rt->own_stream) cudaStreamDestroy(rt->stream);
@@ -599,7 +622,7 @@ static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb
 }
 
 // Fills the pinned block and copies it to `dev_block`.
-static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v, PreparedBatch& pb, uint8_t* dev_block) {
+static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v, PreparedBatch& pb, uint8_t* dev_block, cudaStream_t stream) {
   PinnedBuffer& st = rt->staging[rt->staging_next];
   rt->staging_next ^= 1;
   if (st.in_flight) { CU_TRY(cudaEventSynchronize(st.free_event)); st.in_flight = false; }
@@ -616,8 +639,8 @@ static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v
     else fd[i].pattern.src.pixel_data = dev;
   }
 
-  CU_TRY(cudaMemcpyAsync(dev_block, host_block, pb.lay.upload_bytes, cudaMemcpyHostToDevice, rt->stream));
-  CU_TRY(cudaEventRecord(st.free_event, rt->stream));
+  CU_TRY(cudaMemcpyAsync(dev_block, host_block, pb.lay.upload_bytes, cudaMemcpyHostToDevice, stream));
+  CU_TRY(cudaEventRecord(st.free_event, stream));
   st.in_flight = true;
   rt->stats.h2d_bytes += pb.lay.upload_bytes;
   return B2DGPU_SUCCESS;
@@ -637,9 +660,56 @@ struct RenderInput {
   bool built_known;
   uint32_t built_edges;
   bool edges_staged;
+  bool prepped;                   // init_bbox + count + scan already ran (on the prep stream) for this block
   bool stream_ok;                 // only box fills, few of them: eligible for the streaming compositor
   int stream_box[4];              // union of their boxes in pixels
 };
+
+static BuildParams make_build_params(b2dgpu_runtime* rt, const RenderInput& in) {
+  const BlockLayout& L = *in.lay;
+  uint8_t* blk = in.block;
+  BuildParams B;
+  B.vertices = reinterpret_cast<const double*>(blk + L.vertices);
+  B.segments = reinterpret_cast<const b2dgpu_segment*>(blk + L.segments);
+  B.segment_count = in.segment_count;
+  B.commands = reinterpret_cast<const b2dgpu_command*>(blk + L.commands);
+  B.states = reinterpret_cast<const b2dgpu_geometry_state*>(blk + L.states);
+  B.seg_counts = reinterpret_cast<uint32_t*>(blk + L.seg_counts);
+  B.seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
+  B.edge_base = in.supplied_edges;
+  B.cmd_bbox_fixed = reinterpret_cast<int4*>(blk + L.bbox_fixed);
+  B.error_flag = rt->d_scalars + 1;
+  B.edges = nullptr; B.edge_capacity = 0;
+  return B;
+}
+
+// K1 pass 1 (edge counts per segment) + exclusive scan, on stream `s`.  These run on every render - they are part of
+// the path even when the total is already known; the total is only read back (which synchronises `s`) the first
+// time a geometry is seen, because the edge buffer has to be sized on the host.
+static b2dgpu_result prep_block(b2dgpu_runtime* rt, RenderInput& in, cudaStream_t s, uint32_t* d_total, uint32_t* h_total, int& launches) {
+  const BlockLayout& L = *in.lay;
+  uint8_t* blk = in.block;
+  BuildParams B = make_build_params(rt, in);
+  launches += launch_init_bbox(B.cmd_bbox_fixed, in.command_count, s);
+  if (in.segment_count) {
+    launches += launch_count_edges(B, s);
+    launches += launch_exclusive_scan(B.seg_counts, const_cast<uint32_t*>(B.seg_offsets), in.segment_count,
+                                      reinterpret_cast<uint32_t*>(blk + L.scan_scratch), d_total, s);
+    if (!in.built_known) {
+      CU_TRY(cudaMemcpyAsync(h_total, d_total, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      in.built_edges = h_total[0];
+      in.built_known = true;
+      rt->stats.d2h_bytes += 4;
+    }
+  }
+  else {
+    in.built_edges = 0;
+    in.built_known = true;
+  }
+  in.prepped = true;
+  return B2DGPU_SUCCESS;
+}
 
 static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderInput& in) {
   const BlockLayout& L = *in.lay;
@@ -658,37 +728,12 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
     CU_TRY(cudaEventRecord(ev[0], s));
   }
 
-  launches += launch_init_bbox(d_bbox_fixed, in.command_count, s);
-
-  BuildParams B;
-  B.vertices = reinterpret_cast<const double*>(blk + L.vertices);
-  B.segments = reinterpret_cast<const b2dgpu_segment*>(blk + L.segments);
-  B.segment_count = in.segment_count;
-  B.commands = d_cmds;
-  B.states = reinterpret_cast<const b2dgpu_geometry_state*>(blk + L.states);
-  B.seg_counts = d_seg_counts;
-  B.seg_offsets = d_seg_offsets;
-  B.edge_base = in.supplied_edges;
-  B.cmd_bbox_fixed = d_bbox_fixed;
-  B.error_flag = rt->d_scalars + 1;
-
-  if (in.segment_count) {
-    // K1 pass 1 + scan run on every render: they are part of the path even when the total is already known.
-    launches += launch_count_edges(B, s);
-    launches += launch_exclusive_scan(d_seg_counts, d_seg_offsets, in.segment_count,
-                                      reinterpret_cast<uint32_t*>(blk + L.scan_scratch), rt->d_scalars, s);
-    if (!in.built_known) {
-      // First time this geometry is seen: the edge buffer has to be sized, which needs the total on the host.
-      CU_TRY(cudaMemcpyAsync(rt->h_scalars, rt->d_scalars, 4, cudaMemcpyDeviceToHost, s));
-      CU_TRY(cudaStreamSynchronize(s));
-      in.built_edges = rt->h_scalars[0];
-      in.built_known = true;
-      rt->stats.d2h_bytes += 4;
-    }
-  }
-  else {
-    in.built_edges = 0;
-    in.built_known = true;
+  BuildParams B = make_build_params(rt, in);
+  if (!in.prepped) {
+    int prep_launches = 0;
+    b2dgpu_result pr = prep_block(rt, in, s, rt->d_scalars, rt->h_scalars, prep_launches);
+    if (pr) return pr;
+    launches += prep_launches;
   }
 
   const size_t total_edges = size_t(in.supplied_edges) + in.built_edges;
@@ -807,12 +852,16 @@ extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target
   b2dgpu_result r = prepare_batch(view, pb);
   if (r) return r;
 
-  if (pb.lay.total_bytes > rt->oneshot_block.cap) {
-    CU_TRY(cudaStreamSynchronize(rt->stream));
-    CU_TRY(rt->oneshot_block.ensure(pb.lay.total_bytes));
-  }
-  uint8_t* blk = static_cast<uint8_t*>(rt->oneshot_block.ptr);
-  r = upload_block(rt, view, pb, blk);
+  // Slot = one of two device blocks.  The slot's previous batch (two submits ago) must have finished rendering.
+  const int slot = rt->slot_next;
+  rt->slot_next ^= 1;
+  if (rt->slot_busy[slot]) { CU_TRY(cudaEventSynchronize(rt->slot_done[slot])); rt->slot_busy[slot] = false; }
+  CU_TRY(rt->oneshot_block[slot].ensure(pb.lay.total_bytes));
+  uint8_t* blk = static_cast<uint8_t*>(rt->oneshot_block[slot].ptr);
+
+  // Upload + K1 count + scan on the prep stream: none of it depends on the batch that may still be rendering on the
+  // main stream, so the edge-total readback below only waits for these few small kernels.
+  r = upload_block(rt, view, pb, blk, rt->prep_stream);
   if (r) return r;
 
   RenderInput in;
@@ -820,10 +869,22 @@ extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target
   in.command_count = view->command_count; in.supplied_edges = view->edge_count; in.segment_count = view->segment_count;
   in.origin_x = view->pixel_origin_x; in.origin_y = view->pixel_origin_y;
   in.has_analytic = pb.has_analytic;
-  in.built_known = false; in.built_edges = 0; in.edges_staged = false;
+  in.built_known = false; in.built_edges = 0; in.edges_staged = false; in.prepped = false;
   in.stream_ok = pb.stream_ok; memcpy(in.stream_box, pb.stream_box, sizeof(in.stream_box));
   in.solid = pb.solid;
-  return render_block(rt, target, in);
+
+  int prep_launches = 0;
+  r = prep_block(rt, in, rt->prep_stream, rt->d_scalars + 2 + slot, rt->h_scalars + 2 + slot, prep_launches);
+  if (r) return r;
+  rt->stats.kernel_launches += uint64_t(prep_launches);
+  CU_TRY(cudaEventRecord(rt->prep_ready, rt->prep_stream));
+  CU_TRY(cudaStreamWaitEvent(rt->stream, rt->prep_ready, 0));
+
+  r = render_block(rt, target, in);
+  if (r) return r;
+  CU_TRY(cudaEventRecord(rt->slot_done[slot], rt->stream));
+  rt->slot_busy[slot] = true;
+  return B2DGPU_SUCCESS;
 }
 
 extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_batch** out) {
@@ -851,7 +912,7 @@ extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_ba
   b->edges_staged = false;
   b->stream_ok = pb.stream_ok; memcpy(b->stream_box, pb.stream_box, sizeof(b->stream_box));
   b->solid = pb.solid;
-  r = upload_block(rt, view, pb, static_cast<uint8_t*>(b->block.ptr));
+  r = upload_block(rt, view, pb, static_cast<uint8_t*>(b->block.ptr), rt->stream);
   if (r) { b->block.release(); b->edges.release(); delete b; return r; }
   *out = b;
   return B2DGPU_SUCCESS;
@@ -878,7 +939,7 @@ extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* 
   in.command_count = b->command_count; in.supplied_edges = b->supplied_edges; in.segment_count = b->segment_count;
   in.origin_x = b->origin_x; in.origin_y = b->origin_y;
   in.has_analytic = b->has_analytic;
-  in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged;
+  in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged; in.prepped = false;
   in.stream_ok = b->stream_ok; memcpy(in.stream_box, b->stream_box, sizeof(in.stream_box));
   in.solid = b->solid;
   // The whole path (K1 count, scan, K1 write, finalize, K2+K3) re-runs on every render; only the host read-back of the
