@@ -32,7 +32,17 @@ B2D_HD int x86_nearby_f32(float v) {
 #endif
 }
 
-B2D_HD float f32_abs(float v) { return v < 0.0f ? -v : v; }                  // bl_abs
+// bl_abs(float) of the reference is `v < 0 ? -v : v`, which keeps -0.0f where fabsf() gives +0.0f.  In the two
+// gradient fetchers that use it the sign of a zero never reaches the table index (it can only flow into additions,
+// a square root and a float -> int conversion, all of which map -0 and +0 to the same index; the one division is
+// 0 / 0 = NaN for either sign), so the device uses the free |x| operand modifier.
+B2D_HD float f32_abs(float v) {
+#if defined(__CUDA_ARCH__)
+  return fabsf(v);
+#else
+  return v < 0.0f ? -v : v;
+#endif
+}
 B2D_HD uint32_t f32_bits(float v) { union { float f; uint32_t u; } c; c.f = v; return c.u; }
 
 // Everything a fetcher needs besides (x, y).

@@ -84,14 +84,14 @@ B2D_HD NormEdge normalize_edge(b2dgpu_edge ed) {
 // Columns an edge can touch inside the band of rows [band_y, band_y + kTileH): cells [min >> 8, (max >> 8) + 1]
 // (cell_merge writes x and x + 1) of the edge's part inside the band, with one more column of slack on each side for
 // the DDA's rounding.  Used by k_band_extents to cull (tile, command) pairs; must never be too tight.
-B2D_HD_COLD long long sdiv64(long long a, long long b) { return a / b; }      // out of line: ~100 instructions on the GPU
-
 B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi) {
-  const long long dx = (long long)ed.x1 - ed.x0, dy = (long long)ed.y1 - ed.y0;
+  // x at the band's first and last scanline boundary, by double-precision interpolation: |error| is far below the
+  // one-pixel slack added on each side (the products are exact in a double, the quotient is off by < 1 ulp).
+  const double slope = double(ed.x1 - ed.x0) / double(ed.y1 - ed.y0);
   const int ya = tmax(ed.y0, band_y << 8);
   const int yb = tmin(ed.y1, (band_y + kTileH) << 8);
-  const int xa = ed.x0 + int(sdiv64(dx * (ya - ed.y0), dy));
-  const int xb = ed.x0 + int(sdiv64(dx * (yb - ed.y0), dy));
+  const int xa = ed.x0 + int(slope * double(ya - ed.y0));
+  const int xb = ed.x0 + int(slope * double(yb - ed.y0));
   lo = tmax((tmin(xa, xb) >> 8) - 1, 0);
   hi = tmax((tmax(xa, xb) >> 8) + 2, 0);
 }

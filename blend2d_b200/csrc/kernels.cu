@@ -540,19 +540,21 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
             for (int i = 0; i < 4; i++) { m_lo[i] = mm; m_hi[i] = mm; }
           }
           else {
-            uint32_t c[kLanePx];
-            #pragma unroll
-            for (int i = 0; i < kLanePx; i++) c[i] = 0;
+            uint32_t cov[kLanePx];
+            const uint32_t rule = cmd.fill_rule_mask;
             const uint32_t n = pre.nent[row];
             if (!(flags & kPreOverflow) || n <= uint32_t(kEntCap)) {
-              // Fast path: the row's cells are the handful of entries phase 1 recorded.
-              carry += pre.carry_st[row];
+              // Fast path: the row's cells are the handful of entries phase 1 recorded.  The running sum of
+              // fillgeneric_p.h:285-297 at pixel x is the backdrop plus every entry at or left of x (u32 adds commute),
+              // so no prefix scan is needed: each entry is added to the pixels from its cell onwards.
+              carry += pre.carry_st[row] + (256u << 9);
+              #pragma unroll
+              for (int i = 0; i < kLanePx; i++) cov[i] = carry;
               for (uint32_t j = 0; j < n; j++) {
                 const uint2 en = pre.ent[row][j];
-                const uint32_t v = (int(en.x >> 3) == lane) ? en.y : 0u;
-                const uint32_t sel = en.x & 7u;
+                const int first = int(en.x) - lane * kLanePx;       // first pixel of this lane that the cell reaches
                 #pragma unroll
-                for (int i = 0; i < kLanePx; i++) c[i] += sel == uint32_t(i) ? v : 0u;
+                for (int i = 0; i < kLanePx; i++) cov[i] += (i >= first) ? en.y : 0u;
               }
             }
             else {
@@ -560,26 +562,27 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
               #pragma unroll
               for (int i = 0; i < kLanePx / 4; i++) {
                 uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * kLanePx + i * 4]);
-                c[i * 4 + 0] = cv.x; c[i * 4 + 1] = cv.y; c[i * 4 + 2] = cv.z; c[i * 4 + 3] = cv.w;
+                cov[i * 4 + 0] = cv.x; cov[i * 4 + 1] = cv.y; cov[i * 4 + 2] = cv.z; cov[i * 4 + 3] = cv.w;
               }
               carry += s_carry[row];
               __syncwarp();
+              // Prefix-sum of the row's cells: in the lane, then across the warp.
+              #pragma unroll
+              for (int i = 1; i < kLanePx; i++) cov[i] += cov[i - 1];
+              uint32_t inc = cov[kLanePx - 1];
+              #pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += t;
+              }
+              const uint32_t cov_base = (256u << 9) + carry + (inc - cov[kLanePx - 1]);
+              #pragma unroll
+              for (int i = 0; i < kLanePx; i++) cov[i] += cov_base;
             }
-            // Prefix-sum of the row's cells (fillgeneric_p.h:285-297) and 8-bit masks.
-            #pragma unroll
-            for (int i = 1; i < kLanePx; i++) c[i] += c[i - 1];
-            uint32_t inc = c[kLanePx - 1];
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-              if (lane >= o) inc += t;
-            }
-            const uint32_t cov_base = (256u << 9) + carry + (inc - c[kLanePx - 1]);
-            const uint32_t rule = cmd.fill_rule_mask;
             #pragma unroll
             for (int i = 0; i < 4; i++) {
-              m_lo[i] = calc_mask(cov_base + c[i], rule, alpha);
-              m_hi[i] = calc_mask(cov_base + c[4 + i], rule, alpha);
+              m_lo[i] = calc_mask(cov[i], rule, alpha);
+              m_hi[i] = calc_mask(cov[4 + i], rule, alpha);
             }
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
