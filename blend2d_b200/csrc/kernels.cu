@@ -308,7 +308,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 48, kEntCap = 10, kRing = 512, kLanePx = kTileW / 32 };
+enum : int { kSubChunk = 64, kEntCap = 10, kRing = 512, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 
 struct PreCmd {
@@ -318,7 +318,13 @@ struct PreCmd {
   uint32_t flags;
   uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
   uint2 ent[kTileH][kEntCap];       // (cell index relative to the tile, value to add)
+  // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B) and the right end of
+  // its clipped box.  (Staging the 176-byte FetchData as well was measured slower than reading it through L1.)
+  int bx1;
+  uint32_t pad_[5];
+  uint32_t cmd_words[sizeof(b2dgpu_command) / 4];
 };
+static_assert(sizeof(PreCmd) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
 
 // Coverage sink of phase 1: the few cells a straddling edge touches in a row are appended to that row's entry list.
 struct EntrySink {
@@ -366,7 +372,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
   __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
   __shared__ uint32_t s_carry[kTileH];
   __shared__ uint32_t s_list[kRing];
-  __shared__ __align__(16) PreCmd s_pre[kSubChunk];
+  extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSubChunk PreCmd records (dynamic: > 48 KB)
+  PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
   __shared__ uint32_t s_wcount[kTileH];
 
   const int tid = threadIdx.x;
@@ -445,14 +452,20 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
         if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; }
-        if (lane == 0) pre->flags = 0;
+        if (lane == 0) { pre->flags = 0; pre->bx1 = P.cmd_bbox_px[ci].z; }
+        {
+          // stage the command (one coalesced 64-byte load)
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(P.commands + ci);
+          uint32_t w = lane < int(sizeof(b2dgpu_command) / 4) ? __ldg(src + lane) : 0u;
+          if (lane < int(sizeof(b2dgpu_command) / 4)) pre->cmd_words[lane] = w;
+        }
         __syncwarp();
 
         uint32_t left_acc[kTileH];
         #pragma unroll
         for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
         uint32_t nstr = 0;
-        const bool is_box = P.commands[ci].type < B2DGPU_CMD_FILL_ANALYTIC;
+        const bool is_box = pre->cmd_words[0] < B2DGPU_CMD_FILL_ANALYTIC;
 
         if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
@@ -508,7 +521,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
         if (act_lo) { k = uint32_t(__ffs(act_lo) - 1); act_lo &= act_lo - 1; }
         else { k = 32u + uint32_t(__ffs(act_hi) - 1); act_hi &= act_hi - 1; }
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
-        const b2dgpu_command& cmd = P.commands[ci];
+        const PreCmd& pre = s_pre[k];
+        const b2dgpu_command& cmd = *reinterpret_cast<const b2dgpu_command*>(pre.cmd_words);
         const uint32_t type = cmd.type;
         const uint32_t alpha = cmd.alpha;
         uint32_t m_lo[4] = { 0, 0, 0, 0 }, m_hi[4] = { 0, 0, 0, 0 };
@@ -529,7 +543,6 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
           for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + 4 + i, py); }
         }
         else {
-          const PreCmd& pre = s_pre[k];
           const uint32_t flags = pre.flags;
           uint32_t carry = pre.carry_left[row];
           if (!(flags & kPreStraddle)) {
@@ -586,7 +599,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
             }
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
-          const int bx1 = P.cmd_bbox_px[ci].z;
+          const int bx1 = pre.bx1;
           if (bx1 < tx0 + kTileW) {
             #pragma unroll
             for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + 4 + i >= bx1) m_hi[i] = 0; }
@@ -926,17 +939,15 @@ int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
   if (!P.command_count) return 0;
   uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
   if (!tiles) return 0;
-  static int exp_dyn = -1;
-  if (exp_dyn < 0) {
-    const char* e = getenv("B2D_EXP_DYNSMEM");
-    exp_dyn = e ? atoi(e) : 0;
-    if (exp_dyn) {
-      cudaFuncSetAttribute(k_tile_render<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, exp_dyn);
-      cudaFuncSetAttribute(k_tile_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, exp_dyn);
-    }
+  static bool configured = false;
+  const int dyn = int(sizeof(PreCmd)) * kSubChunk;
+  if (!configured) {
+    cudaFuncSetAttribute(k_tile_render<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(k_tile_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    configured = true;
   }
-  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, exp_dyn, s>>>(P);
-  else k_tile_render<1><<<tiles, kTileThreads, exp_dyn, s>>>(P);
+  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, dyn, s>>>(P);
+  else k_tile_render<1><<<tiles, kTileThreads, dyn, s>>>(P);
   return 1;
 }
 
