@@ -28,7 +28,8 @@ enum : int { kA8Shift = 8, kA8Scale = 256, kA8Mask = 255 };
 // Tile geometry of the compositor (see DESIGN.md "Data layout in HBM").
 enum : int {
   kTileW = 256,            // pixels per tile row  (one warp, 8 px per lane -> 1 KiB of PRGB32 per row)
-  kTileH = 8,              // rows per tile        (one warp per row)
+  kTileHShift = 4,
+  kTileH = 1 << kTileHShift,   // rows per tile    (one warp per row)
   kTileThreads = 32 * kTileH
 };
 

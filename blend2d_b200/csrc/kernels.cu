@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
   if (c >= P.command_count) return;
   const int4 bb = P.cmd_bbox_px[c];
   if (bb.x >= bb.z || bb.y >= bb.w) return;
-  const int band0 = (bb.y - P.y_begin) >> 3, band1 = (bb.w - 1 - P.y_begin) >> 3;
+  const int band0 = (bb.y - P.y_begin) >> kTileHShift, band1 = (bb.w - 1 - P.y_begin) >> kTileHShift;
   uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
   if (P.commands[c].type < B2DGPU_CMD_FILL_ANALYTIC) {
     for (int b = band0 + int(lane); b <= band1; b += 32)
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
     if (ne.y0 == ne.y1) continue;
     const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
     if (row_first > row_last) continue;
-    for (int b = (row_first - P.y_begin) >> 3; b <= ((row_last - P.y_begin) >> 3); b++) {
+    for (int b = (row_first - P.y_begin) >> kTileHShift; b <= ((row_last - P.y_begin) >> kTileHShift); b++) {
       int lo, hi;
       band_edge_extent(ne, P.y_begin + b * kTileH, lo, hi);
       uint32_t* cell = ext + (size_t(b) * P.command_count + c) * 2;
@@ -368,7 +368,7 @@ __device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint
 }
 
 template<int BPP>
-__global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
+__global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
   __shared__ uint32_t s_carry[kTileH];
   __shared__ uint32_t s_list[kRing];
@@ -481,17 +481,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile_render(TileParams P) {
             uint32_t sb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle);
             nstr += __popc(sb);
             while (sb) {
-              // Up to 4 straddling edges x 8 rows = 32 (edge, row) items, one per lane.
+              // (32 / kTileH) straddling edges x kTileH rows = 32 (edge, row) items, one per lane.
               int src = -1;
               #pragma unroll
-              for (int q = 0; q < 4; q++) {
+              for (int q = 0; q < 32 / kTileH; q++) {
                 int bit = sb ? (__ffs(sb) - 1) : -1;
                 if (sb) sb &= sb - 1;
-                if ((lane >> 3) == q) src = bit;
+                if ((lane >> kTileHShift) == q) src = bit;
               }
               if (src >= 0) {
                 NormEdge ne = load_edge(edges, er.x + e0 + uint32_t(src));
-                const int r = lane & 7, y = ty0 + r;
+                const int r = lane & (kTileH - 1), y = ty0 + r;
                 if (y >= (ne.y0 >> 8) && y <= ((ne.y1 - 1) >> 8)) {
                   sink.row = r;
                   tile_rasterize_edge_row(ne, y, sink);

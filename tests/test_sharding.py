@@ -22,7 +22,7 @@ def test_slab_table_partitions_rows(height, world):
         assert a1 == b0 and a0 <= a1
     assert all(a % SH.TILE_ROWS == 0 for a, _ in t if a < height)
     sizes = [b - a for a, b in t]
-    assert max(sizes) - min(sizes) <= SH.TILE_ROWS or height < world * SH.TILE_ROWS
+    assert max(sizes) - min(sizes) < 2 * SH.TILE_ROWS or height < world * SH.TILE_ROWS   # one group, plus the clipped last slab
 
 
 def test_frames_round_robin():
