@@ -339,6 +339,10 @@ def run_gpu(args):
     else:
         px_all, e2e_px_all = px_per_step, e2e_px
 
+    band = None
+    if world > 1 and not args.no_band:
+        band = measure_band_sharded(G, N, lib, torch, dist, stream, rank, world, local_rank, args)
+
     if rank == 0:
         peaks = {}
         try:
@@ -381,6 +385,7 @@ def run_gpu(args):
                                  "algorithmic bytes (8 B per composited pixel) exceed DRAM traffic by the overdraw factor"},
             "clocks": clocks,
             "pixels_per_step": px_per_step, "canvas_checksum": checksum,
+            "band_sharded": band,
             "roofline_full_canvas": None if full is None else {
                 k: {"bound": "hbm", "kernel": "k_stream_solid<SrcOver>", "achieved": v["gbs"], "peak": peak, "unit": "GB/s",
                     "frac": v["gbs"] / peak, "kernel_ms": v["ms"], "algorithmic_bytes_per_launch": v["bytes"],
@@ -437,6 +442,62 @@ def measure_full_canvas(G, N, rt, lib, torch, stream, flush_buf):
     return out
 
 
+def measure_band_sharded(G, N, lib, torch, dist, stream, rank, world, local_rank, args):
+    """Config 5(i): ONE large canvas cut into tile-aligned slabs of rows, one per GPU (band sharding).
+    Every rank replays the whole command list clipped to its slab (b2dgpu_target_create_slab); the only exchange is the
+    final gather of the slabs to rank 0 over NCCL.  Strong scaling: the frame is fixed, the rows per GPU shrink."""
+    from blend2d_b200 import sharding as SH
+    side, n_fills = args.band_canvas, args.band_fills
+    scene, keep = make_config1_scene(n_fills, side, side, seed=4321)           # the same frame on every rank
+    rt = G.Runtime(device=local_rank, stream=stream.cuda_stream)
+    rec = G.Context(G.Image(side, side, G.FORMAT_PRGB32), record_only=True)    # host image: clip box only, never touched
+    N.check(lib.b2d_scene_replay(rec._h, C.byref(scene), 0, n_fills), "b2d_scene_replay(record)")
+    batch = G.ResidentBatch(rt._h, rec.peek_batch())
+    y0, y1 = SH.slab_rows(side, world, rank)
+    tgt = C.c_void_p()
+    N.check(lib.b2dgpu_target_create_slab(rt._h, side, side, y0, y1, G.FORMAT_PRGB32, C.byref(tgt)), "target_create_slab")
+    for _ in range(2):
+        N.check(lib.b2dgpu_target_clear(tgt), "clear"); batch.render(tgt)
+    torch.cuda.synchronize(); dist.barrier()
+    rt.stats(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    N.check(lib.b2dgpu_target_clear(tgt), "clear")
+    e0.record(stream); batch.render(tgt); e1.record(stream)
+    torch.cuda.synchronize()
+    st = rt.stats(reset=True)
+    # gather of the slabs (device to device over NVLink), timed separately
+    ptr, stride, pw, ph = C.c_void_p(), C.c_ssize_t(), C.c_int32(), C.c_int32()
+    N.check(lib.b2dgpu_target_device_view(tgt, C.byref(ptr), C.byref(stride), C.byref(pw), C.byref(ph)), "device_view")
+
+    class _Mem:
+        pass
+    m = _Mem()
+    m.__cuda_array_interface__ = {"shape": (ph.value, stride.value), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+    slab = torch.as_tensor(m, device=torch.device("cuda", local_rank))[: y1 - y0, : side * 4]
+    full = SH.gather_canvas(slab, side, dst=0)                                 # warm-up: NCCL channel setup, allocator
+    del full
+    dist.barrier(); torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(stream)
+    full = SH.gather_canvas(slab, side, dst=0)
+    g1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    px = torch.tensor([float(st["pixels_composited"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(px, op=dist.ReduceOp.SUM)
+    out = None
+    if rank == 0:
+        out = {"workload": f"config5(i): {n_fills} fills on one {side}x{side} PRGB32 canvas, band-sharded into {world} slabs of rows",
+               "render_ms_max_over_ranks": float(t[0]), "gather_ms": float(t[1]), "gathered_bytes": int(full.numel()),
+               "value": float(px[0]) / (float(t[0]) * 1e-3) / 1e6, "unit": "Mpix/s", "scaling": "strong",
+               "collective": "one torch.distributed.gather of the row slabs (NCCL), outside the render"}
+    del full
+    batch.close()
+    N.check(lib.b2dgpu_target_destroy(tgt), "target_destroy")
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -466,6 +527,9 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--no-band", action="store_true", help="skip the band-sharded 16384^2 measurement that runs when N > 1")
+    ap.add_argument("--band-canvas", type=int, default=16384)
+    ap.add_argument("--band-fills", type=int, default=600)
     ap.add_argument("--queue-limit", type=int, default=1024, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
