@@ -308,7 +308,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 64, kEntCap = 10, kRing = 512, kLanePx = kTileW / 32 };
+enum : int { kSubChunk = 64, kEntCap = 10, kRing = 1024, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 
 struct PreCmd {
@@ -514,12 +514,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
 
       // ---- phase 2 (K3): every warp replays the commands in order for ITS row; warps never wait for each other ----
       // Commands that leave the tile untouched (bounding box hit only) are compacted away first.
-      uint32_t act_lo = __ballot_sync(0xFFFFFFFFu, uint32_t(lane) < sub_n && s_pre[lane].active != 0);
-      uint32_t act_hi = __ballot_sync(0xFFFFFFFFu, uint32_t(lane + 32) < sub_n && s_pre[lane + 32].active != 0);
-      while (act_lo | act_hi) {
-        uint32_t k;
-        if (act_lo) { k = uint32_t(__ffs(act_lo) - 1); act_lo &= act_lo - 1; }
-        else { k = 32u + uint32_t(__ffs(act_hi) - 1); act_hi &= act_hi - 1; }
+      #pragma unroll 1
+      for (uint32_t kb = 0; kb < sub_n; kb += 32) {
+      uint32_t act = __ballot_sync(0xFFFFFFFFu, kb + uint32_t(lane) < sub_n && s_pre[kb + lane].active != 0);
+      while (act) {
+        const uint32_t k = kb + uint32_t(__ffs(act) - 1);
+        act &= act - 1;
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         const PreCmd& pre = s_pre[k];
         const b2dgpu_command& cmd = *reinterpret_cast<const b2dgpu_command*>(pre.cmd_words);
@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           }
         }
         dirty = true;
+      }
       }
     }
   }
