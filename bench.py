@@ -150,7 +150,7 @@ def host_threads():
     return max(1, min(32, n))            # BL_RUNTIME_MAX_THREAD_COUNT = 32 (blend2d/core/runtime.h:25)
 
 
-def run_reference(scene, sample, W, H, steps, warmup, threads):
+def run_reference(scene, sample, W, H, steps, warmup, threads, return_pixels=False):
     """Times the reference's CPU renderer (async MT) on the first `sample` fills.  Returns a dict or None."""
     lib = load_ref_driver()
     if lib is None:
@@ -160,13 +160,18 @@ def run_reference(scene, sample, W, H, steps, warmup, threads):
     if rc != 0:
         raise RuntimeError(f"ref_scene_count_pixels failed: 0x{rc:08X}")
     secs = (C.c_double * (steps + warmup))()
-    rc = lib.ref_scene_run(C.byref(scene), 0, sample, W, H, 1, threads, steps + warmup, secs, None, 0)
+    pixels = np.zeros((H, W), dtype=np.uint32) if return_pixels else None
+    rc = lib.ref_scene_run(C.byref(scene), 0, sample, W, H, 1, threads, steps + warmup, secs,
+                           pixels.ctypes.data_as(C.c_void_p) if return_pixels else None, W * 4 if return_pixels else 0)
     if rc != 0:
         raise RuntimeError(f"ref_scene_run failed: 0x{rc:08X}")
     timed = list(secs)[warmup:]
     total = sum(timed)
-    return {"mpix_s": px.value * steps / total / 1e6, "fills_s": sample * steps / total, "ms_per_step": total / steps * 1e3,
-            "pixels_per_step": int(px.value), "threads": threads}
+    out = {"mpix_s": px.value * steps / total / 1e6, "fills_s": sample * steps / total, "ms_per_step": total / steps * 1e3,
+           "pixels_per_step": int(px.value), "threads": threads}
+    if return_pixels:
+        out["pixels"] = pixels
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------------
