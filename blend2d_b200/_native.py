@@ -100,6 +100,8 @@ _SIGS = {
     "b2dgpu_target_upload": (_R, [_P, C.POINTER(ImageData)]),
     "b2dgpu_target_download": (_R, [_P, C.POINTER(ImageData)]),
     "b2dgpu_target_clear": (_R, [_P]),
+    "b2dgpu_host_register": (_R, [_P, _P, C.c_size_t]),
+    "b2dgpu_host_unregister": (_R, [_P, _P]),
     "b2dgpu_target_device_view": (_R, [_P, C.POINTER(_P), C.POINTER(C.c_ssize_t), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b2dgpu_submit": (_R, [_P, _P, C.POINTER(BatchView)]),
     "b2dgpu_batch_upload": (_R, [_P, C.POINTER(BatchView), C.POINTER(_P)]),

@@ -833,6 +833,7 @@ struct b2d_context {
   int32_t origin_x, origin_y;
   uint32_t queue_limit;
   bool record_only;             // commands are only queued (peek_batch); nothing can be flushed
+  bool registered;              // the image's pixels were page-locked by this context
 
   // State.
   uint32_t comp_op;
@@ -1085,11 +1086,17 @@ extern "C" b2dgpu_result b2d_context_create(b2d_image* target, const b2d_context
     if (info && (info->slab_y0 || info->slab_y1)) { y0 = info->slab_y0; y1 = info->slab_y1; }
     r = b2dgpu_target_create_slab(c->rt, target->w, target->h, y0, y1, target->format, &c->target);
   }
+  c->registered = false;
   if (!r && !c->record_only) {
     b2dgpu_image_data id; b2d_image_get_data(target, &id);
+    // Large canvases are page-locked for the lifetime of the context: flush(SYNC) then copies straight into them.
+    const size_t image_bytes = size_t(id.stride < 0 ? -id.stride : id.stride) * size_t(target->h);
+    if (image_bytes >= (size_t(4) << 20) && id.stride > 0)
+      c->registered = b2dgpu_host_register(c->rt, id.pixel_data, image_bytes) == B2DGPU_SUCCESS;
     r = b2dgpu_target_upload(c->target, &id);
   }
   if (r) {
+    if (c->registered) { b2dgpu_image_data id; b2d_image_get_data(target, &id); b2dgpu_host_unregister(c->rt, id.pixel_data); }
     if (c->target) b2dgpu_target_destroy(c->target);
     if (c->own_rt) b2dgpu_runtime_destroy(c->rt);
     delete c;
@@ -1139,6 +1146,7 @@ extern "C" b2dgpu_result b2d_context_destroy(b2d_context* c) {
   if (!c) return B2DGPU_ERROR_INVALID_VALUE;
   b2dgpu_result r = b2d_context_end(c);
   release_kept(c, false);
+  if (c->registered) { b2dgpu_image_data id; b2d_image_get_data(c->image, &id); b2dgpu_host_unregister(c->rt, id.pixel_data); }
   if (c->target) b2dgpu_target_destroy(c->target);
   if (c->own_rt) b2dgpu_runtime_destroy(c->rt);
   delete c;

@@ -418,6 +418,30 @@ extern "C" b2dgpu_result b2dgpu_target_device_view(b2dgpu_target* t, void** dev_
   return B2DGPU_SUCCESS;
 }
 
+extern "C" b2dgpu_result b2dgpu_host_register(b2dgpu_runtime* rt, void* pixels, size_t bytes) {
+  if (!rt || rt->magic != kRuntimeMagic || !pixels || !bytes) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_host_register: invalid argument");
+  cudaSetDevice(rt->device);
+  cudaError_t e = cudaHostRegister(pixels, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return B2DGPU_SUCCESS; }
+  if (e != cudaSuccess) return cuda_fail(e, "b2dgpu_host_register");
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_host_unregister(b2dgpu_runtime* rt, void* pixels) {
+  if (!rt || rt->magic != kRuntimeMagic || !pixels) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_host_unregister: invalid argument");
+  cudaSetDevice(rt->device);
+  cudaStreamSynchronize(rt->stream);
+  cudaError_t e = cudaHostUnregister(pixels);
+  if (e != cudaSuccess) { cudaGetLastError(); }
+  return B2DGPU_SUCCESS;
+}
+
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 // The host image covers the FULL image; a slab target transfers only its own rows [y0, y0 + h).
 static b2dgpu_result target_copy(b2dgpu_target* t, const b2dgpu_image_data* img, bool upload) {
   if (!t || !img || !img->pixel_data) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target copy: invalid argument");
@@ -428,8 +452,22 @@ static b2dgpu_result target_copy(b2dgpu_target* t, const b2dgpu_image_data* img,
   cudaSetDevice(rt->device);
   size_t row_bytes = size_t(t->w) * t->bpp;
   uint8_t* host = static_cast<uint8_t*>(img->pixel_data) + intptr_t(t->y0) * img->stride;
-  // Pageable host memory: stage through a pinned buffer so the copy runs at full PCIe rate and stays stream ordered.
   size_t bytes = row_bytes * t->h;
+  if (host_is_pinned(host) && host_is_pinned(host + intptr_t(t->h - 1) * img->stride + row_bytes - 1)) {
+    // Page-locked image (b2dgpu_host_register): one direct 2-D DMA, no staging copy.
+    if (upload) {
+      CU_TRY(cudaMemcpy2DAsync(t->d_pixels, t->stride, host, size_t(img->stride), row_bytes, t->h, cudaMemcpyHostToDevice, rt->stream));
+      CU_TRY(cudaStreamSynchronize(rt->stream));               // the caller may modify the image right after
+      rt->stats.h2d_bytes += bytes;
+    }
+    else {
+      CU_TRY(cudaMemcpy2DAsync(host, size_t(img->stride), t->d_pixels, t->stride, row_bytes, t->h, cudaMemcpyDeviceToHost, rt->stream));
+      CU_TRY(cudaStreamSynchronize(rt->stream));
+      rt->stats.d2h_bytes += bytes;
+    }
+    return B2DGPU_SUCCESS;
+  }
+  // Pageable host memory: stage through a pinned buffer so the copy runs at full PCIe rate and stays stream ordered.
   CU_TRY(rt->image_staging.ensure(bytes));
   uint8_t* stage = static_cast<uint8_t*>(rt->image_staging.ptr);
   if (upload) {
@@ -719,7 +757,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
 
   const b2dgpu_command* d_cmds = reinterpret_cast<const b2dgpu_command*>(blk + L.commands);
   int4* d_bbox_fixed = reinterpret_cast<int4*>(blk + L.bbox_fixed);
-  uint32_t* d_seg_counts = reinterpret_cast<uint32_t*>(blk + L.seg_counts);
+
   uint32_t* d_seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
 
   cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };

@@ -256,6 +256,11 @@ B2DGPU_API b2dgpu_result b2dgpu_target_destroy(b2dgpu_target* t);
 B2DGPU_API b2dgpu_result b2dgpu_target_upload(b2dgpu_target* t, const b2dgpu_image_data* src);
 B2DGPU_API b2dgpu_result b2dgpu_target_download(b2dgpu_target* t, const b2dgpu_image_data* dst);
 B2DGPU_API b2dgpu_result b2dgpu_target_clear(b2dgpu_target* t);
+/* Optional: page-lock the host pixels of an image that will be uploaded / downloaded repeatedly, so the copies are
+ * direct DMA instead of going through the runtime's staging buffer.  The caller keeps the memory alive until
+ * b2dgpu_host_unregister().  (BLImage pixel memory is plain malloc memory: core/image.cpp:39-41.) */
+B2DGPU_API b2dgpu_result b2dgpu_host_register(b2dgpu_runtime* rt, void* pixels, size_t bytes);
+B2DGPU_API b2dgpu_result b2dgpu_host_unregister(b2dgpu_runtime* rt, void* pixels);
 /* Device view of the canvas (for torch / NCCL plumbing): base pointer of row y0, stride in bytes, padded extents. */
 B2DGPU_API b2dgpu_result b2dgpu_target_device_view(b2dgpu_target* t, void** dev_ptr, intptr_t* stride, int32_t* padded_w, int32_t* padded_h);
 
