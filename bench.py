@@ -70,6 +70,8 @@ def make_config1_scene(n_fills, W, H, seed):
     for i in range(n_fills):
         f = fills[i]
         kind = i % 3
+        if os.environ.get("B2D_BENCH_KIND"):             # experiment knob: 0 polygons only, 1 quads only, 2 cubics only
+            kind = int(os.environ["B2D_BENCH_KIND"])
         f.fill_rule = (i // 3) % 2
         f.comp_op = 0
         f.style = 1 + (i % 3 + i // 7) % 3
@@ -390,6 +392,11 @@ def run_gpu(args):
                                  "algorithmic bytes (8 B per composited pixel) exceed DRAM traffic by the overdraw factor"},
             "clocks": clocks,
             "pixels_per_step": px_per_step, "canvas_checksum": checksum,
+            "rasterizer": {"edges_per_step": st["edges"] / args.steps, "segments_per_step": int(view.segment_count),
+                           "edge_builder_and_binning_ms": build_ms_avg,
+                           "edges_per_s": (st["edges"] / args.steps) / (build_ms_avg * 1e-3) if build_ms_avg > 0 else None,
+                           "note": "K1 = k_count_edges + scan + k_write_edges + bbox + k_band_extents (CUDA events around them); "
+                                   "issue-slot utilisation of K2/K3 (k_tile_render) is in profiles/*.summary.txt"},
             "band_sharded": band,
             "roofline_full_canvas": None if full is None else {
                 k: {"bound": "hbm", "kernel": "k_stream_solid<SrcOver>", "achieved": v["gbs"], "peak": peak, "unit": "GB/s",

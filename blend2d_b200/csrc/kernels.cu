@@ -674,79 +674,92 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
 // nothing to order across tiles, so instead of one short-lived CTA per tile a persistent grid walks the canvas in
 // 16-byte chunks with four independent vector loads in flight per thread before any of them is consumed.
 // =================================================================================================================
-enum : int { kStreamMaxCmds = 8, kStreamUnroll = 4 };
+enum : int { kStreamMaxCmds = 8, kStreamUnroll = 2 };
+
+// What a streaming thread needs of one command, decoded once per CTA.
+struct StreamCmd {
+  uint32_t type, alpha, comp_op, pad_;
+  int box[4];                 // BOX_A: pixels
+  BoxUParams bu;              // BOX_U: closed form of the mask-command program
+  FetchEnv env;
+};
 
 template<int BPP>
-__device__ __forceinline__ void stream_chunk(const TileParams& P, const b2dgpu_command* cmds, int ncmd, int x, int y, uint32_t* d, uint32_t& written) {
+__device__ __forceinline__ void stream_chunk(const StreamCmd* cmds, int ncmd, int x, int y, uint32_t* d, uint32_t& written) {
   for (int k = 0; k < ncmd; k++) {
-    const b2dgpu_command& cmd = cmds[k];
+    const StreamCmd& cmd = cmds[k];
     uint32_t m[4];
+    bool opaque;
     if (cmd.type == B2DGPU_CMD_FILL_BOX_A) {
       const bool in_y = y >= cmd.box[1] && y < cmd.box[3];
       #pragma unroll
       for (int i = 0; i < 4; i++) m[i] = (in_y && x + i >= cmd.box[0] && x + i < cmd.box[2]) ? cmd.alpha : 0u;
+      opaque = cmd.alpha == 255u;
     }
     else {
-      BoxUParams bu = box_u_setup(cmd.box, cmd.alpha);
       #pragma unroll
-      for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, x + i, y);
+      for (int i = 0; i < 4; i++) m[i] = box_u_mask(cmd.bu, x + i, y);
+      opaque = false;
     }
     if ((m[0] | m[1] | m[2] | m[3]) == 0) continue;
-    const uint32_t sig = cmd.signature;
-    FetchEnv env;
-    env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
-    env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
-    env.solid = cmd.solid_prgb32;
-    env.fd = P.fetch_data + cmd.fetch_index;
-    env.bayer = P.bayer;
-    env.origin_x = P.origin_x; env.origin_y = P.origin_y;
     uint32_t s[4] = { 0, 0, 0, 0 };
-    fetch4(env, uint32_t(x), uint32_t(y), m, s);
+    fetch4(cmd.env, uint32_t(x), uint32_t(y), m, s);
     if (BPP == 1) {
       #pragma unroll
       for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
     }
-    composite4(B2DGPU_SIG_COMP_OP(sig), d, s, m);
+    composite4(cmd.comp_op, d, s, m, opaque);
     written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
   }
 }
 
 template<int BPP>
-__global__ void __launch_bounds__(256) k_box_stream(TileParams P, int rows, int y0r, int x0c, int chunks_per_row) {
-  __shared__ b2dgpu_command s_cmds[kStreamMaxCmds];
+__global__ void __launch_bounds__(256) k_box_stream(TileParams P, int rows, int y0r, int x0c, int chunks_per_row, int step_r, int step_c) {
+  __shared__ StreamCmd s_cmds[kStreamMaxCmds];
   const int ncmd = int(P.command_count);
-  for (int i = threadIdx.x; i < ncmd * int(sizeof(b2dgpu_command) / 4); i += blockDim.x)
-    reinterpret_cast<uint32_t*>(s_cmds)[i] = reinterpret_cast<const uint32_t*>(P.commands)[i];
+  if (threadIdx.x < ncmd) {
+    const b2dgpu_command& c = P.commands[threadIdx.x];
+    StreamCmd& o = s_cmds[threadIdx.x];
+    o.type = c.type; o.alpha = c.alpha; o.comp_op = B2DGPU_SIG_COMP_OP(c.signature); o.pad_ = 0;
+    o.box[0] = c.box[0]; o.box[1] = c.box[1]; o.box[2] = c.box[2]; o.box[3] = c.box[3];
+    o.bu = box_u_setup(c.box, c.alpha);
+    o.env.fetch_type = B2DGPU_SIG_FETCH_TYPE(c.signature);
+    o.env.src_format = B2DGPU_SIG_SRC_FORMAT(c.signature);
+    o.env.solid = c.solid_prgb32;
+    o.env.fd = P.fetch_data + c.fetch_index;
+    o.env.bayer = P.bayer;
+    o.env.origin_x = P.origin_x; o.env.origin_y = P.origin_y;
+  }
   __syncthreads();
 
-  // The dirty region [x0c*4, ...) x [y0r, y0r + rows) in 4-pixel chunks; chunk -> (row, column) without division in
-  // the inner loop would need 2-D indexing, the 64-bit divide below costs less than 1% of the memory time.
-  const long long total = (long long)rows * chunks_per_row;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  // The dirty region in 4-pixel chunks.  The linear chunk index advances by a fixed stride; (row, column) follow it
+  // without a division: stride = step_r rows + step_c columns (computed by the launcher).
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int r = int(tid / chunks_per_row);
+  int c = int(tid - (long long)r * chunks_per_row);
   uint32_t written = 0;
-  for (long long c0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; c0 < total; c0 += stride * kStreamUnroll) {
+  while (r < rows) {
     uint4 v[kStreamUnroll];
     int xs[kStreamUnroll], ys[kStreamUnroll];
     uint8_t* ptr[kStreamUnroll];
     #pragma unroll
     for (int u = 0; u < kStreamUnroll; u++) {
-      long long c = c0 + stride * u;
-      bool ok = c < total;
-      int r = ok ? int(c / chunks_per_row) : 0;
-      int cc = ok ? int(c - (long long)r * chunks_per_row) : 0;
-      ys[u] = y0r + r;
-      xs[u] = (x0c + cc) * 4;
-      ptr[u] = ok ? P.dst + size_t(ys[u] - P.y_begin) * P.dst_stride + size_t(xs[u]) * BPP : nullptr;
-      if (ok) {
+      ptr[u] = nullptr;
+      if (r < rows) {
+        ys[u] = y0r + r;
+        xs[u] = (x0c + c) * 4;
+        ptr[u] = P.dst + size_t(ys[u] - P.y_begin) * P.dst_stride + size_t(xs[u]) * BPP;
         if (BPP == 4) v[u] = *reinterpret_cast<const uint4*>(ptr[u]);
         else { uint32_t b = *reinterpret_cast<const uint32_t*>(ptr[u]); v[u] = make_uint4((b & 0xFFu) * 0x01010101u, ((b >> 8) & 0xFFu) * 0x01010101u, ((b >> 16) & 0xFFu) * 0x01010101u, (b >> 24) * 0x01010101u); }
       }
+      c += step_c; r += step_r;
+      if (c >= chunks_per_row) { c -= chunks_per_row; r++; }
     }
     #pragma unroll
     for (int u = 0; u < kStreamUnroll; u++) {
       if (!ptr[u]) continue;
       uint32_t d[4] = { v[u].x, v[u].y, v[u].z, v[u].w };
-      stream_chunk<BPP>(P, s_cmds, ncmd, xs[u], ys[u], d, written);
+      stream_chunk<BPP>(s_cmds, ncmd, xs[u], ys[u], d, written);
       if (BPP == 4) *reinterpret_cast<uint4*>(ptr[u]) = make_uint4(d[0], d[1], d[2], d[3]);
       else *reinterpret_cast<uint32_t*>(ptr[u]) = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
     }
@@ -897,12 +910,22 @@ int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count
   int rows = box[3] - box[1];
   int chunks_per_row = x1c - x0c;
   if (rows <= 0 || chunks_per_row <= 0) return 0;
+  static int per_sm[2] = { 0, 0 };
+  const int which = bpp == 4 ? 0 : 1;
+  if (!per_sm[which]) {
+    int n = 0;
+    const void* fn = bpp == 4 ? (const void*)k_box_stream<4> : (const void*)k_box_stream<1>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, 256, 0) != cudaSuccess || n < 1) n = 2;
+    per_sm[which] = n;
+  }
   long long total = (long long)rows * chunks_per_row;
   long long want = (total + 256LL * kStreamUnroll - 1) / (256LL * kStreamUnroll);
-  int grid = int(want < (long long)sm_count * 8 ? want : (long long)sm_count * 8);
-  if (grid < 1) grid = 1;
-  if (bpp == 4) k_box_stream<4><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
-  else k_box_stream<1><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row);
+  const long long cap = (long long)sm_count * per_sm[which];
+  int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
+  const long long stride = (long long)grid * 256;
+  const int step_r = int(stride / chunks_per_row), step_c = int(stride - (long long)step_r * chunks_per_row);
+  if (bpp == 4) k_box_stream<4><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row, step_r, step_c);
+  else k_box_stream<1><<<grid, 256, 0, s>>>(P, rows, box[1], x0c, chunks_per_row, step_r, step_c);
   return 1;
 }
 

@@ -49,3 +49,16 @@ run("pattern round nearest SrcCopy 4K", S.pattern_shapes("round", 5000, 256, W, 
 run("pattern rot bilinear Multiply 4K", S.pattern_shapes("rot", 5000, 256, W, H, 1, 1, S.MULTIPLY), W, H)
 run("glyph-like 20px paths 4K", glyph_like(50000, W, H), W, H)
 run("mixed fuzz 4K", S.mixed(5000, W, H), W, H)
+
+def fill_all_scene(style):
+    def scene(api, ctx, rng):
+        W, H = ctx.image.w, ctx.image.h
+        if style == "solid":
+            ctx.set_fill_style(0x80336699)
+        else:
+            ctx.set_fill_style(S.make_gradient(api, rng, {"linear": 0, "radial": 1, "conic": 2}[style], 0, 0.0, 0.0, float(W), float(H)))
+        ctx.fill_all()
+    return scene
+
+for style in ("solid", "linear", "radial", "conic"):
+    run(f"fill_all {style} 8192^2", fill_all_scene(style), 8192, 8192)
