@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSubChunk PreCmd records (dynamic: > 48 KB)
   PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
   __shared__ uint32_t s_wcount[kTileH];
+  __shared__ uint32_t s_next;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -444,11 +445,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       const uint32_t sub = ring_head;
       const uint32_t sub_n = min(uint32_t(kSubChunk), ring_tail - ring_head);
       ring_head += sub_n;
+      if (tid == 0) s_next = kTileH;                    // commands beyond the first kTileH are handed out dynamically
       __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
-      for (uint32_t k = row; k < sub_n; k += kTileH) {
+      for (uint32_t k = row; k < sub_n; ) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
         if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; }
@@ -509,6 +511,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           if (nstr) atomicOr(&pre->flags, kPreStraddle);
           pre->active = (is_box || nstr || any_left) ? 1u : 0u;
         }
+        // next command: whichever warp is free takes it (edge counts differ a lot between commands)
+        uint32_t nk = 0;
+        if (lane == 0) nk = atomicAdd(&s_next, 1u);
+        k = __shfl_sync(0xFFFFFFFFu, nk, 0);
       }
       __syncthreads();
 
