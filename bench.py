@@ -465,33 +465,49 @@ def measure_band_sharded(G, N, lib, torch, dist, stream, rank, world, local_rank
     rec = G.Context(G.Image(side, side, G.FORMAT_PRGB32), record_only=True)    # host image: clip box only, never touched
     N.check(lib.b2d_scene_replay(rec._h, C.byref(scene), 0, n_fills), "b2d_scene_replay(record)")
     batch = G.ResidentBatch(rt._h, rec.peek_batch())
-    y0, y1 = SH.slab_rows(side, world, rank)
-    tgt = C.c_void_p()
-    N.check(lib.b2dgpu_target_create_slab(rt._h, side, side, y0, y1, G.FORMAT_PRGB32, C.byref(tgt)), "target_create_slab")
+    # Interleaved ownership: `k` stripes per rank spread over the canvas (coverage is not uniform over the rows).
+    k = args.band_stripes
+    stripes = SH.stripes_of(rank, world, k, side)
+    tgts = []
+    for (y0, y1) in stripes:
+        t_ = C.c_void_p()
+        N.check(lib.b2dgpu_target_create_slab(rt._h, side, side, y0, y1, G.FORMAT_PRGB32, C.byref(t_)), "target_create_slab")
+        tgts.append(t_)
+
+    def render_all():
+        for t_ in tgts:
+            batch.render(t_)
+
     for _ in range(2):
-        N.check(lib.b2dgpu_target_clear(tgt), "clear"); batch.render(tgt)
+        for t_ in tgts:
+            N.check(lib.b2dgpu_target_clear(t_), "clear")
+        render_all()
     torch.cuda.synchronize(); dist.barrier()
     rt.stats(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    N.check(lib.b2dgpu_target_clear(tgt), "clear")
-    e0.record(stream); batch.render(tgt); e1.record(stream)
+    for t_ in tgts:
+        N.check(lib.b2dgpu_target_clear(t_), "clear")
+    e0.record(stream); render_all(); e1.record(stream)
     torch.cuda.synchronize()
     st = rt.stats(reset=True)
-    # gather of the slabs (device to device over NVLink), timed separately
-    ptr, stride, pw, ph = C.c_void_p(), C.c_ssize_t(), C.c_int32(), C.c_int32()
-    N.check(lib.b2dgpu_target_device_view(tgt, C.byref(ptr), C.byref(stride), C.byref(pw), C.byref(ph)), "device_view")
 
+    # gather of the stripes (device to device over NVLink), timed separately
     class _Mem:
         pass
-    m = _Mem()
-    m.__cuda_array_interface__ = {"shape": (ph.value, stride.value), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
-    slab = torch.as_tensor(m, device=torch.device("cuda", local_rank))[: y1 - y0, : side * 4]
-    full = SH.gather_canvas(slab, side, dst=0)                                 # warm-up: NCCL channel setup, allocator
+
+    def view_of(t_, rows):
+        ptr, stride, pw, ph = C.c_void_p(), C.c_ssize_t(), C.c_int32(), C.c_int32()
+        N.check(lib.b2dgpu_target_device_view(t_, C.byref(ptr), C.byref(stride), C.byref(pw), C.byref(ph)), "device_view")
+        m = _Mem()
+        m.__cuda_array_interface__ = {"shape": (ph.value, stride.value), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(m, device=torch.device("cuda", local_rank))[:rows, : side * 4]
+    local = [view_of(t_, y1 - y0) for t_, (y0, y1) in zip(tgts, stripes)]
+    full = SH.gather_stripes(local, side, k, dst=0)                            # warm-up: NCCL channel setup, allocator
     del full
     dist.barrier(); torch.cuda.synchronize()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(stream)
-    full = SH.gather_canvas(slab, side, dst=0)
+    full = SH.gather_stripes(local, side, k, dst=0)
     g1.record(stream)
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1), g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
@@ -500,13 +516,14 @@ def measure_band_sharded(G, N, lib, torch, dist, stream, rank, world, local_rank
     dist.all_reduce(px, op=dist.ReduceOp.SUM)
     out = None
     if rank == 0:
-        out = {"workload": f"config5(i): {n_fills} fills on one {side}x{side} PRGB32 canvas, band-sharded into {world} slabs of rows",
+        out = {"workload": f"config5(i): {n_fills} fills on one {side}x{side} PRGB32 canvas, band-sharded into {world} x {k} interleaved stripes of rows",
                "render_ms_max_over_ranks": float(t[0]), "gather_ms": float(t[1]), "gathered_bytes": int(full.numel()),
                "value": float(px[0]) / (float(t[0]) * 1e-3) / 1e6, "unit": "Mpix/s", "scaling": "strong",
                "collective": "one torch.distributed.gather of the row slabs (NCCL), outside the render"}
     del full
     batch.close()
-    N.check(lib.b2dgpu_target_destroy(tgt), "target_destroy")
+    for t_ in tgts:
+        N.check(lib.b2dgpu_target_destroy(t_), "target_destroy")
     return out
 
 
@@ -542,6 +559,7 @@ def main():
     ap.add_argument("--no-band", action="store_true", help="skip the band-sharded 16384^2 measurement that runs when N > 1")
     ap.add_argument("--band-canvas", type=int, default=16384)
     ap.add_argument("--band-fills", type=int, default=600)
+    ap.add_argument("--band-stripes", type=int, default=4, help="interleaved stripes per GPU in the band-sharded measurement")
     ap.add_argument("--queue-limit", type=int, default=1024, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)

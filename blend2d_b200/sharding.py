@@ -33,6 +33,42 @@ def slab_rows(height, world, rank, align=TILE_ROWS):
     return slab_table(height, world, align)[rank]
 
 
+def stripe_table(height, world, stripes_per_rank, align=TILE_ROWS):
+    """Interleaved band ownership (the reference hands bands to workers round robin for the same reason,
+    raster/workerproc.cpp:260-299): the canvas is cut into world * stripes_per_rank tile-aligned stripes and stripe j
+    belongs to rank j mod world, so every rank gets rows from all over the canvas and uneven coverage averages out.
+    Returns [(y0, y1)] for all stripes in canvas order."""
+    return slab_table(height, world * stripes_per_rank, align)
+
+
+def stripes_of(rank, world, stripes_per_rank, height, align=TILE_ROWS):
+    t = stripe_table(height, world, stripes_per_rank, align)
+    return [t[j] for j in range(rank, len(t), world)]
+
+
+def gather_stripes(local_stripes, height, stripes_per_rank, dst=0, group=None):
+    """Gathers interleaved stripes into the full image on rank `dst`.
+    local_stripes: list of tensors [rows of stripe, row_bytes], this rank's stripes in canvas order."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    table = stripe_table(height, world, stripes_per_rank)
+    tallest = max(b - a for a, b in table)
+    row_bytes = local_stripes[0].shape[1]
+    send = torch.zeros((stripes_per_rank, tallest, row_bytes), dtype=local_stripes[0].dtype, device=local_stripes[0].device)
+    mine = [table[j] for j in range(rank, len(table), world)]
+    for i, ((a, b), t) in enumerate(zip(mine, local_stripes)):
+        send[i, : b - a].copy_(t[: b - a])
+    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst, group=group)
+    if rank != dst:
+        return None
+    parts = []
+    for j, (a, b) in enumerate(table):
+        parts.append(recv[j % world][j // world, : b - a])
+    return torch.cat(parts, dim=0)
+
+
 def frames_of(rank, world, frame_count):
     """Indices of the frames rank `rank` renders (round robin, like scene i -> GPU i mod G)."""
     return range(rank, frame_count, world)

@@ -31,6 +31,14 @@ def test_frames_round_robin():
     assert owned[1] == [1, 5, 9]
 
 
+def test_stripes_interleave_and_cover():
+    t = SH.stripe_table(2160, 4, 3)
+    assert len(t) == 12 and t[0][0] == 0 and t[-1][1] == 2160
+    owned = [SH.stripes_of(r, 4, 3, 2160) for r in range(4)]
+    assert sorted(sum(owned, [])) == t
+    assert owned[1] == [t[1], t[5], t[9]]
+
+
 def free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -54,6 +62,12 @@ def worker(rank, world, port, out_dir):
         y0, y1 = SH.slab_rows(H, world, rank)
         slab = torch.from_numpy(full_render(7)[y0:y1].copy().view(np.uint8))
         canvas = SH.gather_canvas(slab, H, dst=0)
+        # interleaved stripes: two per rank
+        full_img = full_render(7)
+        mine = [torch.from_numpy(full_img[a:b].copy().view(np.uint8)) for a, b in SH.stripes_of(rank, world, 2, H)]
+        striped = SH.gather_stripes(mine, H, 2, dst=0)
+        if rank == 0:
+            assert np.array_equal(striped.numpy().view(np.uint32), full_img)
         # frame sharding: independent frames, only a checksum of checksums is reduced for the report
         sums = torch.zeros(6, dtype=torch.int64)
         for i in SH.frames_of(rank, world, 6):
