@@ -384,7 +384,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   const int tile_y = blockIdx.x / P.tiles_x;
   const int tx0 = tile_x * kTileW;
   const int ty0 = P.y_begin + tile_y * kTileH;          // absolute y of the tile's first row
-  const int px = tx0 + lane * kLanePx;
+  // A lane owns two groups of 4 consecutive pixels: `lo` in the left half of the row (px .. px + 3) and `hi` in the
+  // right half (px + kTileW/2 ..).  Each half is one perfectly coalesced 512-byte run per warp, and a half without
+  // coverage is skipped as a whole.
+  const int px = tx0 + lane * 4;
+  constexpr int kHalf = kTileW / 2;
   const int py = ty0 + row;
   const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
 
@@ -394,12 +398,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   uint32_t d_lo[4], d_hi[4];
   if (BPP == 4) {
     uint4 v0 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
-    uint4 v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4 + 16);
+    uint4 v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px + kHalf) * 4);
     d_lo[0] = v0.x; d_lo[1] = v0.y; d_lo[2] = v0.z; d_lo[3] = v0.w;
     d_hi[0] = v1.x; d_hi[1] = v1.y; d_hi[2] = v1.z; d_hi[3] = v1.w;
   }
   else {
-    uint2 v = *reinterpret_cast<const uint2*>(dst_row + px);
+    uint2 v;
+    v.x = *reinterpret_cast<const uint32_t*>(dst_row + px);
+    v.y = *reinterpret_cast<const uint32_t*>(dst_row + px + kHalf);
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       d_lo[i] = ((v.x >> (8 * i)) & 0xFFu) * 0x01010101u;
@@ -539,14 +545,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             #pragma unroll
             for (int i = 0; i < 4; i++) {
               m_lo[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
-              m_hi[i] = (px + 4 + i >= cmd.box[0] && px + 4 + i < cmd.box[2]) ? alpha : 0u;
+              m_hi[i] = (px + kHalf + i >= cmd.box[0] && px + kHalf + i < cmd.box[2]) ? alpha : 0u;
             }
           }
         }
         else if (type == B2DGPU_CMD_FILL_BOX_U) {
           BoxUParams bu = box_u_setup(cmd.box, alpha);
           #pragma unroll
-          for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + 4 + i, py); }
+          for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + kHalf + i, py); }
         }
         else {
           const uint32_t flags = pre.flags;
@@ -571,32 +577,38 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
               for (int i = 0; i < kLanePx; i++) cov[i] = carry;
               for (uint32_t j = 0; j < n; j++) {
                 const uint2 en = pre.ent[row][j];
-                const int first = int(en.x) - lane * kLanePx;       // first pixel of this lane that the cell reaches
+                const int first = int(en.x) - lane * 4;             // first pixel of the lo group that the cell reaches
                 #pragma unroll
-                for (int i = 0; i < kLanePx; i++) cov[i] += (i >= first) ? en.y : 0u;
+                for (int i = 0; i < 4; i++) {
+                  cov[i] += (i >= first) ? en.y : 0u;
+                  cov[4 + i] += (i + kHalf >= first) ? en.y : 0u;
+                }
               }
             }
             else {
               slow_row_cells(edges, P.cmd_edges[ci], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
-              #pragma unroll
-              for (int i = 0; i < kLanePx / 4; i++) {
-                uint4 cv = *reinterpret_cast<uint4*>(&s_cells[row][lane * kLanePx + i * 4]);
-                cov[i * 4 + 0] = cv.x; cov[i * 4 + 1] = cv.y; cov[i * 4 + 2] = cv.z; cov[i * 4 + 3] = cv.w;
+              {
+                uint4 c0 = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
+                uint4 c1 = *reinterpret_cast<uint4*>(&s_cells[row][kHalf + lane * 4]);
+                cov[0] = c0.x; cov[1] = c0.y; cov[2] = c0.z; cov[3] = c0.w;
+                cov[4] = c1.x; cov[5] = c1.y; cov[6] = c1.z; cov[7] = c1.w;
               }
               carry += s_carry[row];
               __syncwarp();
-              // Prefix-sum of the row's cells: in the lane, then across the warp.
+              // Prefix-sum of the row's cells: in the lane's groups, then across the warp, left half first.
               #pragma unroll
-              for (int i = 1; i < kLanePx; i++) cov[i] += cov[i - 1];
-              uint32_t inc = cov[kLanePx - 1];
+              for (int i = 1; i < 4; i++) { cov[i] += cov[i - 1]; cov[4 + i] += cov[4 + i - 1]; }
+              uint32_t inc_lo = cov[3], inc_hi = cov[7];
               #pragma unroll
               for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= o) inc += t;
+                uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, inc_lo, o), t1 = __shfl_up_sync(0xFFFFFFFFu, inc_hi, o);
+                if (lane >= o) { inc_lo += t0; inc_hi += t1; }
               }
-              const uint32_t cov_base = (256u << 9) + carry + (inc - cov[kLanePx - 1]);
+              const uint32_t total_lo = __shfl_sync(0xFFFFFFFFu, inc_lo, 31);
+              const uint32_t base_lo = (256u << 9) + carry + (inc_lo - cov[3]);
+              const uint32_t base_hi = (256u << 9) + carry + total_lo + (inc_hi - cov[7]);
               #pragma unroll
-              for (int i = 0; i < kLanePx; i++) cov[i] += cov_base;
+              for (int i = 0; i < 4; i++) { cov[i] += base_lo; cov[4 + i] += base_hi; }
             }
             #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -608,15 +620,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           const int bx1 = pre.bx1;
           if (bx1 < tx0 + kTileW) {
             #pragma unroll
-            for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + 4 + i >= bx1) m_hi[i] = 0; }
+            for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + kHalf + i >= bx1) m_hi[i] = 0; }
           }
         }
 
-        // ---- fetch + composite ----
-        // Warp-uniform exit: the lanes stay converged for the votes / shuffles of this and the next iteration.
-        const uint32_t any_m = m_lo[0] | m_lo[1] | m_lo[2] | m_lo[3] | m_hi[0] | m_hi[1] | m_hi[2] | m_hi[3];
-        if (!__any_sync(0xFFFFFFFFu, any_m != 0u)) continue;
-
+        // ---- fetch + composite, one half of the row at a time ----
+        // The votes keep every branch warp-uniform, so the lanes stay converged for the next iteration.
         const uint32_t sig = cmd.signature;
         FetchEnv env;
         env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
@@ -627,30 +636,29 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         env.origin_x = P.origin_x; env.origin_y = P.origin_y;
         const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
 
-        uint32_t not_opaque = 0;
-        #pragma unroll
-        for (int i = 0; i < 4; i++) not_opaque |= ((m_lo[i] + 1u) | (m_hi[i] + 1u)) & 0xFEu;
-        const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
-
-        // The two halves of the lane's 8 pixels go through ONE copy of the fetch / composite code (the loop is not
-        // unrolled; lo and hi swap places after each pass and are back where they started after the second).
+        // Both halves go through ONE copy of the fetch / composite code (the loop is not unrolled; lo and hi swap places
+        // after each pass and are back where they started after the second).
         #pragma unroll 1
         for (int h = 0; h < 2; h++) {
-          uint32_t s[4] = { 0, 0, 0, 0 };
-          fetch4(env, uint32_t(px + 4 * h), uint32_t(py), m_lo, s);
-          if (BPP == 1) {
-            #pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+          if (__any_sync(0xFFFFFFFFu, (m_lo[0] | m_lo[1] | m_lo[2] | m_lo[3]) != 0u)) {
+            const uint32_t not_opaque = ((m_lo[0] + 1u) | (m_lo[1] + 1u) | (m_lo[2] + 1u) | (m_lo[3] + 1u)) & 0xFEu;
+            const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
+            uint32_t s[4] = { 0, 0, 0, 0 };
+            fetch4(env, uint32_t(px + kHalf * h), uint32_t(py), m_lo, s);
+            if (BPP == 1) {
+              #pragma unroll
+              for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
+            }
+            composite4(comp_op, d_lo, s, m_lo, opaque);
+            px_written += (m_lo[0] != 0) + (m_lo[1] != 0) + (m_lo[2] != 0) + (m_lo[3] != 0);
+            dirty = true;
           }
-          composite4(comp_op, d_lo, s, m_lo, opaque);
-          px_written += (m_lo[0] != 0) + (m_lo[1] != 0) + (m_lo[2] != 0) + (m_lo[3] != 0);
           #pragma unroll
           for (int i = 0; i < 4; i++) {
             uint32_t t = d_lo[i]; d_lo[i] = d_hi[i]; d_hi[i] = t;
             t = m_lo[i]; m_lo[i] = m_hi[i]; m_hi[i] = t;
           }
         }
-        dirty = true;
       }
       }
     }
@@ -659,13 +667,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   if (dirty) {
     if (BPP == 4) {
       *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d_lo[0], d_lo[1], d_lo[2], d_lo[3]);
-      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4 + 16) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
+      *reinterpret_cast<uint4*>(dst_row + size_t(px + kHalf) * 4) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
     }
     else {
       uint2 v;
       v.x = (d_lo[0] >> 24) | ((d_lo[1] >> 24) << 8) | ((d_lo[2] >> 24) << 16) | ((d_lo[3] >> 24) << 24);
       v.y = (d_hi[0] >> 24) | ((d_hi[1] >> 24) << 8) | ((d_hi[2] >> 24) << 16) | ((d_hi[3] >> 24) << 24);
-      *reinterpret_cast<uint2*>(dst_row + px) = v;
+      *reinterpret_cast<uint32_t*>(dst_row + px) = v.x;
+      *reinterpret_cast<uint32_t*>(dst_row + px + kHalf) = v.y;
     }
   }
 
