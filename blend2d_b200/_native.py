@@ -138,6 +138,7 @@ _SIGS = {
     "b2d_context_clear_all": (_R, [_P]),
     "b2d_context_fill_all": (_R, [_P]),
     "b2d_context_fill_rect_i": (_R, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "b2d_context_fill_mask_i": (_R, [_P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int32)]),
     "b2d_context_fill_rect_d": (_R, [_P, C.c_double, C.c_double, C.c_double, C.c_double]),
     "b2d_context_fill_path_d": (_R, [_P, C.c_double, C.c_double, u8p, f64p, C.c_uint32]),
     "b2d_context_fill_polygon_d": (_R, [_P, f64p, C.c_uint32]),

@@ -229,6 +229,11 @@ class Context:
     def fill_rect_i(self, x, y, w, h): check(lib.b2d_context_fill_rect_i(self._h, x, y, w, h), "fill_rect_i")
     def fill_rect_d(self, x, y, w, h): check(lib.b2d_context_fill_rect_d(self._h, x, y, w, h), "fill_rect_d")
 
+    def fill_mask(self, x, y, mask, area=None):
+        """bl_context_fill_mask_i: the fill style through an A8 mask image placed at (x, y)."""
+        a = (C.c_int32 * 4)(*area) if area is not None else None
+        check(lib.b2d_context_fill_mask_i(self._h, x, y, mask._h, a), "fill_mask_i")
+
     def fill_path(self, path, origin=(0.0, 0.0)):
         cmd, vtx = path.arrays() if isinstance(path, Path) else path
         cmd = np.ascontiguousarray(cmd, dtype=np.uint8)

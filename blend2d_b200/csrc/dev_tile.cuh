@@ -3,6 +3,7 @@
 // (kernels.cu) and the test-only host simulator (tests/hostsim).
 #pragma once
 #include "dev_common.cuh"
+#include "dev_pixel.cuh"
 #include "dev_raster.cuh"
 #include "../../include/b2dgpu.h"
 
@@ -150,6 +151,17 @@ B2D_HD void tile_rasterize_edge_row(const NormEdge& ed, int y, Sink& sink) {
   edge_step_scanline(st, sink);
 }
 
+B2D_HD bool command_has_edges(uint32_t type) { return type == B2DGPU_CMD_FILL_ANALYTIC || type == B2DGPU_CMD_FILL_GEOMETRY; }
+
+// FillBoxMaskA (rendercommandprocsync_p.h:65-86): one VMask span per row of the box.  alpha == 255 takes the mask byte
+// as it is (kVMaskA8WithGA), otherwise m = udiv255(mask * alpha) (kVMaskA8WithoutGA, compopgeneric_p.h:175-183).
+B2D_HD uint32_t box_mask_a(const b2dgpu_command& cmd, const b2dgpu_pattern_source& mask, int x, int y) {
+  if (x < cmd.box[0] || x >= cmd.box[2] || y < cmd.box[1] || y >= cmd.box[3]) return 0u;
+  const uint8_t* row = static_cast<const uint8_t*>(mask.pixel_data) + intptr_t(y - cmd.box[1]) * mask.stride;
+  uint32_t m = row[x - cmd.box[0]];
+  return cmd.alpha >= 255u ? m : udiv255(m * cmd.alpha);
+}
+
 // Pixel bounding box [x0,x1) x [y0,y1) of a command, clipped to the rows [y_begin, y_end) of a `width`-wide target;
 // all zeros when the command cannot touch it.  `bb_fixed` = 24.8 bounds of an analytic command's edges.
 struct CmdBox { int x0, y0, x1, y1; };
@@ -157,7 +169,7 @@ struct CmdBox { int x0, y0, x1, y1; };
 B2D_HD CmdBox command_pixel_box(const b2dgpu_command& cmd, uint32_t edge_count, int fx0, int fy0, int fx1, int fy1,
                                 int width, int y_begin, int y_end) {
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-  if (cmd.type == B2DGPU_CMD_FILL_BOX_A) {
+  if (cmd.type == B2DGPU_CMD_FILL_BOX_A || cmd.type == B2DGPU_CMD_FILL_BOX_MASK_A) {
     x0 = cmd.box[0]; y0 = cmd.box[1]; x1 = cmd.box[2]; y1 = cmd.box[3];
   }
   else if (cmd.type == B2DGPU_CMD_FILL_BOX_U) {

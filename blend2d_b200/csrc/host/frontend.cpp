@@ -861,6 +861,7 @@ struct b2d_context {
   // like RenderFetchData's reference to its style (renderfetchdata_p.h:43, 181-184).
   std::vector<b2d_gradient*> kept_gradients;
   std::vector<b2d_pattern*> kept_patterns;
+  std::vector<b2d_image*> kept_images;          // masks of queued fill_mask commands
   bool dirty;                   // device canvas differs from the host image
 };
 
@@ -893,7 +894,8 @@ void release_kept(b2d_context* c, bool keep_current) {
   b2d_pattern* cur_p = (keep_current && !c->kept_patterns.empty()) ? c->kept_patterns.back() : nullptr;
   for (b2d_gradient* g : c->kept_gradients) if (g != cur_g) b2d_gradient_destroy(g);
   for (b2d_pattern* p : c->kept_patterns) if (p != cur_p) b2d_pattern_destroy(p);
-  c->kept_gradients.clear(); c->kept_patterns.clear();
+  for (b2d_image* im : c->kept_images) b2d_image_destroy(im);
+  c->kept_gradients.clear(); c->kept_patterns.clear(); c->kept_images.clear();
   if (cur_g) c->kept_gradients.push_back(cur_g);
   if (cur_p) c->kept_patterns.push_back(cur_p);
 }
@@ -1322,6 +1324,43 @@ extern "C" b2dgpu_result b2d_context_fill_rect_i(b2d_context* c, int32_t x, int3
   x1 = bmin<int64_t>(x1, c->image->w); y1 = bmin<int64_t>(y1, c->image->h);
   if ((x0 >= x1) | (y0 >= y1)) return B2DGPU_SUCCESS;
   return fill_box_a(c, r, int(x0), int(y0), int(x1), int(y1));
+}
+
+// bl_context_fill_mask_i: fill_mask_i_impl -> translate_and_clip_rect_to_blit_i -> fill_clipped_box_masked_a
+// (rastercontext.cpp:3723-3742, 922-1000, 3135-3175).  Only what the reference itself implements: an integral
+// translation; its fill_unclipped_mask_d() returns NOT_IMPLEMENTED for everything that is not pixel aligned.
+extern "C" b2dgpu_result b2d_context_fill_mask_i(b2d_context* c, int32_t x, int32_t y, const b2d_image* mask, const int32_t* area) {
+  if (!c || !mask) return B2DGPU_ERROR_INVALID_VALUE;
+  if (c->final_type >= kTTInvalid) return B2DGPU_SUCCESS;
+  int sx = 0, sy = 0, w = mask->w, h = mask->h;
+  if (area) {
+    unsigned max_w = unsigned(w) - unsigned(area[0]), max_h = unsigned(h) - unsigned(area[1]);
+    if ((max_w > unsigned(w)) | (unsigned(area[2]) > max_w) | (max_h > unsigned(h)) | (unsigned(area[3]) > max_h)) return B2DGPU_ERROR_INVALID_VALUE;
+    sx = area[0]; sy = area[1]; w = area[2]; h = area[3];
+  }
+  if (!c->integral_translation) return B2DGPU_ERROR_NOT_IMPLEMENTED;
+  if (mask->format != B2DGPU_FORMAT_A8) return B2DGPU_ERROR_NOT_IMPLEMENTED;         // the reference reads the mask rows as bytes
+  int64_t dx = int64_t(x) + c->tr_x, dy = int64_t(y) + c->tr_y;
+  int64_t x0 = dx, y0 = dy, x1 = dx + w, y1 = dy + h;
+  x0 = bmax<int64_t>(x0, 0); y0 = bmax<int64_t>(y0, 0);
+  x1 = bmin<int64_t>(x1, c->image->w); y1 = bmin<int64_t>(y1, c->image->h);
+  if ((x0 >= x1) | (y0 >= y1)) return B2DGPU_SUCCESS;
+  sx += int(x0 - dx); sy += int(y0 - dy);
+  Resolved r = resolve(c, false);
+  if (r.err) return r.err;
+  if (r.nop) return B2DGPU_SUCCESS;
+
+  b2dgpu_fetch_data fd; memset(&fd, 0, sizeof(fd));
+  fd.pattern.src.pixel_data = mask->data + intptr_t(sy) * mask->stride + intptr_t(sx);
+  fd.pattern.src.stride = mask->stride;
+  fd.pattern.src.w = int32_t(x1 - x0); fd.pattern.src.h = int32_t(y1 - y0);
+  b2dgpu_command cmd = make_command(r, B2DGPU_CMD_FILL_BOX_MASK_A, B2DGPU_FILL_MASK);
+  cmd.box[0] = int(x0); cmd.box[1] = int(y0); cmd.box[2] = int(x1); cmd.box[3] = int(y1);
+  cmd.reserved[0] = uint32_t(c->fetch.size());
+  c->fetch.push_back(fd);
+  const_cast<b2d_image*>(mask)->refs++;                                 // retained until the batch is submitted
+  c->kept_images.push_back(const_cast<b2d_image*>(mask));
+  return push_command(c, cmd);
 }
 
 extern "C" b2dgpu_result b2d_context_fill_rect_d(b2d_context* c, double x, double y, double w, double h) {

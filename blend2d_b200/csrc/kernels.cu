@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
   if (bb.x >= bb.z || bb.y >= bb.w) return;
   const int band0 = (bb.y - P.y_begin) >> kTileHShift, band1 = (bb.w - 1 - P.y_begin) >> kTileHShift;
   uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
-  if (P.commands[c].type < B2DGPU_CMD_FILL_ANALYTIC) {
+  if (!command_has_edges(P.commands[c].type)) {
     for (int b = band0 + int(lane); b <= band1; b += 32)
       band_ext[size_t(b) * P.command_count + c] = make_uint2(0u, 0u);               // every column
     return;
@@ -346,6 +346,15 @@ struct EntrySink {
     put(x + 1, area);
   }
 };
+
+// Masks of a lane's eight pixels for a FillBoxMaskA command (image masks are not in the bench's configurations: cold).
+struct Mask8 { uint4 lo, hi; };
+__device__ __noinline__ Mask8 box_mask_a_row(const b2dgpu_command& cmd, const b2dgpu_pattern_source& ms, int x_lo, int x_hi, int y) {
+  Mask8 m;
+  m.lo = make_uint4(box_mask_a(cmd, ms, x_lo, y), box_mask_a(cmd, ms, x_lo + 1, y), box_mask_a(cmd, ms, x_lo + 2, y), box_mask_a(cmd, ms, x_lo + 3, y));
+  m.hi = make_uint4(box_mask_a(cmd, ms, x_hi, y), box_mask_a(cmd, ms, x_hi + 1, y), box_mask_a(cmd, ms, x_hi + 2, y), box_mask_a(cmd, ms, x_hi + 3, y));
+  return m;
+}
 
 // Slow path of the replay (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
 // rasterizes its own row into its private shared-memory cell row.  Out of line: it is rare and large.
@@ -473,7 +482,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         #pragma unroll
         for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
         uint32_t nstr = 0;
-        const bool is_box = pre->cmd_words[0] < B2DGPU_CMD_FILL_ANALYTIC;
+        const bool is_box = !command_has_edges(pre->cmd_words[0]);
 
         if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
@@ -553,6 +562,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           BoxUParams bu = box_u_setup(cmd.box, alpha);
           #pragma unroll
           for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + kHalf + i, py); }
+        }
+        else if (type == B2DGPU_CMD_FILL_BOX_MASK_A) {
+          const Mask8 mk = box_mask_a_row(cmd, P.fetch_data[cmd.reserved[0]].pattern.src, px, px + kHalf, py);
+          m_lo[0] = mk.lo.x; m_lo[1] = mk.lo.y; m_lo[2] = mk.lo.z; m_lo[3] = mk.lo.w;
+          m_hi[0] = mk.hi.x; m_hi[1] = mk.hi.y; m_hi[2] = mk.hi.z; m_hi[3] = mk.hi.w;
         }
         else {
           const uint32_t flags = pre.flags;

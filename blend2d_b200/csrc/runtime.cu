@@ -513,7 +513,13 @@ static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
   if (v->command_count && !v->commands) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: commands is null");
   for (uint32_t i = 0; i < v->command_count; i++) {
     const b2dgpu_command& c = v->commands[i];
-    if (c.type < B2DGPU_CMD_FILL_BOX_A || c.type > B2DGPU_CMD_FILL_GEOMETRY) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: unknown command type");
+    if (c.type < B2DGPU_CMD_FILL_BOX_A || c.type > B2DGPU_CMD_FILL_BOX_MASK_A) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: unknown command type");
+    if (c.type == B2DGPU_CMD_FILL_BOX_MASK_A) {
+      if (c.reserved[0] >= v->fetch_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: mask index out of range");
+      const b2dgpu_pattern_source& ms = v->fetch_data[c.reserved[0]].pattern.src;
+      if (!(c.box[0] < c.box[2] && c.box[1] < c.box[3]) || ms.w < c.box[2] - c.box[0] || ms.h < c.box[3] - c.box[1])
+        return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: mask smaller than its box");
+    }
     if (!signature_supported(c.signature)) return fail(B2DGPU_ERROR_NOT_IMPLEMENTED, "batch view: command signature not implemented");
     if (c.alpha > 255) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: alpha out of range");
     if (B2DGPU_SIG_FETCH_TYPE(c.signature) != B2DGPU_FETCH_SOLID && c.fetch_index >= v->fetch_count)
@@ -587,6 +593,15 @@ static b2dgpu_result collect_blobs(const b2dgpu_batch_view* v, std::vector<Fetch
       return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: one fetch_data entry used with two different fetch types");
     }
     u.fetch_type = ft; u.src_format = sf; u.used = true;
+  }
+  // Image masks travel like A8 pattern pixels: a fetch_data entry whose pattern.src points at the mask rows.
+  for (uint32_t i = 0; i < v->command_count; i++) {
+    const b2dgpu_command& c = v->commands[i];
+    if (c.type != B2DGPU_CMD_FILL_BOX_MASK_A) continue;
+    FetchUse& u = uses[c.reserved[0]];
+    if (u.used && (u.fetch_type != B2DGPU_FETCH_PATTERN_ALIGNED_BLIT || u.src_format != B2DGPU_FORMAT_A8))
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: a mask entry is also used as a source");
+    u.fetch_type = B2DGPU_FETCH_PATTERN_ALIGNED_BLIT; u.src_format = B2DGPU_FORMAT_A8; u.used = true;
   }
 
   std::unordered_map<const void*, size_t> seen;

@@ -97,6 +97,10 @@ B2DGPU_API b2dgpu_result b2d_context_apply_transform_op(b2d_context* ctx, uint32
 B2DGPU_API b2dgpu_result b2d_context_clear_all(b2d_context* ctx);
 B2DGPU_API b2dgpu_result b2d_context_fill_all(b2d_context* ctx);
 B2DGPU_API b2dgpu_result b2d_context_fill_rect_i(b2d_context* ctx, int32_t x, int32_t y, int32_t w, int32_t h);
+/* bl_context_fill_mask_i (core/context.h): the fill style through an A8 mask image placed at (x, y); `mask_area` =
+ * {x, y, w, h} inside the mask or NULL for all of it.  Like the reference (rastercontext.cpp:3594-3650) only pixel
+ * aligned placements under a translation are implemented; anything else returns BL_ERROR_NOT_IMPLEMENTED. */
+B2DGPU_API b2dgpu_result b2d_context_fill_mask_i(b2d_context* ctx, int32_t x, int32_t y, const b2d_image* mask, const int32_t* mask_area);
 B2DGPU_API b2dgpu_result b2d_context_fill_rect_d(b2d_context* ctx, double x, double y, double w, double h);
 /* bl_context_fill_path_d(origin, path): BLPathView given as command bytes + vertices (x,y pairs). */
 B2DGPU_API b2dgpu_result b2d_context_fill_path_d(b2d_context* ctx, double ox, double oy, const uint8_t* cmd, const double* vtx, uint32_t count);

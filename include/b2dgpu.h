@@ -274,8 +274,12 @@ enum {
   B2DGPU_CMD_FILL_BOX_A    = 1,               /* RenderCommandType::kFillBoxA   - box in pixels                  */
   B2DGPU_CMD_FILL_BOX_U    = 2,               /* RenderCommandType::kFillBoxU   - box in 24.8 fixed point        */
   B2DGPU_CMD_FILL_ANALYTIC = 3,               /* RenderCommandType::kFillAnalytic with CPU-built edges           */
-  B2DGPU_CMD_FILL_GEOMETRY = 4                /* kFillAnalytic whose edges come from a RenderJob_GeometryOp:     */
-};                                            /* the GPU edge builder flattens/clips the path itself             */
+  B2DGPU_CMD_FILL_GEOMETRY = 4,               /* kFillAnalytic whose edges come from a RenderJob_GeometryOp:     */
+                                              /* the GPU edge builder flattens/clips the path itself             */
+  B2DGPU_CMD_FILL_BOX_MASK_A = 5              /* RenderCommandType::kFillBoxMaskA (rendercommand_p.h:44,107):    */
+};                                            /* box in pixels, per-pixel A8 mask; reserved[0] = index of a      */
+                                              /* fetch_data entry whose pattern.src describes the mask rows that */
+                                              /* start at the box's top-left pixel                                */
 
 typedef struct b2dgpu_command {               /* 64 bytes */
   uint32_t type;                              /* B2DGPU_CMD_*                                                    */

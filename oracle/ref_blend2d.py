@@ -59,6 +59,10 @@ class Rect(C.Structure):
     _fields_ = [("x", C.c_double), ("y", C.c_double), ("w", C.c_double), ("h", C.c_double)]
 
 
+class PointI(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32)]
+
+
 class Point(C.Structure):
     _fields_ = [("x", C.c_double), ("y", C.c_double)]
 
@@ -75,6 +79,7 @@ def _declare(l):
         "bl_image_init_as": [P(Core), C.c_int, C.c_int, u32],
         "bl_image_destroy": [P(Core)],
         "bl_image_make_mutable": [P(Core), P(ImageData)],
+        "bl_context_fill_mask_i": [P(Core), P(PointI), P(Core), P(RectI)],
         "bl_path_init": [P(Core)],
         "bl_path_destroy": [P(Core)],
         "bl_path_move_to": [P(Core), d, d],
@@ -262,6 +267,11 @@ class Context:
     def fill_rect_i(self, x, y, w, h):
         r = RectI(x, y, w, h)
         _check(lib().bl_context_fill_rect_i(C.byref(self._c), C.byref(r)), "fill_rect_i")
+
+    def fill_mask(self, x, y, mask, area=None):
+        pt = PointI(x, y)
+        a = RectI(*area) if area is not None else None
+        _check(lib().bl_context_fill_mask_i(C.byref(self._c), C.byref(pt), C.byref(mask._c), C.byref(a) if a is not None else None), "fill_mask_i")
 
     def fill_rect_d(self, x, y, w, h):
         r = Rect(x, y, w, h)

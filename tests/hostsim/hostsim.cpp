@@ -112,7 +112,7 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
   for (uint32_t c = 0; c < B->command_count; c++) {
     const CmdBox& bb = boxes[c];
     if (bb.x0 >= bb.x1 || bb.y0 >= bb.y1) continue;
-    if (B->commands[c].type < B2DGPU_CMD_FILL_ANALYTIC) {
+    if (!command_has_edges(B->commands[c].type)) {
       for (int b = bb.y0 >> kTileHShift; b <= (bb.y1 - 1) >> kTileHShift; b++) { ext_lo[size_t(b) * B->command_count + c] = 0; ext_hi[size_t(b) * B->command_count + c] = INT_MAX; }
       continue;
     }
@@ -147,6 +147,10 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
           int px = tx0 + x, py = ty0 + r;
           masks[r][x] = (py >= cmd.box[1] && py < cmd.box[3] && px >= cmd.box[0] && px < cmd.box[2]) ? alpha : 0u;
         }
+      }
+      else if (cmd.type == B2DGPU_CMD_FILL_BOX_MASK_A) {
+        const b2dgpu_pattern_source& ms = B->fetch_data[cmd.reserved[0]].pattern.src;
+        for (int r = 0; r < kTileH; r++) for (int x = 0; x < kTileW; x++) masks[r][x] = box_mask_a(cmd, ms, tx0 + x, ty0 + r);
       }
       else if (cmd.type == B2DGPU_CMD_FILL_BOX_U) {
         BoxUParams bu = box_u_setup(cmd.box, alpha);

@@ -207,3 +207,29 @@ def channel_diff(a, b):
     else:
         ca, cb = a.astype(np.int32), b.astype(np.int32)
     return int((a != b).sum()), int(np.abs(ca - cb).max()) if a.size else 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fill_mask (FillBoxMaskA): the style through A8 image masks, pixel aligned, clipped by the canvas and by mask areas
+# ---------------------------------------------------------------------------------------------------------------------
+def masked_fills(count, W, H, op=SRC_OVER, style="solid"):
+    def scene(api, ctx, rng):
+        masks = [make_texture(api, w, h, 3, 40 + k) for k, (w, h) in enumerate([(64, 48), (17, 33), (200, 9)])]
+        ctx.set_comp_op(op)
+        for i in range(count):
+            mask = masks[i % len(masks)]
+            x, y = int(rng.integers(-30, W - 10)), int(rng.integers(-20, H - 5))
+            style_for(api, ctx, rng, style, float(x), float(y), float(mask.w), float(mask.h))
+            ctx.set_global_alpha(1.0 if i % 3 else float(rng.uniform(0.1, 0.9)))
+            if i % 4 == 0:
+                aw, ah = int(rng.integers(1, mask.w + 1)), int(rng.integers(1, mask.h + 1))
+                ax, ay = int(rng.integers(0, mask.w - aw + 1)), int(rng.integers(0, mask.h - ah + 1))
+                ctx.fill_mask(x, y, mask, (ax, ay, aw, ah))
+            else:
+                ctx.fill_mask(x, y, mask)
+            if i % 5 == 0:
+                ctx.translate(3.0, -2.0)
+        ctx.reset_transform()
+        ctx.set_global_alpha(1.0)
+        ctx._keep_masks = masks
+    return scene

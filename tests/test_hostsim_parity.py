@@ -46,3 +46,9 @@ def test_patterns(ref, quality):
 @pytest.mark.parametrize("fmt", [1, 2, 3])
 def test_mixed_unaligned_canvas(ref, fmt):
     compare(ref, S.mixed(200, 513, 257), 513, 257, fmt, 9, max_diff=1)
+
+
+@pytest.mark.parametrize("style", ["solid", "radial"])
+@pytest.mark.parametrize("fmt", [1, 3])
+def test_fill_mask(ref, style, fmt):
+    compare(ref, S.masked_fills(80, 300, 200, S.SRC_OVER, style), 300, 200, fmt, 4)

@@ -128,3 +128,23 @@ def solid_stream_scene(op, alpha, rect):
 @pytest.mark.parametrize("rect", ["all", (8, 1, 1392, 990), (5, 3, 1391, 995)])
 def test_streaming_solid_fill(ref, gpu, fmt, op, alpha, rect):
     compare(ref, gpu, solid_stream_scene(op, alpha, rect), 1403, 1001, fmt)
+
+
+@pytest.mark.parametrize("style", ["solid", "linear", "radial"])
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+@pytest.mark.parametrize("op", [S.SRC_OVER, S.SRC_COPY])
+def test_fill_mask(ref, gpu, style, fmt, op):
+    """FillBoxMaskA: the style through A8 image masks (clipped, with mask areas, with and without global alpha)."""
+    compare(ref, gpu, S.masked_fills(120, 700, 300, op, style), 700, 300, fmt, 4)
+
+
+def test_fill_mask_unaligned_is_not_implemented(ref, gpu):
+    """Like the reference (rastercontext.cpp:3594-3650) a mask that is not pixel aligned is refused, not approximated."""
+    for api in (ref, gpu):
+        img = api.Image(64, 64, 1)
+        ctx = api.Context(img)
+        mask = S.make_texture(api, 16, 16, 3, 1)
+        ctx.translate(0.5, 0.25)
+        with pytest.raises(Exception):
+            ctx.fill_mask(3, 3, mask)
+        ctx.end()
