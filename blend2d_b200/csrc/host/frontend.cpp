@@ -18,6 +18,7 @@
 
 #include <new>
 #include <vector>
+#include <unordered_set>
 
 namespace {
 
@@ -862,6 +863,7 @@ struct b2d_context {
   std::vector<b2d_gradient*> kept_gradients;
   std::vector<b2d_pattern*> kept_patterns;
   std::vector<b2d_image*> kept_images;          // masks of queued fill_mask commands
+  std::unordered_set<uint32_t> known_signatures; // PipeLookupCache stand-in
   bool dirty;                   // device canvas differs from the host image
 };
 
@@ -967,6 +969,15 @@ b2dgpu_command make_command(const Resolved& r, uint32_t type, uint32_t fill_type
 }
 
 b2dgpu_result push_command(b2d_context* c, const b2dgpu_command& cmd) {
+  // Pipeline lookup (ensure_fetch_and_dispatch_data -> PipeProvider::get, rastercontext.cpp:1920-2029): the first time
+  // a signature is used the runtime is asked for it; BL_ERROR_NOT_IMPLEMENTED surfaces to the caller like the
+  // reference's static runtime does (fixedpiperuntime.cpp:314-315).
+  if (c->rt && c->known_signatures.find(cmd.signature) == c->known_signatures.end()) {
+    b2dgpu_dispatch_data dd;
+    b2dgpu_result lr = b2dgpu_runtime_get(c->rt, cmd.signature, &dd, nullptr);
+    if (lr) return lr;
+    c->known_signatures.insert(cmd.signature);
+  }
   c->cmds.push_back(cmd);
   if (c->cmds.size() >= c->queue_limit) return flush_batch(c);
   return B2DGPU_SUCCESS;

@@ -148,3 +148,21 @@ def test_fill_mask_unaligned_is_not_implemented(ref, gpu):
         with pytest.raises(Exception):
             ctx.fill_mask(3, 3, mask)
         ctx.end()
+
+
+def test_pipe_runtime_lookup_semantics(gpu):
+    """PipeRuntime::get / test (pipeline/piperuntime_p.h:39-62): success + a non-null token for implemented signatures,
+    BL_ERROR_NOT_IMPLEMENTED from get (fixedpiperuntime.cpp:314) and BL_ERROR_NO_ENTRY from test (pipegenruntime.cpp:78)."""
+    import ctypes as C
+    from blend2d_b200 import _native as N
+    rt = gpu.Runtime(device=0)
+    sig = lambda dst, src, op, fill, fetch: dst | (src << 4) | (op << 8) | (fill << 14) | (fetch << 16)
+    dd = N.DispatchData()
+    ok = sig(1, 1, 0, 3, 0)                                   # PRGB32 <- PRGB32, SrcOver, analytic fill, solid fetch
+    assert N.lib.b2dgpu_runtime_get(rt._h, ok, C.byref(dd), None) == 0 and dd.fill_func
+    assert N.lib.b2dgpu_runtime_test(rt._h, ok, C.byref(dd), None) == 0
+    src_in = sig(1, 1, 2, 3, 0)                               # BL_COMP_OP_SRC_IN: a next-row operator
+    assert N.lib.b2dgpu_runtime_get(rt._h, src_in, C.byref(dd), None) == 0x10007      # BL_ERROR_NOT_IMPLEMENTED
+    assert N.lib.b2dgpu_runtime_test(rt._h, src_in, C.byref(dd), None) == 0x10017     # BL_ERROR_NO_ENTRY
+    assert N.lib.b2dgpu_runtime_get(rt._h, ok | 0x80000000, C.byref(dd), None) != 0    # pending flag: not a pipeline
+    rt.close()
