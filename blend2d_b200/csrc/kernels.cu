@@ -992,12 +992,15 @@ int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
   if (!P.command_count) return 0;
   uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
   if (!tiles) return 0;
-  static bool configured = false;
+  // Function attributes are per device: remember which devices of this process were configured.
+  static bool configured[64] = {};
   const int dyn = int(sizeof(PreCmd)) * kSubChunk;
-  if (!configured) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(k_tile_render<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     cudaFuncSetAttribute(k_tile_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, dyn, s>>>(P);
   else k_tile_render<1><<<tiles, kTileThreads, dyn, s>>>(P);
