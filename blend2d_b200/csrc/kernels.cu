@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
   if (c >= P.command_count) return;
   const int4 bb = P.cmd_bbox_px[c];
   if (bb.x >= bb.z || bb.y >= bb.w) return;
-  const int band0 = (bb.y - P.y_begin) >> kTileHShift, band1 = (bb.w - 1 - P.y_begin) >> kTileHShift;
+  const int band0 = (bb.y - P.y_begin) / kTileH, band1 = (bb.w - 1 - P.y_begin) / kTileH;
   uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
   if (!command_has_edges(P.commands[c].type)) {
     for (int b = band0 + int(lane); b <= band1; b += 32)
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
     if (ne.y0 == ne.y1) continue;
     const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
     if (row_first > row_last) continue;
-    for (int b = (row_first - P.y_begin) >> kTileHShift; b <= ((row_last - P.y_begin) >> kTileHShift); b++) {
+    for (int b = (row_first - P.y_begin) / kTileH; b <= (row_last - P.y_begin) / kTileH; b++) {
       int lo, hi;
       band_edge_extent(ne, P.y_begin + b * kTileH, lo, hi);
       uint32_t* cell = ext + (size_t(b) * P.command_count + c) * 2;
@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   // right half (px + kTileW/2 ..).  Each half is one perfectly coalesced 512-byte run per warp, and a half without
   // coverage is skipped as a whole.
   const int px = tx0 + lane * 4;
-  constexpr int kHalf = kTileW / 2;
+  constexpr bool kTwoHalves = kTileW == 256;              // 8 pixels per lane; kTileW == 128: 4 pixels, no `hi` group
+  constexpr int kHalf = kTwoHalves ? kTileW / 2 : 0;
   const int py = ty0 + row;
   const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
 
@@ -407,14 +408,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   uint32_t d_lo[4], d_hi[4];
   if (BPP == 4) {
     uint4 v0 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
-    uint4 v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px + kHalf) * 4);
+    uint4 v1 = make_uint4(0, 0, 0, 0);
+    if (kTwoHalves) v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px + kHalf) * 4);
     d_lo[0] = v0.x; d_lo[1] = v0.y; d_lo[2] = v0.z; d_lo[3] = v0.w;
     d_hi[0] = v1.x; d_hi[1] = v1.y; d_hi[2] = v1.z; d_hi[3] = v1.w;
   }
   else {
     uint2 v;
     v.x = *reinterpret_cast<const uint32_t*>(dst_row + px);
-    v.y = *reinterpret_cast<const uint32_t*>(dst_row + px + kHalf);
+    v.y = kTwoHalves ? *reinterpret_cast<const uint32_t*>(dst_row + px + kHalf) : 0u;
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       d_lo[i] = ((v.x >> (8 * i)) & 0xFFu) * 0x01010101u;
@@ -498,17 +500,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             uint32_t sb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle);
             nstr += __popc(sb);
             while (sb) {
-              // (32 / kTileH) straddling edges x kTileH rows = 32 (edge, row) items, one per lane.
+              // (32 / kTileH) straddling edges x kTileH rows (edge, row) items, one per lane.
               int src = -1;
               #pragma unroll
               for (int q = 0; q < 32 / kTileH; q++) {
                 int bit = sb ? (__ffs(sb) - 1) : -1;
                 if (sb) sb &= sb - 1;
-                if ((lane >> kTileHShift) == q) src = bit;
+                if ((lane / kTileH) == q) src = bit;
               }
               if (src >= 0) {
                 NormEdge ne = load_edge(edges, er.x + e0 + uint32_t(src));
-                const int r = lane & (kTileH - 1), y = ty0 + r;
+                const int r = lane % kTileH, y = ty0 + r;
                 if (y >= (ne.y0 >> 8) && y <= ((ne.y1 - 1) >> 8)) {
                   sink.row = r;
                   tile_rasterize_edge_row(ne, y, sink);
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         // Both halves go through ONE copy of the fetch / composite code (the loop is not unrolled; lo and hi swap places
         // after each pass and are back where they started after the second).
         #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < (kTwoHalves ? 2 : 1); h++) {
           if (__any_sync(0xFFFFFFFFu, (m_lo[0] | m_lo[1] | m_lo[2] | m_lo[3]) != 0u)) {
             const uint32_t not_opaque = ((m_lo[0] + 1u) | (m_lo[1] + 1u) | (m_lo[2] + 1u) | (m_lo[3] + 1u)) & 0xFEu;
             const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
@@ -667,10 +669,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             px_written += (m_lo[0] != 0) + (m_lo[1] != 0) + (m_lo[2] != 0) + (m_lo[3] != 0);
             dirty = true;
           }
-          #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            uint32_t t = d_lo[i]; d_lo[i] = d_hi[i]; d_hi[i] = t;
-            t = m_lo[i]; m_lo[i] = m_hi[i]; m_hi[i] = t;
+          if (kTwoHalves) {
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+              uint32_t t = d_lo[i]; d_lo[i] = d_hi[i]; d_hi[i] = t;
+              t = m_lo[i]; m_lo[i] = m_hi[i]; m_hi[i] = t;
+            }
           }
         }
       }
@@ -681,14 +685,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   if (dirty) {
     if (BPP == 4) {
       *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d_lo[0], d_lo[1], d_lo[2], d_lo[3]);
-      *reinterpret_cast<uint4*>(dst_row + size_t(px + kHalf) * 4) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
+      if (kTwoHalves) *reinterpret_cast<uint4*>(dst_row + size_t(px + kHalf) * 4) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
     }
     else {
       uint2 v;
       v.x = (d_lo[0] >> 24) | ((d_lo[1] >> 24) << 8) | ((d_lo[2] >> 24) << 16) | ((d_lo[3] >> 24) << 24);
       v.y = (d_hi[0] >> 24) | ((d_hi[1] >> 24) << 8) | ((d_hi[2] >> 24) << 16) | ((d_hi[3] >> 24) << 24);
       *reinterpret_cast<uint32_t*>(dst_row + px) = v.x;
-      *reinterpret_cast<uint32_t*>(dst_row + px + kHalf) = v.y;
+      if (kTwoHalves) *reinterpret_cast<uint32_t*>(dst_row + px + kHalf) = v.y;
     }
   }
 

@@ -113,14 +113,14 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
     const CmdBox& bb = boxes[c];
     if (bb.x0 >= bb.x1 || bb.y0 >= bb.y1) continue;
     if (!command_has_edges(B->commands[c].type)) {
-      for (int b = bb.y0 >> kTileHShift; b <= (bb.y1 - 1) >> kTileHShift; b++) { ext_lo[size_t(b) * B->command_count + c] = 0; ext_hi[size_t(b) * B->command_count + c] = INT_MAX; }
+      for (int b = bb.y0 / kTileH; b <= (bb.y1 - 1) / kTileH; b++) { ext_lo[size_t(b) * B->command_count + c] = 0; ext_hi[size_t(b) * B->command_count + c] = INT_MAX; }
       continue;
     }
     for (uint32_t e = 0; e < e_count[c]; e++) {
       NormEdge ne = normalize_edge(edges[e_begin[c] + e]);
       if (ne.y0 == ne.y1) continue;
       const int row_first = tmax(ne.y0 >> 8, bb.y0), row_last = tmin((ne.y1 - 1) >> 8, bb.y1 - 1);
-      for (int b = row_first >> kTileHShift; row_first <= row_last && b <= (row_last >> kTileHShift); b++) {
+      for (int b = row_first / kTileH; row_first <= row_last && b <= row_last / kTileH; b++) {
         int lo, hi;
         band_edge_extent(ne, b * kTileH, lo, hi);
         int& l = ext_lo[size_t(b) * B->command_count + c]; l = tmin(l, lo);
