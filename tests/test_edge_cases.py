@@ -104,3 +104,50 @@ def test_gpu_empty_batch_and_repeated_flush(gpu):
     a = img.to_numpy()
     assert a[5, 5] == 0xFF00FF00 and a[20, 20] == 0
     ctx.close()
+
+
+def big_path_scene(api, ctx, rng):
+    """One path with tens of thousands of segments (a map-like outline): many edges per command, many crossings per
+    scanline - the entry lists overflow everywhere and the per-row fallback rasterizer is exercised on every tile."""
+    W, H = ctx.image.w, ctx.image.h
+    n = 20000
+    t = np.linspace(0.0, 40.0 * np.pi, n)
+    r = (0.1 + 0.9 * t / t[-1]) * min(W, H) * 0.48 * (1.0 + 0.08 * np.sin(37.0 * t))
+    xs, ys = W / 2 + r * np.cos(t), H / 2 + r * np.sin(t)
+    p = api.Path()
+    p.move_to(float(xs[0]), float(ys[0]))
+    for i in range(1, n, 3):
+        if i + 2 < n:
+            p.cubic_to(float(xs[i]), float(ys[i]), float(xs[i + 1]), float(ys[i + 1]), float(xs[i + 2]), float(ys[i + 2]))
+    p.close()
+    for rule, color in ((0, 0xC03070F0), (1, 0x80F0A020)):
+        ctx.set_fill_rule(rule)
+        ctx.set_fill_style(color)
+        ctx.fill_path(p)
+
+
+def test_hostsim_big_path(ref):
+    from tests import hostsim
+    n, d = run(hostsim.draw, ref, big_path_scene, 400, 300, 1)
+    assert (n, d) == (0, 0)
+
+
+@pytest.mark.gpu
+def test_gpu_big_path(ref, gpu):
+    n, d = run(gpu_draw(gpu), ref, big_path_scene, 1000, 700, 1)
+    assert (n, d) == (0, 0)
+
+
+@pytest.mark.gpu
+def test_gpu_many_commands_one_batch(ref, gpu):
+    """60 000 tiny fills in a single batch (the default queue limit is 65 536 commands)."""
+    W, H = 640, 480
+
+    def scene(api, ctx, rng):
+        xs, ys = rng.integers(0, W - 4, 60000), rng.integers(0, H - 4, 60000)
+        cols = rng.integers(0, 2 ** 32, 60000)
+        for x, y, c in zip(xs, ys, cols):
+            ctx.set_fill_style(int(c))
+            ctx.fill_rect_i(int(x), int(y), 3, 2)
+    n, d = run(gpu_draw(gpu), ref, scene, W, H, 1)
+    assert (n, d) == (0, 0)
