@@ -308,13 +308,15 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 64, kEntCap = 10, kRing = 1024, kLanePx = kTileW / 32 };
+enum : int { kSubChunk = 64, kEntCap = 6, kPoolCap = 4096, kRing = 1024, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
+enum : uint32_t { kDenseItems = 8u * kTileH };     // (edge, row) crossings per tile beyond which phase 1 gives up
 
 struct PreCmd {
   uint32_t carry_left[kTileH];      // backdrop per tile row from the edges entirely left of the tile
   uint32_t carry_st[kTileH];        // backdrop per tile row from straddling edges (their cells left of the tile)
-  uint32_t nent[kTileH];            // number of cell entries appended per row (may exceed kEntCap: overflow)
+  uint32_t nent[kTileH];            // number of cell entries appended per row (beyond kEntCap: chained in the pool)
+  uint32_t ovf_head[kTileH];        // 1 + pool index of the row's last chained entry, 0 = none
   uint32_t flags;
   uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
   uint2 ent[kTileH][kEntCap];       // (cell index relative to the tile, value to add)
@@ -327,8 +329,12 @@ struct PreCmd {
 static_assert(sizeof(PreCmd) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
 
 // Coverage sink of phase 1: the few cells a straddling edge touches in a row are appended to that row's entry list.
+// A row with more cells than its inline list holds (many crossings per scanline: bl_bench's random polygons, map-like
+// paths) chains the rest through a pool shared by the sub-chunk: pool entry = (cell | previous entry << 16, value).
 struct EntrySink {
   PreCmd* pre;
+  uint2* pool;
+  uint32_t* pool_next;
   int tx0;
   int row;
   __device__ __forceinline__ void put(int x, uint32_t v) {
@@ -338,7 +344,14 @@ struct EntrySink {
     else if (rel < kTileW) {
       uint32_t idx = atomicAdd(&pre->nent[row], 1u);
       if (idx < uint32_t(kEntCap)) pre->ent[row][idx] = make_uint2(uint32_t(rel), v);
-      else atomicOr(&pre->flags, kPreOverflow);
+      else {
+        const uint32_t pi = atomicAdd(pool_next, 1u);
+        if (pi < uint32_t(kPoolCap)) {
+          const uint32_t prev = atomicExch(&pre->ovf_head[row], pi + 1u);
+          pool[pi] = make_uint2(uint32_t(rel) | (prev << 16), v);
+        }
+        else atomicOr(&pre->flags, kPreOverflow);       // pool exhausted: the row re-rasterizes itself (slow_row_cells)
+      }
     }
   }
   __device__ __forceinline__ void merge(int x, uint32_t cover, uint32_t area) {
@@ -383,8 +396,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   __shared__ uint32_t s_list[kRing];
   extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSubChunk PreCmd records (dynamic: > 48 KB)
   PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
+  uint2* const s_pool = reinterpret_cast<uint2*>(s_dynamic + sizeof(PreCmd) * kSubChunk);      // kPoolCap chained entries
   __shared__ uint32_t s_wcount[kTileH];
   __shared__ uint32_t s_next;
+  __shared__ uint32_t s_pool_next;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       const uint32_t sub = ring_head;
       const uint32_t sub_n = min(uint32_t(kSubChunk), ring_tail - ring_head);
       ring_head += sub_n;
-      if (tid == 0) s_next = kTileH;                    // commands beyond the first kTileH are handed out dynamically
+      if (tid == 0) { s_next = kTileH; s_pool_next = 0; } // commands beyond the first kTileH are handed out dynamically
       __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       for (uint32_t k = row; k < sub_n; ) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
-        if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; }
+        if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
         if (lane == 0) { pre->flags = 0; pre->bx1 = P.cmd_bbox_px[ci].z; }
         {
           // stage the command (one coalesced 64-byte load)
@@ -483,22 +498,29 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         uint32_t left_acc[kTileH];
         #pragma unroll
         for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
-        uint32_t nstr = 0;
+        uint32_t nstr = 0, items = 0;                 // straddling edges / their (edge, row) crossings in this tile
         const bool is_box = !command_has_edges(pre->cmd_words[0]);
 
         if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
-          EntrySink sink; sink.pre = pre; sink.tx0 = tx0; sink.row = 0;
+          EntrySink sink; sink.pre = pre; sink.pool = s_pool; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
+            uint32_t rows_crossed = 0;
             if (e < er.y) {
               NormEdge ne = load_edge(edges, er.x + e);
               cls = tile_edge_class(ne, tx0, ty0);
               if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
+              if (cls == kEdgeStraddle)
+                rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + kTileH - 1) - max(ne.y0 >> 8, ty0) + 1);
             }
             uint32_t sb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle);
             nstr += __popc(sb);
+            items += __reduce_add_sync(0xFFFFFFFFu, rows_crossed);
+            // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
+            // row of the replay rasterizes itself (slow_row_cells).
+            if (items > kDenseItems) sb = 0;
             while (sb) {
               // (32 / kTileH) straddling edges x kTileH rows (edge, row) items, one per lane.
               int src = -1;
@@ -525,7 +547,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         if (lane == 0) {
           #pragma unroll
           for (int r = 0; r < kTileH; r++) pre->carry_left[r] = left_acc[r];
-          if (nstr) atomicOr(&pre->flags, kPreStraddle);
+          if (nstr) atomicOr(&pre->flags, items > kDenseItems ? (kPreStraddle | kPreOverflow) : kPreStraddle);
           pre->active = (is_box || nstr || any_left) ? 1u : 0u;
         }
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
@@ -584,15 +606,19 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             uint32_t cov[kLanePx];
             const uint32_t rule = cmd.fill_rule_mask;
             const uint32_t n = pre.nent[row];
-            if (!(flags & kPreOverflow) || n <= uint32_t(kEntCap)) {
+            if (!(flags & kPreOverflow)) {
               // Fast path: the row's cells are the handful of entries phase 1 recorded.  The running sum of
               // fillgeneric_p.h:285-297 at pixel x is the backdrop plus every entry at or left of x (u32 adds commute),
               // so no prefix scan is needed: each entry is added to the pixels from its cell onwards.
               carry += pre.carry_st[row] + (256u << 9);
               #pragma unroll
               for (int i = 0; i < kLanePx; i++) cov[i] = carry;
-              for (uint32_t j = 0; j < n; j++) {
-                const uint2 en = pre.ent[row][j];
+              const uint32_t n_inline = min(n, uint32_t(kEntCap));
+              uint32_t chain = n > uint32_t(kEntCap) ? pre.ovf_head[row] : 0u;
+              for (uint32_t j = 0; j < n_inline || chain; j++) {
+                uint2 en;
+                if (j < n_inline) en = pre.ent[row][j];
+                else { en = s_pool[chain - 1u]; chain = en.x >> 16; en.x &= 0xFFFFu; }
                 const int first = int(en.x) - lane * 4;             // first pixel of the lo group that the cell reaches
                 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -998,7 +1024,7 @@ int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
   if (!tiles) return 0;
   // Function attributes are per device: remember which devices of this process were configured.
   static bool configured[64] = {};
-  const int dyn = int(sizeof(PreCmd)) * kSubChunk;
+  const int dyn = int(sizeof(PreCmd)) * kSubChunk + kPoolCap * int(sizeof(uint2));
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
