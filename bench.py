@@ -253,7 +253,8 @@ def run_gpu(args):
     torch.cuda.set_stream(stream)
     rt = G.Runtime(device=local_rank, stream=stream.cuda_stream)
     img = G.Image(W, H, G.FORMAT_PRGB32)
-    # The e2e context flushes every `--queue-limit` commands: batch k renders while the host builds batch k + 1.
+    # The e2e context flushes in batches (adaptive by default: 512 commands, then doubling): batch k renders while the
+    # host builds batch k + 1.
     ctx = G.Context(img, device=local_rank, runtime=rt, command_queue_limit=args.queue_limit)
     lib = N.lib
     G_check = N.check
@@ -560,7 +561,7 @@ def main():
     ap.add_argument("--band-canvas", type=int, default=16384)
     ap.add_argument("--band-fills", type=int, default=600)
     ap.add_argument("--band-stripes", type=int, default=4, help="interleaved stripes per GPU in the band-sharded measurement")
-    ap.add_argument("--queue-limit", type=int, default=1024, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit)")
+    ap.add_argument("--queue-limit", type=int, default=0, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit); 0 = adaptive (512, doubling)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -833,6 +833,7 @@ struct b2d_context {
   uint32_t dst_format;
   int32_t origin_x, origin_y;
   uint32_t queue_limit;
+  bool adaptive_queue;          // command_queue_limit == 0: small first batch (the GPU starts early), then doubling
   bool record_only;             // commands are only queued (peek_batch); nothing can be flushed
   bool registered;              // the image's pixels were page-locked by this context
 
@@ -979,7 +980,13 @@ b2dgpu_result push_command(b2d_context* c, const b2dgpu_command& cmd) {
     c->known_signatures.insert(cmd.signature);
   }
   c->cmds.push_back(cmd);
-  if (c->cmds.size() >= c->queue_limit) return flush_batch(c);
+  if (c->cmds.size() >= c->queue_limit) {
+    b2dgpu_result fr = flush_batch(c);
+    // Adaptive batching: the first implicit flush of a frame comes early so the GPU starts while the host is still
+    // recording; later batches double in size, which amortises the per-batch kernels (b2dgpu_submit is pipelined).
+    if (c->adaptive_queue && c->queue_limit < 8192u) c->queue_limit *= 2u;
+    return fr;
+  }
   return B2DGPU_SUCCESS;
 }
 
@@ -1118,7 +1125,8 @@ extern "C" b2dgpu_result b2d_context_create(b2d_image* target, const b2d_context
   c->dst_format = target->format;
   c->origin_x = info ? info->pixel_origin_x : 0;
   c->origin_y = info ? info->pixel_origin_y : 0;
-  c->queue_limit = c->record_only ? 0xFFFFFFFFu : (info && info->command_queue_limit) ? info->command_queue_limit : 65536u;
+  c->adaptive_queue = !c->record_only && !(info && info->command_queue_limit);
+  c->queue_limit = c->record_only ? 0xFFFFFFFFu : c->adaptive_queue ? 512u : info->command_queue_limit;
   c->comp_op = kOpSrcOver;
   c->fill_rule = B2D_FILL_RULE_NON_ZERO;
   c->global_alpha = 1.0; c->fill_alpha = 1.0;
@@ -1142,6 +1150,7 @@ extern "C" b2dgpu_result b2d_context_flush(b2d_context* c, uint32_t flags) {
   if (c->record_only) return B2DGPU_SUCCESS;
   b2dgpu_result r = flush_batch(c);
   if (r) return r;
+  if (c->adaptive_queue) c->queue_limit = 512u;           // an explicit flush ends the frame: start small again
   if (flags & 0x80000000u) {
     if (c->dirty) {
       b2dgpu_image_data id; b2d_image_get_data(c->image, &id);

@@ -66,7 +66,9 @@ typedef struct b2d_context_create_info {      /* BLContextCreateInfo (core/conte
   uint32_t thread_count;                      /* ignored: the GPU grid replaces the worker pool                  */
   int32_t  pixel_origin_x, pixel_origin_y;
   int32_t  device;                            /* CUDA device ordinal                                             */
-  uint32_t command_queue_limit;               /* commands per batch before an implicit flush (0 = default)       */
+  uint32_t command_queue_limit;               /* commands per batch before an implicit flush; 0 = adaptive: 512,  */
+                                              /* doubling up to 8192 within a frame (BLContextCreateInfo has the  */
+                                              /* same field, core/context.h:338-346)                              */
   void*    runtime;                           /* optional shared b2dgpu_runtime*                                  */
   void*    stream;                            /* optional cudaStream_t for a runtime created by this context     */
   int32_t  slab_y0, slab_y1;                  /* band sharding: this context owns image rows [slab_y0, slab_y1) only;
