@@ -507,36 +507,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
-            uint32_t rows_crossed = 0;
+            uint32_t rows_crossed = 0, first_row = 0;
             if (e < er.y) {
               NormEdge ne = load_edge(edges, er.x + e);
               cls = tile_edge_class(ne, tx0, ty0);
               if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
-              if (cls == kEdgeStraddle)
-                rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + kTileH - 1) - max(ne.y0 >> 8, ty0) + 1);
+              if (cls == kEdgeStraddle) {
+                first_row = uint32_t(max(ne.y0 >> 8, ty0) - ty0);
+                rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + kTileH - 1) - ty0) - first_row + 1u;
+              }
             }
-            uint32_t sb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle);
-            nstr += __popc(sb);
-            items += __reduce_add_sync(0xFFFFFFFFu, rows_crossed);
+            nstr += __popc(__ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle));
+            // (edge, row) items of this chunk, packed densely over the lanes: inclusive scan of the rows each straddling
+            // edge crosses; item i belongs to the first edge whose inclusive count exceeds i.
+            uint32_t inc = rows_crossed;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+              if (lane >= o) inc += t;
+            }
+            const uint32_t chunk_items = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            items += chunk_items;
             // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
             // row of the replay rasterizes itself (slow_row_cells).
-            if (items > kDenseItems) sb = 0;
-            while (sb) {
-              // (32 / kTileH) straddling edges x kTileH rows (edge, row) items, one per lane.
-              int src = -1;
+            if (items > kDenseItems) continue;
+            for (uint32_t base_i = 0; base_i < chunk_items; base_i += 32) {
+              const uint32_t i = base_i + lane;
+              uint32_t j = 0;
               #pragma unroll
-              for (int q = 0; q < 32 / kTileH; q++) {
-                int bit = sb ? (__ffs(sb) - 1) : -1;
-                if (sb) sb &= sb - 1;
-                if ((lane / kTileH) == q) src = bit;
+              for (uint32_t step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, inc, int(j + step - 1u));
+                if (v <= i) j += step;
               }
-              if (src >= 0) {
-                NormEdge ne = load_edge(edges, er.x + e0 + uint32_t(src));
-                const int r = lane % kTileH, y = ty0 + r;
-                if (y >= (ne.y0 >> 8) && y <= ((ne.y1 - 1) >> 8)) {
-                  sink.row = r;
-                  tile_rasterize_edge_row(ne, y, sink);
-                }
+              const uint32_t j_inc = __shfl_sync(0xFFFFFFFFu, inc, int(j & 31u));
+              const uint32_t j_rows = __shfl_sync(0xFFFFFFFFu, rows_crossed, int(j & 31u));
+              const uint32_t j_first = __shfl_sync(0xFFFFFFFFu, first_row, int(j & 31u));
+              if (i < chunk_items) {
+                const int r = int(j_first + (i - (j_inc - j_rows)));
+                NormEdge ne = load_edge(edges, er.x + e0 + j);
+                sink.row = r;
+                tile_rasterize_edge_row(ne, ty0 + r, sink);
               }
             }
           }
