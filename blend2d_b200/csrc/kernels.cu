@@ -495,9 +495,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         }
         __syncwarp();
 
-        uint32_t left_acc[kTileH];
-        #pragma unroll
-        for (int r = 0; r < kTileH; r++) left_acc[r] = 0;
+        uint32_t left_acc = 0;                        // lane r < kTileH: backdrop of tile row r from the edges left of the tile
         uint32_t nstr = 0, items = 0;                 // straddling edges / their (edge, row) crossings in this tile
         const bool is_box = !command_has_edges(pre->cmd_words[0]);
 
@@ -508,16 +506,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
             uint32_t rows_crossed = 0, first_row = 0;
+            int ey0 = 0, ey1 = 0;
+            uint32_t esign = 0;
             if (e < er.y) {
               NormEdge ne = load_edge(edges, er.x + e);
               cls = tile_edge_class(ne, tx0, ty0);
-              if (cls == kEdgeLeft) tile_left_cover(ne, ty0, left_acc);
+              ey0 = ne.y0; ey1 = ne.y1; esign = ne.sign_bit;
               if (cls == kEdgeStraddle) {
                 first_row = uint32_t(max(ne.y0 >> 8, ty0) - ty0);
                 rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + kTileH - 1) - ty0) - first_row + 1u;
               }
             }
             nstr += __popc(__ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle));
+            // Edges entirely left of the tile: every scanline's cells of an edge sum to (cover << 9), cover = its signed
+            // y-extent inside the row.  One edge at a time is broadcast and every lane adds the cover of ITS row.
+            uint32_t lb = __ballot_sync(0xFFFFFFFFu, cls == kEdgeLeft);
+            while (lb) {
+              const int src = __ffs(lb) - 1;
+              lb &= lb - 1;
+              const int y0 = __shfl_sync(0xFFFFFFFFu, ey0, src), y1 = __shfl_sync(0xFFFFFFFFu, ey1, src);
+              const uint32_t sg = __shfl_sync(0xFFFFFFFFu, esign, src);
+              const int yt = (ty0 + lane) << 8;
+              const int cov = min(y1, yt + 256) - max(y0, yt);
+              if (cov > 0 && lane < kTileH) left_acc += uint32_t(sg ? -cov : cov) << 9;
+            }
             // (edge, row) items of this chunk, packed densely over the lanes: inclusive scan of the rows each straddling
             // edge crosses; item i belongs to the first edge whose inclusive count exceeds i.
             uint32_t inc = rows_crossed;
@@ -551,12 +563,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             }
           }
         }
-        uint32_t any_left = 0;
-        #pragma unroll
-        for (int r = 0; r < kTileH; r++) { left_acc[r] = __reduce_add_sync(0xFFFFFFFFu, left_acc[r]); any_left |= left_acc[r]; }
+        const bool any_left = __any_sync(0xFFFFFFFFu, left_acc != 0u);
+        if (lane < kTileH) pre->carry_left[lane] = left_acc;
         if (lane == 0) {
-          #pragma unroll
-          for (int r = 0; r < kTileH; r++) pre->carry_left[r] = left_acc[r];
           if (nstr) atomicOr(&pre->flags, items > kDenseItems ? (kPreStraddle | kPreOverflow) : kPreStraddle);
           pre->active = (is_box || nstr || any_left) ? 1u : 0u;
         }
