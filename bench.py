@@ -475,9 +475,10 @@ def measure_band_sharded(G, N, lib, torch, dist, stream, rank, world, local_rank
         N.check(lib.b2dgpu_target_create_slab(rt._h, side, side, y0, y1, G.FORMAT_PRGB32, C.byref(t_)), "target_create_slab")
         tgts.append(t_)
 
-    def render_all():
-        for t_ in tgts:
-            batch.render(t_)
+    tgt_array = (C.c_void_p * len(tgts))(*[t_.value for t_ in tgts])
+
+    def render_all():                                                           # one geometry pass, one compositing pass per stripe
+        N.check(lib.b2dgpu_batch_render_multi(rt._h, tgt_array, len(tgts), batch._h), "batch_render_multi")
 
     for _ in range(2):
         for t_ in tgts:
@@ -560,7 +561,7 @@ def main():
     ap.add_argument("--no-band", action="store_true", help="skip the band-sharded 16384^2 measurement that runs when N > 1")
     ap.add_argument("--band-canvas", type=int, default=16384)
     ap.add_argument("--band-fills", type=int, default=600)
-    ap.add_argument("--band-stripes", type=int, default=4, help="interleaved stripes per GPU in the band-sharded measurement")
+    ap.add_argument("--band-stripes", type=int, default=8, help="interleaved stripes per GPU in the band-sharded measurement")
     ap.add_argument("--queue-limit", type=int, default=0, help="commands per submitted batch on the e2e path (BLContextCreateInfo.command_queue_limit); 0 = adaptive (512, doubling)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)

@@ -106,6 +106,7 @@ _SIGS = {
     "b2dgpu_submit": (_R, [_P, _P, C.POINTER(BatchView)]),
     "b2dgpu_batch_upload": (_R, [_P, C.POINTER(BatchView), C.POINTER(_P)]),
     "b2dgpu_batch_destroy": (_R, [_P]),
+    "b2dgpu_batch_render_multi": (_R, [_P, C.POINTER(_P), C.c_uint32, _P]),
     "b2dgpu_batch_render": (_R, [_P, _P, _P]),
     "b2dgpu_sync": (_R, [_P]),
     "b2dgpu_get_stats": (_R, [_P, C.POINTER(Stats), C.c_int]),

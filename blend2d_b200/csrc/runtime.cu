@@ -764,7 +764,10 @@ static b2dgpu_result prep_block(b2dgpu_runtime* rt, RenderInput& in, cudaStream_
   return B2DGPU_SUCCESS;
 }
 
-static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderInput& in) {
+// Renders one prepared block into `ntargets` targets of the same image (slabs / stripes of one canvas): the geometry
+// pass (K1: count, scan, write, bounding boxes) runs once, the per-target part (clip to the rows, band extents,
+// compositing) once per target.
+static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targets, uint32_t ntargets, RenderInput& in) {
   const BlockLayout& L = *in.lay;
   cudaStream_t s = rt->stream;
   uint8_t* blk = in.block;
@@ -812,6 +815,8 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
   if (in.segment_count && in.built_edges)
     launches += launch_write_edges(B, s);
 
+  for (uint32_t ti = 0; ti < ntargets; ti++) {
+  b2dgpu_target* t = targets[ti];
   FinalizeParams F;
   F.commands = d_cmds;
   F.command_count = in.command_count;
@@ -855,7 +860,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
     launches += launch_band_extents(T, static_cast<uint2*>(rt->band_ext.ptr), s);
     T.band_ext = static_cast<const uint2*>(rt->band_ext.ptr);
   }
-  if (rt->profiling) CU_TRY(cudaEventRecord(ev[1], s));
+  if (rt->profiling && ti == 0) CU_TRY(cudaEventRecord(ev[1], s));
   bool streamed = false;
   if (in.stream_ok) {
     int box[4] = { in.stream_box[0] < 0 ? 0 : in.stream_box[0], in.stream_box[1] < t->y0 ? t->y0 : in.stream_box[1],
@@ -883,6 +888,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* t, RenderIn
     }
   }
   if (!streamed) launches += launch_tile_render(T, t->bpp, s);
+  }
   if (rt->profiling) {
     CU_TRY(cudaEventRecord(ev[2], s));
     for (int i = 0; i < 3; i++) rt->prof_events.push_back(ev[i]);
@@ -933,7 +939,7 @@ extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target
   CU_TRY(cudaEventRecord(rt->prep_ready, rt->prep_stream));
   CU_TRY(cudaStreamWaitEvent(rt->stream, rt->prep_ready, 0));
 
-  r = render_block(rt, target, in);
+  r = render_block(rt, &target, 1, in);
   if (r) return r;
   CU_TRY(cudaEventRecord(rt->slot_done[slot], rt->stream));
   rt->slot_busy[slot] = true;
@@ -981,9 +987,11 @@ extern "C" b2dgpu_result b2dgpu_batch_destroy(b2dgpu_batch* b) {
   return B2DGPU_SUCCESS;
 }
 
-extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* target, b2dgpu_batch* b) {
-  if (!rt || rt->magic != kRuntimeMagic || !target || target->rt != rt || !b || b->rt != rt)
+extern "C" b2dgpu_result b2dgpu_batch_render_multi(b2dgpu_runtime* rt, b2dgpu_target* const* targets, uint32_t target_count, b2dgpu_batch* b) {
+  if (!rt || rt->magic != kRuntimeMagic || !targets || !target_count || !b || b->rt != rt)
     return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_render: invalid argument");
+  for (uint32_t i = 0; i < target_count; i++)
+    if (!targets[i] || targets[i]->rt != rt) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_render: invalid target");
   if (!b->command_count) return B2DGPU_SUCCESS;
   std::lock_guard<std::mutex> lock(rt->mutex);
   cudaSetDevice(rt->device);
@@ -997,9 +1005,13 @@ extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* 
   in.solid = b->solid;
   // The whole path (K1 count, scan, K1 write, finalize, K2+K3) re-runs on every render; only the host read-back of the
   // edge total is skipped after the first time because the geometry of a resident batch cannot change.
-  b2dgpu_result r = render_block(rt, target, in);
+  b2dgpu_result r = render_block(rt, targets, target_count, in);
   b->built_known = in.built_known; b->built_edges = in.built_edges; b->edges_staged = in.edges_staged;
   return r;
+}
+
+extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* target, b2dgpu_batch* b) {
+  return b2dgpu_batch_render_multi(rt, &target, 1, b);
 }
 
 extern "C" b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_edge* edges_out,

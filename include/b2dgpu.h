@@ -340,6 +340,9 @@ typedef struct b2dgpu_batch b2dgpu_batch;
 B2DGPU_API b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_batch** out);
 B2DGPU_API b2dgpu_result b2dgpu_batch_destroy(b2dgpu_batch* b);
 B2DGPU_API b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* target, b2dgpu_batch* batch);
+/* Same batch into several slab targets of one canvas (interleaved stripes of a band-sharded image): the geometry pass
+ * runs once, clipping + compositing once per target. */
+B2DGPU_API b2dgpu_result b2dgpu_batch_render_multi(b2dgpu_runtime* rt, b2dgpu_target* const* targets, uint32_t target_count, b2dgpu_batch* batch);
 
 /* BL_CONTEXT_FLUSH_SYNC (core/context.h:105): blocks until everything submitted so far has executed. */
 B2DGPU_API b2dgpu_result b2dgpu_sync(b2dgpu_runtime* rt);

@@ -73,3 +73,29 @@ def test_prefix_matches_reference(ref, gpu, scene):
     a, b = got.to_numpy().astype(np.int64), r["pixels"].astype(np.int64)
     diff = max(int(np.abs(((a >> s) & 0xFF) - ((b >> s) & 0xFF)).max()) for s in (0, 8, 16, 24))
     assert diff <= 1, f"max channel difference {diff}"
+
+
+def test_render_multi_equals_separate_slabs(gpu, scene):
+    """b2dgpu_batch_render_multi (one geometry pass, several stripe targets) == rendering each stripe on its own."""
+    from blend2d_b200 import _native as N
+    from blend2d_b200 import sharding as SH
+    count = 2000
+    rec = gpu.Context(gpu.Image(W, H, 1), record_only=True)
+    N.check(N.lib.b2d_scene_replay(rec._h, C.byref(scene[0]), 0, count), "record")
+    rt = gpu.Runtime(device=0)
+    batch = gpu.ResidentBatch(rt._h, rec.peek_batch())
+    stripes = SH.stripe_table(H, 1, 5)
+    tg = []
+    for (y0, y1) in stripes:
+        t = C.c_void_p()
+        N.check(N.lib.b2dgpu_target_create_slab(rt._h, W, H, y0, y1, 1, C.byref(t)), "slab")
+        tg.append(t)
+    arr = (C.c_void_p * len(tg))(*[t.value for t in tg])
+    N.check(N.lib.b2dgpu_batch_render_multi(rt._h, arr, len(tg), batch._h), "render_multi")
+    multi = gpu.Image(W, H, 1)
+    for t in tg:
+        N.check(N.lib.b2dgpu_target_download(t, C.byref(multi._data)), "download")
+        N.check(N.lib.b2dgpu_target_destroy(t), "destroy")
+    whole, _ = replay(gpu, scene, count)
+    assert np.array_equal(whole.to_numpy(), multi.to_numpy())
+    batch.close(); rt.close(); rec.close()
