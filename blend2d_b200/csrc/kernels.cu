@@ -308,7 +308,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 72, kEntCap = 6, kPoolCap = 4096, kRing = 1024, kLanePx = kTileW / 32 };
+enum : int { kSubChunk = 72, kEntCap = 4, kPoolCap = 2048, kRing = 1024, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 enum : uint32_t { kDenseItems = 8u * kTileH };     // (edge, row) crossings per tile beyond which phase 1 gives up
 
@@ -319,7 +319,7 @@ struct PreCmd {
   uint32_t ovf_head[kTileH];        // 1 + pool index of the row's last chained entry, 0 = none
   uint32_t flags;
   uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
-  uint2 ent[kTileH][kEntCap];       // (cell index relative to the tile, value to add)
+  uint2 ent[kTileH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
   // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B) and the right end of
   // its clipped box.  (Staging the 176-byte FetchData as well was measured slower than reading it through L1.)
   int bx1;
@@ -329,34 +329,41 @@ struct PreCmd {
 static_assert(sizeof(PreCmd) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
 
 // Coverage sink of phase 1: the few cells a straddling edge touches in a row are appended to that row's entry list.
-// A row with more cells than its inline list holds (many crossings per scanline: bl_bench's random polygons, map-like
-// paths) chains the rest through a pool shared by the sub-chunk: pool entry = (cell | previous entry << 16, value).
+// One entry per edge crossing: cell `rel` gets v0 = (cover << 9) - area and cell rel + 1 gets `area`
+// (cell_merge, analyticrasterizer_p.h:1202-1210), packed as x = rel | area << 8 (|area| <= 2^17), y = v0.
+// A row with more crossings than its inline list holds (bl_bench's random polygons, map-like paths) chains the rest
+// through a pool shared by the sub-chunk; s_pool_link[i] = 1 + index of the previous chained entry of the same row.
 struct EntrySink {
   PreCmd* pre;
   uint2* pool;
+  uint16_t* pool_link;
   uint32_t* pool_next;
   int tx0;
   int row;
-  __device__ __forceinline__ void put(int x, uint32_t v) {
-    if (!v) return;
-    int rel = x - tx0;
-    if (rel < 0) atomicAdd(&pre->carry_st[row], v);
-    else if (rel < kTileW) {
-      uint32_t idx = atomicAdd(&pre->nent[row], 1u);
-      if (idx < uint32_t(kEntCap)) pre->ent[row][idx] = make_uint2(uint32_t(rel), v);
-      else {
-        const uint32_t pi = atomicAdd(pool_next, 1u);
-        if (pi < uint32_t(kPoolCap)) {
-          const uint32_t prev = atomicExch(&pre->ovf_head[row], pi + 1u);
-          pool[pi] = make_uint2(uint32_t(rel) | (prev << 16), v);
-        }
-        else atomicOr(&pre->flags, kPreOverflow);       // pool exhausted: the row re-rasterizes itself (slow_row_cells)
+  __device__ __forceinline__ void append(int rel, uint32_t v0, uint32_t area) {
+    const uint2 en = make_uint2(uint32_t(rel) | (area << 8), v0);
+    uint32_t idx = atomicAdd(&pre->nent[row], 1u);
+    if (idx < uint32_t(kEntCap)) pre->ent[row][idx] = en;
+    else {
+      const uint32_t pi = atomicAdd(pool_next, 1u);
+      if (pi < uint32_t(kPoolCap)) {
+        const uint32_t prev = atomicExch(&pre->ovf_head[row], pi + 1u);
+        pool[pi] = en;
+        pool_link[pi] = uint16_t(prev);
       }
+      else atomicOr(&pre->flags, kPreOverflow);         // pool exhausted: the row re-rasterizes itself (slow_row_cells)
     }
   }
   __device__ __forceinline__ void merge(int x, uint32_t cover, uint32_t area) {
-    put(x, (cover << 9) - area);
-    put(x + 1, area);
+    const uint32_t v0 = (cover << 9) - area;
+    const int rel = x - tx0;
+    if (rel >= kTileW || (v0 | area) == 0u) return;
+    if (rel >= 0) append(rel, v0, area);
+    else {
+      // cell x is left of the tile: it only feeds the row's backdrop; cell x + 1 may be the tile's first column
+      if (rel == -1) { if (v0) atomicAdd(&pre->carry_st[row], v0); if (area) append(0, area, 0u); }
+      else atomicAdd(&pre->carry_st[row], v0 + area);
+    }
   }
 };
 
@@ -397,6 +404,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSubChunk PreCmd records (dynamic: > 48 KB)
   PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
   uint2* const s_pool = reinterpret_cast<uint2*>(s_dynamic + sizeof(PreCmd) * kSubChunk);      // kPoolCap chained entries
+  uint16_t* const s_pool_link = reinterpret_cast<uint16_t*>(s_pool + kPoolCap);
   __shared__ uint32_t s_wcount[kTileH];
   __shared__ uint32_t s_next;
   __shared__ uint32_t s_pool_next;
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
 
         if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
-          EntrySink sink; sink.pre = pre; sink.pool = s_pool; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
+          EntrySink sink; sink.pre = pre; sink.pool = s_pool; sink.pool_link = s_pool_link; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
@@ -637,12 +645,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
               for (uint32_t j = 0; j < n_inline || chain; j++) {
                 uint2 en;
                 if (j < n_inline) en = pre.ent[row][j];
-                else { en = s_pool[chain - 1u]; chain = en.x >> 16; en.x &= 0xFFFFu; }
-                const int first = int(en.x) - lane * 4;             // first pixel of the lo group that the cell reaches
+                else { en = s_pool[chain - 1u]; chain = s_pool_link[chain - 1u]; }
+                const int first = int(en.x & 0xFFu) - lane * 4;     // first pixel of the lo group that the crossing reaches
+                const uint32_t area = uint32_t(int32_t(en.x) >> 8);
                 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                  cov[i] += (i >= first) ? en.y : 0u;
-                  cov[4 + i] += (i + kHalf >= first) ? en.y : 0u;
+                  cov[i] += ((i >= first) ? en.y : 0u) + ((i > first) ? area : 0u);
+                  cov[4 + i] += ((i + kHalf >= first) ? en.y : 0u) + ((i + kHalf > first) ? area : 0u);
                 }
               }
             }
@@ -1043,7 +1052,7 @@ int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
   if (!tiles) return 0;
   // Function attributes are per device: remember which devices of this process were configured.
   static bool configured[64] = {};
-  const int dyn = int(sizeof(PreCmd)) * kSubChunk + kPoolCap * int(sizeof(uint2));
+  const int dyn = int(sizeof(PreCmd)) * kSubChunk + kPoolCap * int(sizeof(uint2) + sizeof(uint16_t));
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
