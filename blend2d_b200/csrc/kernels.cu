@@ -308,7 +308,7 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 72, kEntCap = 4, kPoolCap = 2048, kRing = 1024, kLanePx = kTileW / 32 };
+enum : int { kSubChunk = 72, kEntCap = 4, kPoolCap = 4096, kRing = 1024, kLanePx = kTileW / 32 };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
 enum : uint32_t { kDenseItems = 8u * kTileH };     // (edge, row) crossings per tile beyond which phase 1 gives up
 
