@@ -309,7 +309,7 @@ struct SmemRowStore {
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
 enum : int { kSubChunk = 72, kEntCap = 4, kPoolCap = 4096, kRing = 1024, kLanePx = kTileW / 32 };
-enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u };
+enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u, kPreClipRight = 4u };   // ClipRight: the clipped box ends inside the tile
 enum : uint32_t { kDenseItems = 8u * kTileH };     // (edge, row) crossings per tile beyond which phase 1 gives up
 
 struct PreCmd {
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
         if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
-        if (lane == 0) { pre->flags = 0; pre->bx1 = P.cmd_bbox_px[ci].z; }
+        if (lane == 0) { const int bx1 = P.cmd_bbox_px[ci].z; pre->bx1 = bx1; pre->flags = bx1 < tx0 + kTileW ? kPreClipRight : 0u; }
         {
           // stage the command (one coalesced 64-byte load)
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.commands + ci);
@@ -592,7 +592,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       while (act) {
         const uint32_t k = kb + uint32_t(__ffs(act) - 1);
         act &= act - 1;
-        const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         const PreCmd& pre = s_pre[k];
         const b2dgpu_command& cmd = *reinterpret_cast<const b2dgpu_command*>(pre.cmd_words);
         const uint32_t type = cmd.type;
@@ -656,7 +655,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
               }
             }
             else {
-              slow_row_cells(edges, P.cmd_edges[ci], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
+              slow_row_cells(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
               {
                 uint4 c0 = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
                 uint4 c1 = *reinterpret_cast<uint4*>(&s_cells[row][kHalf + lane * 4]);
@@ -687,8 +686,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             }
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
-          const int bx1 = pre.bx1;
-          if (bx1 < tx0 + kTileW) {
+          if (flags & kPreClipRight) {
+            const int bx1 = pre.bx1;
             #pragma unroll
             for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + kHalf + i >= bx1) m_hi[i] = 0; }
           }
