@@ -18,6 +18,9 @@ def main():
     use_gpu = "--gpu" in sys.argv
     if use_gpu:
         sys.argv.remove("--gpu")
+    big = "--big" in sys.argv                       # canvases up to 2600 x 1500: many tiles, long edges
+    if big:
+        sys.argv.remove("--big")
     draw = gpu_draw if use_gpu else hostsim.draw
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 50
     seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
@@ -26,7 +29,7 @@ def main():
     for it in range(iters):
         seed = seed0 + it
         rng = np.random.default_rng(seed)
-        W, H = int(rng.integers(2, 700)), int(rng.integers(2, 400))
+        W, H = (int(rng.integers(300, 2600)), int(rng.integers(200, 1500))) if big else (int(rng.integers(2, 700)), int(rng.integers(2, 400)))
         fmt = int(rng.choice([1, 2, 3]))
         kind = it % 6
         if kind == 0: scene = S.mixed(int(rng.integers(20, 200)), W, H)
