@@ -28,7 +28,7 @@ enum : int { kA8Shift = 8, kA8Scale = 256, kA8Mask = 255 };
 // Tile geometry of the compositor (see DESIGN.md "Data layout in HBM").
 enum : int {
   kTileW = 128,            // pixels per tile row  (one warp, 4 px per lane; 256 = 8 px per lane in two halves)
-  kTileH = 24,             // rows per tile        (one warp per row; 24 warps = one 768-thread CTA per SM)
+  kTileH = 32,             // rows per tile        (one warp per row; 32 warps = one 1024-thread CTA per SM)
   kTileThreads = 32 * kTileH
 };
 

@@ -12,7 +12,7 @@ Two partitions, both taken from the reference's own threading model (SURVEY.md s
 """
 import ctypes as C
 
-TILE_ROWS = 24         # kTileH in csrc/dev_common.cuh: slabs are cut on tile boundaries so no tile is shared by two ranks
+TILE_ROWS = 32         # kTileH in csrc/dev_common.cuh: slabs are cut on tile boundaries so no tile is shared by two ranks
 
 
 def slab_table(height, world, align=TILE_ROWS):
