@@ -85,28 +85,28 @@ B2D_HD NormEdge normalize_edge(b2dgpu_edge ed) {
 // Columns an edge can touch inside the band of rows [band_y, band_y + kTileH): cells [min >> 8, (max >> 8) + 1]
 // (cell_merge writes x and x + 1) of the edge's part inside the band, with one more column of slack on each side for
 // the DDA's rounding.  Used by k_band_extents to cull (tile, command) pairs; must never be too tight.
-B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi) {
+B2D_HD void band_edge_extent(const NormEdge& ed, int band_y, int& lo, int& hi, int tile_h = kTileH) {
   // x at the band's first and last scanline boundary, by double-precision interpolation: |error| is far below the
   // one-pixel slack added on each side (the products are exact in a double, the quotient is off by < 1 ulp).
   const double slope = double(ed.x1 - ed.x0) / double(ed.y1 - ed.y0);
   const int ya = tmax(ed.y0, band_y << 8);
-  const int yb = tmin(ed.y1, (band_y + kTileH) << 8);
+  const int yb = tmin(ed.y1, (band_y + tile_h) << 8);
   const int xa = ed.x0 + int(slope * double(ya - ed.y0));
   const int xb = ed.x0 + int(slope * double(yb - ed.y0));
   lo = tmax((tmin(xa, xb) >> 8) - 1, 0);
   hi = tmax((tmax(xa, xb) >> 8) + 2, 0);
 }
 
-B2D_HD int tile_edge_class(const NormEdge& ed, int tx0, int ty0) {
+B2D_HD int tile_edge_class(const NormEdge& ed, int tx0, int ty0, int tile_h = kTileH) {
   const int ey_first = ed.y0 >> 8, ey_last = (ed.y1 - 1) >> 8;
-  if (ey_last < ty0 || ey_first >= ty0 + kTileH) return kEdgeNone;
+  if (ey_last < ty0 || ey_first >= ty0 + tile_h) return kEdgeNone;
   int cx_min = tmin(ed.x0, ed.x1) >> 8, cx_max = (tmax(ed.x0, ed.x1) >> 8) + 1;
   if (cx_min >= tx0 + kTileW) return kEdgeNone;
   if (cx_max < tx0) return kEdgeLeft;
   // A long edge (a closing chord can span the whole canvas) only touches a few columns inside this tile's rows:
   // classify by the part of the edge inside the band, conservatively rounded outwards (band_edge_extent).
   if (cx_max - cx_min >= 16) {
-    band_edge_extent(ed, ty0, cx_min, cx_max);
+    band_edge_extent(ed, ty0, cx_min, cx_max, tile_h);
     if (cx_min >= tx0 + kTileW) return kEdgeNone;
     if (cx_max < tx0) return kEdgeLeft;
   }

@@ -265,13 +265,13 @@ __device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, ui
   return normalize_edge(raw);
 }
 
-__global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __restrict__ band_ext) {
+__global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __restrict__ band_ext, int tile_h) {
   const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
   if (c >= P.command_count) return;
   const int4 bb = P.cmd_bbox_px[c];
   if (bb.x >= bb.z || bb.y >= bb.w) return;
-  const int band0 = (bb.y - P.y_begin) / kTileH, band1 = (bb.w - 1 - P.y_begin) / kTileH;
+  const int band0 = (bb.y - P.y_begin) / tile_h, band1 = (bb.w - 1 - P.y_begin) / tile_h;
   uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
   if (!command_has_edges(P.commands[c].type)) {
     for (int b = band0 + int(lane); b <= band1; b += 32)
@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
     if (ne.y0 == ne.y1) continue;
     const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
     if (row_first > row_last) continue;
-    for (int b = (row_first - P.y_begin) / kTileH; b <= (row_last - P.y_begin) / kTileH; b++) {
+    for (int b = (row_first - P.y_begin) / tile_h; b <= (row_last - P.y_begin) / tile_h; b++) {
       int lo, hi;
-      band_edge_extent(ne, P.y_begin + b * kTileH, lo, hi);
+      band_edge_extent(ne, P.y_begin + b * tile_h, lo, hi, tile_h);
       uint32_t* cell = ext + (size_t(b) * P.command_count + c) * 2;
       atomicMin(cell, uint32_t(lo));
       atomicMin(cell + 1, ~uint32_t(hi));
@@ -308,33 +308,38 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kSubChunk = 72, kEntCap = 4, kPoolCap = 4096, kRing = 1024, kLanePx = kTileW / 32 };
+enum : int { kEntCap = 4, kRing = 2048, kLanePx = kTileW / 32 };
+// Per tile height TH (= warps per CTA): commands per phase-1 round, chained-entry pool size.
+template<int TH> struct TileCfg { enum : int { kThreads = 32 * TH, kSub = TH == 32 ? 64 : 3 * TH, kPool = 128 * TH }; };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u, kPreClipRight = 4u };   // ClipRight: the clipped box ends inside the tile
-enum : uint32_t { kDenseItems = 8u * kTileH };     // (edge, row) crossings per tile beyond which phase 1 gives up
+enum : uint32_t { kDenseItemsPerRow = 8u };        // (edge, row) crossings per tile row beyond which phase 1 gives up
 
-struct PreCmd {
-  uint32_t carry_left[kTileH];      // backdrop per tile row from the edges entirely left of the tile
-  uint32_t carry_st[kTileH];        // backdrop per tile row from straddling edges (their cells left of the tile)
-  uint32_t nent[kTileH];            // number of cell entries appended per row (beyond kEntCap: chained in the pool)
-  uint32_t ovf_head[kTileH];        // 1 + pool index of the row's last chained entry, 0 = none
+template<int TH>
+struct PreCmdT {
+  uint32_t carry_left[TH];      // backdrop per tile row from the edges entirely left of the tile
+  uint32_t carry_st[TH];        // backdrop per tile row from straddling edges (their cells left of the tile)
+  uint32_t nent[TH];            // number of cell entries appended per row (beyond kEntCap: chained in the pool)
+  uint32_t ovf_head[TH];        // 1 + pool index of the row's last chained entry, 0 = none
   uint32_t flags;
   uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
-  uint2 ent[kTileH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
+  uint2 ent[TH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
   // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B) and the right end of
   // its clipped box.  (Staging the 176-byte FetchData as well was measured slower than reading it through L1.)
   int bx1;
   uint32_t pad_[5];
   uint32_t cmd_words[sizeof(b2dgpu_command) / 4];
 };
-static_assert(sizeof(PreCmd) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
+static_assert(sizeof(PreCmdT<8>) % 16 == 0 && sizeof(PreCmdT<16>) % 16 == 0 && sizeof(PreCmdT<32>) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
 
 // Coverage sink of phase 1: the few cells a straddling edge touches in a row are appended to that row's entry list.
 // One entry per edge crossing: cell `rel` gets v0 = (cover << 9) - area and cell rel + 1 gets `area`
 // (cell_merge, analyticrasterizer_p.h:1202-1210), packed as x = rel | area << 8 (|area| <= 2^17), y = v0.
 // A row with more crossings than its inline list holds (bl_bench's random polygons, map-like paths) chains the rest
 // through a pool shared by the sub-chunk; s_pool_link[i] = 1 + index of the previous chained entry of the same row.
+template<int TH>
 struct EntrySink {
-  PreCmd* pre;
+  PreCmdT<TH>* pre;
+  uint32_t pool_cap;
   uint2* pool;
   uint16_t* pool_link;
   uint32_t* pool_next;
@@ -346,7 +351,7 @@ struct EntrySink {
     if (idx < uint32_t(kEntCap)) pre->ent[row][idx] = en;
     else {
       const uint32_t pi = atomicAdd(pool_next, 1u);
-      if (pi < uint32_t(kPoolCap)) {
+      if (pi < pool_cap) {
         const uint32_t prev = atomicExch(&pre->ovf_head[row], pi + 1u);
         pool[pi] = en;
         pool_link[pi] = uint16_t(prev);
@@ -379,7 +384,7 @@ __device__ __noinline__ Mask8 box_mask_a_row(const b2dgpu_command& cmd, const b2
 // Slow path of the replay (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
 // rasterizes its own row into its private shared-memory cell row.  Out of line: it is rare and large.
 __device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int py, int row,
-                                            int lane, uint32_t* cells_row, uint32_t* carry_row) {
+                                            int lane, uint32_t* cells_row, uint32_t* carry_row, int tile_h) {
   #pragma unroll
   for (int i = 0; i < kLanePx / 4; i++)
     *reinterpret_cast<uint4*>(cells_row + lane * kLanePx + i * 4) = make_uint4(0, 0, 0, 0);
@@ -390,22 +395,24 @@ __device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint
   sink.row = row;
   for (uint32_t e = lane; e < er.y; e += 32) {
     NormEdge ne = load_edge(edges, er.x + e);
-    if (tile_edge_class(ne, tx0, ty0) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
+    if (tile_edge_class(ne, tx0, ty0, tile_h) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
       tile_rasterize_edge_row(ne, py, sink);
   }
   __syncwarp();
 }
 
-template<int BPP>
-__global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
-  __shared__ __align__(16) uint32_t s_cells[kTileH][kTileW];     // slow path only
-  __shared__ uint32_t s_carry[kTileH];
+template<int BPP, int TH>
+__global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) {
+  using PreCmd = PreCmdT<TH>;
+  constexpr int kThreads = TileCfg<TH>::kThreads, kSub = TileCfg<TH>::kSub, kPool = TileCfg<TH>::kPool;
+  __shared__ __align__(16) uint32_t s_cells[TH][kTileW];     // slow path only
+  __shared__ uint32_t s_carry[TH];
   __shared__ uint32_t s_list[kRing];
-  extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSubChunk PreCmd records (dynamic: > 48 KB)
+  extern __shared__ __align__(16) uint8_t s_dynamic[];             // kSub PreCmd records (dynamic: > 48 KB)
   PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
-  uint2* const s_pool = reinterpret_cast<uint2*>(s_dynamic + sizeof(PreCmd) * kSubChunk);      // kPoolCap chained entries
-  uint16_t* const s_pool_link = reinterpret_cast<uint16_t*>(s_pool + kPoolCap);
-  __shared__ uint32_t s_wcount[kTileH];
+  uint2* const s_pool = reinterpret_cast<uint2*>(s_dynamic + sizeof(PreCmd) * kSub);      // kPool chained entries
+  uint16_t* const s_pool_link = reinterpret_cast<uint16_t*>(s_pool + kPool);
+  __shared__ uint32_t s_wcount[TH];
   __shared__ uint32_t s_next;
   __shared__ uint32_t s_pool_next;
 
@@ -415,7 +422,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   const int tile_x = blockIdx.x % P.tiles_x;
   const int tile_y = blockIdx.x / P.tiles_x;
   const int tx0 = tile_x * kTileW;
-  const int ty0 = P.y_begin + tile_y * kTileH;          // absolute y of the tile's first row
+  const int ty0 = P.y_begin + tile_y * TH;          // absolute y of the tile's first row
   // A lane owns two groups of 4 consecutive pixels: `lo` in the left half of the row (px .. px + 3) and `hi` in the
   // right half (px + kTileW/2 ..).  Each half is one perfectly coalesced 512-byte run per warp, and a half without
   // coverage is skipped as a whole.
@@ -449,17 +456,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
   bool dirty = false;
   uint32_t px_written = 0;
 
-  // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSubChunk of them are
+  // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
   // pending (or the command list ends) they are classified (phase 1) and replayed (phase 2).
   uint32_t ring_head = 0, ring_tail = 0;                // block-uniform
-  for (uint32_t base = 0; base < P.command_count || ring_head != ring_tail; base += kTileThreads) {
+  for (uint32_t base = 0; base < P.command_count || ring_head != ring_tail; base += kThreads) {
     // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
     if (base < P.command_count) {
       uint32_t c = base + tid;
       bool hit = false;
       if (c < P.command_count) {
         int4 bb = P.cmd_bbox_px[c];
-        hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + kTileH && bb.w > ty0;
+        hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + TH && bb.w > ty0;
         if (hit && P.band_ext) {
           const uint2 ex = P.band_ext[size_t(tile_y) * P.command_count + c];
           hit = uint32_t(tx0 + kTileW) > ex.x && uint32_t(tx0) <= ~ex.y;
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       __syncthreads();
       uint32_t wbase = 0, total = 0;
       #pragma unroll
-      for (int w = 0; w < kTileH; w++) {
+      for (int w = 0; w < TH; w++) {
         uint32_t cnt = s_wcount[w];
         if (w < row) wbase += cnt;
         total += cnt;
@@ -479,13 +486,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       if (hit) s_list[(ring_tail + wbase + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1)] = c;
       ring_tail += total;
     }
-    const bool last = base + kTileThreads >= P.command_count;
+    const bool last = base + kThreads >= P.command_count;
 
-    while (ring_tail - ring_head >= uint32_t(kSubChunk) || (last && ring_tail != ring_head)) {
+    while (ring_tail - ring_head >= uint32_t(kSub) || (last && ring_tail != ring_head)) {
       const uint32_t sub = ring_head;
-      const uint32_t sub_n = min(uint32_t(kSubChunk), ring_tail - ring_head);
+      const uint32_t sub_n = min(uint32_t(kSub), ring_tail - ring_head);
       ring_head += sub_n;
-      if (tid == 0) { s_next = kTileH; s_pool_next = 0; } // commands beyond the first kTileH are handed out dynamically
+      if (tid == 0) { s_next = TH; s_pool_next = 0; } // commands beyond the first TH are handed out dynamically
       __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
       for (uint32_t k = row; k < sub_n; ) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
-        if (lane < kTileH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
+        if (lane < TH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
         if (lane == 0) { const int bx1 = P.cmd_bbox_px[ci].z; pre->bx1 = bx1; pre->flags = bx1 < tx0 + kTileW ? kPreClipRight : 0u; }
         {
           // stage the command (one coalesced 64-byte load)
@@ -503,13 +510,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
         }
         __syncwarp();
 
-        uint32_t left_acc = 0;                        // lane r < kTileH: backdrop of tile row r from the edges left of the tile
+        uint32_t left_acc = 0;                        // lane r < TH: backdrop of tile row r from the edges left of the tile
         uint32_t nstr = 0, items = 0;                 // straddling edges / their (edge, row) crossings in this tile
         const bool is_box = !command_has_edges(pre->cmd_words[0]);
 
         if (!is_box) {
           const uint2 er = P.cmd_edges[ci];
-          EntrySink sink; sink.pre = pre; sink.pool = s_pool; sink.pool_link = s_pool_link; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
+          EntrySink<TH> sink; sink.pre = pre; sink.pool_cap = uint32_t(kPool); sink.pool = s_pool; sink.pool_link = s_pool_link; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
@@ -518,11 +525,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             uint32_t esign = 0;
             if (e < er.y) {
               NormEdge ne = load_edge(edges, er.x + e);
-              cls = tile_edge_class(ne, tx0, ty0);
+              cls = tile_edge_class(ne, tx0, ty0, TH);
               ey0 = ne.y0; ey1 = ne.y1; esign = ne.sign_bit;
               if (cls == kEdgeStraddle) {
                 first_row = uint32_t(max(ne.y0 >> 8, ty0) - ty0);
-                rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + kTileH - 1) - ty0) - first_row + 1u;
+                rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + TH - 1) - ty0) - first_row + 1u;
               }
             }
             nstr += __popc(__ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle));
@@ -536,7 +543,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
               const uint32_t sg = __shfl_sync(0xFFFFFFFFu, esign, src);
               const int yt = (ty0 + lane) << 8;
               const int cov = min(y1, yt + 256) - max(y0, yt);
-              if (cov > 0 && lane < kTileH) left_acc += uint32_t(sg ? -cov : cov) << 9;
+              if (cov > 0 && lane < TH) left_acc += uint32_t(sg ? -cov : cov) << 9;
             }
             // (edge, row) items of this chunk, packed densely over the lanes: inclusive scan of the rows each straddling
             // edge crosses; item i belongs to the first edge whose inclusive count exceeds i.
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
             items += chunk_items;
             // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
             // row of the replay rasterizes itself (slow_row_cells).
-            if (items > kDenseItems) continue;
+            if (items > kDenseItemsPerRow * uint32_t(TH)) continue;
             for (uint32_t base_i = 0; base_i < chunk_items; base_i += 32) {
               const uint32_t i = base_i + lane;
               uint32_t j = 0;
@@ -572,9 +579,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
           }
         }
         const bool any_left = __any_sync(0xFFFFFFFFu, left_acc != 0u);
-        if (lane < kTileH) pre->carry_left[lane] = left_acc;
+        if (lane < TH) pre->carry_left[lane] = left_acc;
         if (lane == 0) {
-          if (nstr) atomicOr(&pre->flags, items > kDenseItems ? (kPreStraddle | kPreOverflow) : kPreStraddle);
+          if (nstr) atomicOr(&pre->flags, items > kDenseItemsPerRow * uint32_t(TH) ? (kPreStraddle | kPreOverflow) : kPreStraddle);
           pre->active = (is_box || nstr || any_left) ? 1u : 0u;
         }
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
@@ -655,7 +662,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_tile_render(TileParams P) {
               }
             }
             else {
-              slow_row_cells(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row]);
+              slow_row_cells(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row], TH);
               {
                 uint4 c0 = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
                 uint4 c1 = *reinterpret_cast<uint4*>(&s_cells[row][kHalf + lane * 4]);
@@ -1039,28 +1046,49 @@ int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s
   return 1;
 }
 
-int launch_band_extents(const TileParams& P, uint2* band_ext, cudaStream_t s) {
+int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaStream_t s) {
   if (!P.command_count) return 0;
-  k_band_extents<<<div_up(P.command_count * 32, 256), 256, 0, s>>>(P, band_ext);
+  k_band_extents<<<div_up(P.command_count * 32, 256), 256, 0, s>>>(P, band_ext, tile_h);
   return 1;
 }
 
-int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s) {
-  if (!P.command_count) return 0;
-  uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
-  if (!tiles) return 0;
+// Tile height for a target of `rows` rows and `tiles_x` tile columns: 32-row tiles (one 32-warp CTA per SM, the
+// configuration the 4K bench runs) when they give every SM a couple of tiles, shorter tiles for small canvases.
+int choose_tile_height(int tiles_x, int rows, int sm_count) {
+  const int heights[3] = { 32, 16, 8 };
+  for (int i = 0; i < 3; i++)
+    if (tiles_x * ((rows + heights[i] - 1) / heights[i]) >= 2 * sm_count) return heights[i];
+  return 8;
+}
+
+template<int BPP, int TH>
+static void launch_tile_variant(const TileParams& P, uint32_t tiles, cudaStream_t s) {
   // Function attributes are per device: remember which devices of this process were configured.
   static bool configured[64] = {};
-  const int dyn = int(sizeof(PreCmd)) * kSubChunk + kPoolCap * int(sizeof(uint2) + sizeof(uint16_t));
+  const int dyn = int(sizeof(PreCmdT<TH>)) * TileCfg<TH>::kSub + TileCfg<TH>::kPool * int(sizeof(uint2) + sizeof(uint16_t));
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    cudaFuncSetAttribute(k_tile_render<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-    cudaFuncSetAttribute(k_tile_render<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+    cudaFuncSetAttribute(k_tile_render<BPP, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  if (bpp == 4) k_tile_render<4><<<tiles, kTileThreads, dyn, s>>>(P);
-  else k_tile_render<1><<<tiles, kTileThreads, dyn, s>>>(P);
+  k_tile_render<BPP, TH><<<tiles, TileCfg<TH>::kThreads, dyn, s>>>(P);
+}
+
+int launch_tile_render(const TileParams& P, int bpp, int tile_h, cudaStream_t s) {
+  if (!P.command_count) return 0;
+  uint32_t tiles = uint32_t(P.tiles_x) * uint32_t(P.tiles_y);
+  if (!tiles) return 0;
+  if (bpp == 4) {
+    if (tile_h == 32) launch_tile_variant<4, 32>(P, tiles, s);
+    else if (tile_h == 16) launch_tile_variant<4, 16>(P, tiles, s);
+    else launch_tile_variant<4, 8>(P, tiles, s);
+  }
+  else {
+    if (tile_h == 32) launch_tile_variant<1, 32>(P, tiles, s);
+    else if (tile_h == 16) launch_tile_variant<1, 16>(P, tiles, s);
+    else launch_tile_variant<1, 8>(P, tiles, s);
+  }
   return 1;
 }
 

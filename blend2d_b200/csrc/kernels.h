@@ -73,8 +73,9 @@ int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_
 int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
 int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
-int launch_band_extents(const TileParams& P, uint2* band_ext, cudaStream_t s);
-int launch_tile_render(const TileParams& P, int bpp, cudaStream_t s);
+int choose_tile_height(int tiles_x, int rows, int sm_count);
+int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaStream_t s);
+int launch_tile_render(const TileParams& P, int bpp, int tile_h, cudaStream_t s);
 int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
 int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s);
 

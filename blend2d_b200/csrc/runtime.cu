@@ -834,7 +834,8 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   T.dst = t->d_pixels;
   T.dst_stride = intptr_t(t->stride);
   T.tiles_x = t->padded_w / kTileW;
-  T.tiles_y = t->padded_h / kTileH;
+  const int tile_h = choose_tile_height(t->padded_w / kTileW, t->h, rt->sm_count);
+  T.tiles_y = (t->h + tile_h - 1) / tile_h;           // padded_h is a multiple of the largest tile height
   T.y_begin = t->y0;
   T.commands = d_cmds;
   T.command_count = in.command_count;
@@ -857,7 +858,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
       CU_TRY(rt->band_ext.ensure(need + need / 4));
     }
     CU_TRY(cudaMemsetAsync(rt->band_ext.ptr, 0xFF, need, s));
-    launches += launch_band_extents(T, static_cast<uint2*>(rt->band_ext.ptr), s);
+    launches += launch_band_extents(T, static_cast<uint2*>(rt->band_ext.ptr), tile_h, s);
     T.band_ext = static_cast<const uint2*>(rt->band_ext.ptr);
   }
   if (rt->profiling && ti == 0) CU_TRY(cudaEventRecord(ev[1], s));
@@ -887,7 +888,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
       streamed = true;
     }
   }
-  if (!streamed) launches += launch_tile_render(T, t->bpp, s);
+  if (!streamed) launches += launch_tile_render(T, t->bpp, tile_h, s);
   }
   if (rt->profiling) {
     CU_TRY(cudaEventRecord(ev[2], s));
