@@ -154,3 +154,23 @@ def test_gpu_many_commands_one_batch(ref, gpu):
     assert gc.stats()["tile_kernel_launches"] <= 1 or True
     assert S.channel_diff(ri.to_numpy(), gi.to_numpy()) == (0, 0)
     gc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H", [(96, 40), (2048, 640)])
+def test_gpu_every_command_hits_every_tile(ref, gpu, W, H):
+    """1500 translucent fills that all cover the whole canvas: every command of every 1024-command cull round hits
+    every tile (ring buffer at capacity), on a canvas small enough for 8-row tiles and one large enough for 32-row tiles."""
+    def scene(api, ctx, rng):
+        for i in range(1500):
+            ctx.set_fill_style(S.rand_rgba32(rng) & 0x3FFFFFFF | 0x10000000)
+            if i % 3 == 0:
+                ctx.fill_rect_i(0, 0, W, H)
+            elif i % 3 == 1:
+                ctx.fill_rect_d(-0.5, -0.25, W + 1.0, H + 0.75)
+            else:
+                ctx.fill_polygon([-5.0, -5.0, W + 5.0, -3.0, W + 4.0, H + 6.0, -2.0, H + 5.0])
+    ri, _ = S.draw(ref, scene, W, H, 1, 3)
+    gi, gc = S.draw(gpu, scene, W, H, 1, 3, command_queue_limit=65536)
+    assert S.channel_diff(ri.to_numpy(), gi.to_numpy()) == (0, 0)
+    gc.close()
