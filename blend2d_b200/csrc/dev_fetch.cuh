@@ -373,7 +373,7 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     for (int i = 0; i < 4; i++) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
     return;
   }
-  #pragma unroll 1
+  #pragma unroll
   for (int i = 0; i < 4; i++)
     if (m[i]) s[i] = fetch_pixel_cold(env, x + i, y);
 }

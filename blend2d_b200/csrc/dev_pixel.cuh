@@ -181,7 +181,7 @@ B2D_HD void composite4(uint32_t comp_op, uint32_t* d, const uint32_t* s, const u
     }
   }
   else {
-    #pragma unroll 1
+    #pragma unroll
     for (int i = 0; i < 4; i++) if (m[i]) d[i] = composite_cold(comp_op, d[i], s[i], m[i]);
   }
 }
