@@ -18,16 +18,23 @@
 
 namespace b2d {
 
-// x86 float -> int conversions.
+// x86 float -> int conversions (cvttss2si / cvtss2si return INT_MIN for NaN and for anything outside the int range).
+// Device variants: cvt.rzi / cvt.rni saturate, so values below -2^31 already give INT_MIN; NaN gives 0 instead of
+// INT_MIN, which is indistinguishable in the only users, the gradient table indices (pad clamps both to 0, repeat /
+// reflect / conic mask both to 0 because the masks are below 2^31); only v >= 2^31 needs the x86 result forced.
 B2D_HD int x86_trunc_f32(float v) {
+#if defined(__CUDA_ARCH__)
+  return v >= 2147483648.0f ? int(0x80000000u) : __float2int_rz(v);
+#else
   if (!(v >= -2147483648.0f && v < 2147483648.0f)) return int(0x80000000u);
   return int(v);
+#endif
 }
 B2D_HD int x86_nearby_f32(float v) {
-  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return int(0x80000000u);
 #if defined(__CUDA_ARCH__)
-  return __float2int_rn(v);
+  return v >= 2147483648.0f ? int(0x80000000u) : __float2int_rn(v);
 #else
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return int(0x80000000u);
   return int(lrintf(v));
 #endif
 }
