@@ -276,6 +276,24 @@ B2D_HD void fetch_row_init(const FetchEnv& env, uint32_t y, RowCtx& rc) {
     rc.conic = conic_row(env.fd->gradient.conic, y);
 }
 
+B2D_HD uint32_t fetch_pattern_pixel(const b2dgpu_fetch_pattern& p, uint32_t ft, uint32_t src_format, uint32_t x, uint32_t y) {
+  switch (ft) {
+    case B2DGPU_FETCH_PATTERN_ALIGNED_BLIT:   return fetch_pattern_blit(p, src_format, x, y);
+    case B2DGPU_FETCH_PATTERN_ALIGNED_PAD:    return fetch_pattern_aligned(p, src_format, 0, x, y);
+    case B2DGPU_FETCH_PATTERN_ALIGNED_REPEAT: return fetch_pattern_aligned(p, src_format, 1, x, y);
+    case B2DGPU_FETCH_PATTERN_ALIGNED_ROR:    return fetch_pattern_aligned(p, src_format, 2, x, y);
+    case B2DGPU_FETCH_PATTERN_FX_PAD:
+    case B2DGPU_FETCH_PATTERN_FY_PAD:
+    case B2DGPU_FETCH_PATTERN_FXFY_PAD:       return fetch_pattern_fxfy(p, src_format, 0, x, y);
+    case B2DGPU_FETCH_PATTERN_FX_ROR:
+    case B2DGPU_FETCH_PATTERN_FY_ROR:
+    case B2DGPU_FETCH_PATTERN_FXFY_ROR:       return fetch_pattern_fxfy(p, src_format, 2, x, y);
+    case B2DGPU_FETCH_PATTERN_AFFINE_NN_ANY:
+    case B2DGPU_FETCH_PATTERN_AFFINE_NN_OPT:  return fetch_pattern_affine_nn(p, src_format, x, y);
+    default:                                  return fetch_pattern_affine_bi(p, src_format, x, y);
+  }
+}
+
 B2D_HD uint32_t fetch_pixel(const FetchEnv& env, const RowCtx& rc, uint32_t x, uint32_t y) {
   const uint32_t ft = env.fetch_type;
   if (ft == B2DGPU_FETCH_SOLID) return env.solid;
@@ -306,22 +324,7 @@ B2D_HD uint32_t fetch_pixel(const FetchEnv& env, const RowCtx& rc, uint32_t x, u
     return dither ? lut_fetch_dither(env, g, idx, x, y) : lut_fetch_nn(g, idx);
   }
 
-  const b2dgpu_fetch_pattern& p = env.fd->pattern;
-  switch (ft) {
-    case B2DGPU_FETCH_PATTERN_ALIGNED_BLIT:   return fetch_pattern_blit(p, env.src_format, x, y);
-    case B2DGPU_FETCH_PATTERN_ALIGNED_PAD:    return fetch_pattern_aligned(p, env.src_format, 0, x, y);
-    case B2DGPU_FETCH_PATTERN_ALIGNED_REPEAT: return fetch_pattern_aligned(p, env.src_format, 1, x, y);
-    case B2DGPU_FETCH_PATTERN_ALIGNED_ROR:    return fetch_pattern_aligned(p, env.src_format, 2, x, y);
-    case B2DGPU_FETCH_PATTERN_FX_PAD:
-    case B2DGPU_FETCH_PATTERN_FY_PAD:
-    case B2DGPU_FETCH_PATTERN_FXFY_PAD:       return fetch_pattern_fxfy(p, env.src_format, 0, x, y);
-    case B2DGPU_FETCH_PATTERN_FX_ROR:
-    case B2DGPU_FETCH_PATTERN_FY_ROR:
-    case B2DGPU_FETCH_PATTERN_FXFY_ROR:       return fetch_pattern_fxfy(p, env.src_format, 2, x, y);
-    case B2DGPU_FETCH_PATTERN_AFFINE_NN_ANY:
-    case B2DGPU_FETCH_PATTERN_AFFINE_NN_OPT:  return fetch_pattern_affine_nn(p, env.src_format, x, y);
-    default:                                  return fetch_pattern_affine_bi(p, env.src_format, x, y);
-  }
+  return fetch_pattern_pixel(env.fd->pattern, ft, env.src_format, x, y);
 }
 
 // Everything that is not a solid colour or a nearest-neighbour gradient (dithered gradients, all patterns): kept out of
@@ -378,6 +381,15 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     const ConicRow row = conic_row(g.conic, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
+    return;
+  }
+  if (ft <= B2DGPU_FETCH_PATTERN_AFFINE_BI_OPT) {
+    // Patterns (the aligned blit assumes the pixel is inside the source, so the masks guard the fetch).
+    const b2dgpu_fetch_pattern& p = env.fd->pattern;
+    const uint32_t sf = env.src_format;
+    #pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (m[i]) s[i] = fetch_pattern_pixel(p, ft, sf, x + i, y);
     return;
   }
   #pragma unroll
