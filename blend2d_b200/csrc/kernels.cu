@@ -654,10 +654,17 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
                 else { en = s_pool[chain - 1u]; chain = s_pool_link[chain - 1u]; }
                 const int first = int(en.x & 0xFFu) - lane * 4;     // first pixel of the lo group that the crossing reaches
                 const uint32_t area = uint32_t(int32_t(en.x) >> 8);
-                #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                  cov[i] += ((i >= first) ? en.y : 0u) + ((i > first) ? area : 0u);
-                  cov[4 + i] += ((i + kHalf >= first) ? en.y : 0u) + ((i + kHalf > first) ? area : 0u);
+                // pixel i gets v0 from cell `first` on and `area` from cell `first + 1` on: i > first <=> i - 1 >= first,
+                // so five comparisons serve the eight selects of the group
+                const bool pm = first < 0, p0 = first <= 0, p1 = first <= 1, p2 = first <= 2, p3 = first <= 3;
+                cov[0] += (p0 ? en.y : 0u) + (pm ? area : 0u);
+                cov[1] += (p1 ? en.y : 0u) + (p0 ? area : 0u);
+                cov[2] += (p2 ? en.y : 0u) + (p1 ? area : 0u);
+                cov[3] += (p3 ? en.y : 0u) + (p2 ? area : 0u);
+                if (kTwoHalves) {
+                  #pragma unroll
+                  for (int i = 0; i < 4; i++)
+                    cov[4 + i] += ((i + kHalf >= first) ? en.y : 0u) + ((i + kHalf > first) ? area : 0u);
                 }
               }
             }
