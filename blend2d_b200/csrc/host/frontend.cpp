@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include <new>
+#include <memory>
 #include <vector>
 #include <unordered_set>
 
@@ -377,8 +378,8 @@ struct b2d_gradient {
   // BLGradientInfo (core/gradient.cpp:202-281)
   bool empty, solid;
   uint32_t format, lut_size;
-  std::vector<uint32_t> lut32;
-  std::vector<uint64_t> lut64;
+  std::unique_ptr<uint32_t[]> lut32;            // tables are written in full by make_lut*: no zero fill
+  std::unique_ptr<uint64_t[]> lut64;
 };
 
 struct b2d_pattern {
@@ -436,6 +437,7 @@ extern "C" b2dgpu_result b2d_gradient_create(uint32_t type, const double* values
   memcpy(g->values, values, nv * sizeof(double));
   if (matrix) memcpy(&g->transform, matrix, sizeof(Matrix)); else g->transform = kIdentity;
   g->transform_type = matrix ? matrix_type(g->transform) : kTTIdentity;
+  g->stops.reserve(stop_count);
   for (uint32_t i = 0; i < stop_count; i++) {
     if (i && stops[i].offset < stops[i - 1].offset) { delete g; return B2DGPU_ERROR_INVALID_VALUE; }
     g->stops.push_back(Stop{ bclamp(stops[i].offset, 0.0, 1.0), stops[i].rgba64 });
@@ -1271,12 +1273,12 @@ extern "C" b2dgpu_result b2d_context_set_fill_style_gradient(b2d_context* c, con
 
   b2dgpu_fetch_data fd; memset(&fd, 0, sizeof(fd));
   if (dither) {
-    if (g->lut64.empty()) { g->lut64.resize(lut_size); make_lut64(g->lut64.data(), lut_size, g->stops.data(), g->stops.size()); }
-    fd.gradient.lut.data = g->lut64.data();
+    if (!g->lut64) { g->lut64.reset(new uint64_t[lut_size]); make_lut64(g->lut64.get(), lut_size, g->stops.data(), g->stops.size()); }
+    fd.gradient.lut.data = g->lut64.get();
   }
   else {
-    if (g->lut32.empty()) { g->lut32.resize(lut_size); make_lut32(g->lut32.data(), lut_size, g->stops.data(), g->stops.size()); }
-    fd.gradient.lut.data = g->lut32.data();
+    if (!g->lut32) { g->lut32.reset(new uint32_t[lut_size]); make_lut32(g->lut32.get(), lut_size, g->stops.data(), g->stops.size()); }
+    fd.gradient.lut.data = g->lut32.get();
   }
   fd.gradient.lut.size = lut_size;
 
