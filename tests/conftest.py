@@ -21,6 +21,11 @@ def pytest_configure(config):
 def ref():
     """The unmodified reference, built from /root/reference into oracle/_ref (travels to the GPU box)."""
     from oracle import ref_blend2d as R
+    if not R.available() and os.path.isdir("/root/reference/blend2d"):
+        # first use on a fresh checkout: build the unmodified reference with the committed recipe (about a minute)
+        import subprocess
+        subprocess.call(["make", "-s", "-j8", "-f", os.path.join(ROOT, "oracle", "Makefile.ref")], cwd=os.path.join(ROOT, "oracle"),
+                        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     if not R.available():
         pytest.skip("oracle/_ref/libblend2d_ref.so not built (needs /root/reference): run make -f oracle/Makefile.ref")
     return R
