@@ -189,7 +189,9 @@ static b2dgpu_result runtime_lookup(b2dgpu_runtime* rt, uint32_t signature, b2dg
   if (!signature_supported(signature))
     return fail(is_test ? B2DGPU_ERROR_NO_ENTRY : B2DGPU_ERROR_NOT_IMPLEMENTED, "signature not implemented by the GPU runtime");
   out->fill_func = fill_func_token;
-  out->fetch_func = nullptr;
+  // Never called either: carries the signature, because RenderCommand::_dispatch_data overwrites the command's
+  // _signature (rendercommand_p.h:169-174) and the batch consumer needs it back (B2DGPU_DISPATCH_SIGNATURE).
+  out->fetch_func = reinterpret_cast<b2dgpu_fill_func>(uintptr_t(B2DGPU_DISPATCH_TAG) | uintptr_t(signature));
   return B2DGPU_SUCCESS;
 }
 

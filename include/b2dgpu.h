@@ -105,7 +105,7 @@ enum {
 
 /* ------------------------------------------------------------------------------------------------------------------
  * FetchData - bit-for-bit the reference's `bl::Pipeline::FetchData` (pipedefs_p.h:838-1060; 176 bytes, align 16;
- * offsets probed from the reference headers with gcc 13 / x86-64, see tests/test_abi_layout.py).  The reference's
+ * offsets checked against the reference headers with gcc 13 / x86-64 by tests/test_abi.py).  The reference's
  * host-side initialisers (pipeline/pipedefs.cpp:53-699) fill it; the GPU fetchers consume exactly these fields.
  * Pointers inside (`pixel_data`, `lut_data`) are HOST pointers at the boundary; b2dgpu_submit() uploads what they
  * reference and patches device addresses into its private copy.
@@ -216,8 +216,12 @@ typedef void (*b2dgpu_fill_func)(void* ctx_data, const void* fill_data, const vo
 
 typedef struct b2dgpu_dispatch_data {         /* DispatchData, pipedefs_p.h:370-388 */
   b2dgpu_fill_func fill_func;                 /* non-null token; calling it is a programming error (aborts)    */
-  b2dgpu_fill_func fetch_func;                /* always null: one-stage pipelines                              */
-} b2dgpu_dispatch_data;
+  b2dgpu_fill_func fetch_func;                /* not callable either: B2DGPU_DISPATCH_TAG | signature.  The     */
+} b2dgpu_dispatch_data;                       /* frontend stores DispatchData over the command's signature      */
+                                              /* (rendercommand_p.h:169-174); the batch consumer reads it back  */
+#define B2DGPU_DISPATCH_TAG 0xB2D6000000000000ull   /* non-canonical x86-64 address: a call faults               */
+#define B2DGPU_DISPATCH_SIGNATURE(dd) ((uint32_t)(uintptr_t)(dd)->fetch_func)
+#define B2DGPU_DISPATCH_IS_GPU(dd) ((((uintptr_t)(dd)->fetch_func) >> 48) == (B2DGPU_DISPATCH_TAG >> 48))
 
 typedef struct b2dgpu_create_info {
   uint32_t struct_size;                       /* sizeof(b2dgpu_create_info)                                     */

@@ -1,0 +1,724 @@
+// b2dgpu_shim_impl.h - second half of the Blend2D <-> libb2dgpu binding (see b2dgpu_shim_fwd.h).
+//
+// Included by the overlay INSIDE `namespace bl::RasterEngine` of the build-tree copy of rastercontext.cpp, after the
+// asynchronous enqueue helpers (rastercontext.cpp:2410-2520) and before the fill frontends that call into it.
+//
+// What it does, all of it on the user thread (a GPU context has no worker threads):
+//   * create_runtime()   BL_CONTEXT_CREATE_FLAG 0x10000000 -> a PipeRuntime (piperuntime_p.h:39-62) whose get()/test()
+//                        forward to b2dgpu_runtime_get/test; DispatchData carries tokens, never host code.
+//   * record_path/poly   small paths and polygons, which the reference flattens on the user thread even when it is
+//                        asynchronous (rastercontext.cpp:2784-2866), are recorded as path segments instead: the GPU
+//                        edge builder (K1) flattens and clips them.
+//   * consume_batch()    replaces WorkerProc::process_work_data() (workerproc.cpp:322-352): walks the command queues
+//                        and the job queue of a RenderBatch, turns them into one b2dgpu_batch_view and submits it.
+//                        Jobs: fill-geometry -> path segments; stroke-geometry -> the reference's own stroker
+//                        (core/pathstroke.cpp) runs on the host and its a/b/c output paths become segments
+//                        (b reversed, as EdgeSourceReversePathFromStrokeSink does); text -> glyph outlines decoded
+//                        by the reference (bl_font_get_glyph_run_outlines) become segments.
+//   * sync_to_host()     flush(BL_CONTEXT_FLUSH_SYNC) / end(): device canvas -> BLImage pixels.
+//
+// Environment (debug aids): B2DGPU_SHIM_CPU_EDGES=1 builds every edge with the reference's EdgeBuilder on the host
+// and ships edges instead of segments; B2DGPU_SHIM_PIN=0 disables page-locking of the target image.
+#ifndef B2DGPU_SHIM_IMPL_H_INCLUDED
+#define B2DGPU_SHIM_IMPL_H_INCLUDED
+
+namespace GpuShim {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-context state, owned by the PipeRuntime object (destroyed by detach(): the runtime is flagged kIsolated).
+// ---------------------------------------------------------------------------------------------------------------
+struct DirectGeometry { uint32_t seg_begin, seg_count, state_index; };
+
+struct State {
+  b2dgpu_runtime* rt = nullptr;
+  b2dgpu_target* target = nullptr;
+  void* registered_pixels = nullptr;
+  bool device_dirty = false;        // the device canvas is newer than the host image
+  bool cpu_edges = false;
+  bool pin_images = true;
+
+  // Geometry: filled at call time by record_*() and at flush time by the job pass.
+  std::vector<double> vtx;
+  std::vector<b2dgpu_segment> segs;
+  std::vector<b2dgpu_geometry_state> states;
+  std::vector<DirectGeometry> direct;
+
+  // Flush-time arrays.
+  std::vector<b2dgpu_command> cmds;
+  std::vector<b2dgpu_fetch_data> fetch;
+  std::vector<b2dgpu_edge> edges;
+  std::vector<const void*> fetch_keys;
+
+  BLPath tmp_path[5];               // stroker scratch: a, b, c, input copy, glyph outlines
+
+  void clear_geometry() noexcept { vtx.clear(); segs.clear(); states.clear(); direct.clear(); }
+};
+
+struct Runtime : public Pipeline::PipeRuntime {
+  State* state;
+};
+
+static BL_INLINE State* state_of(const BLRasterContextImpl* ctx_impl) noexcept {
+  return static_cast<Runtime*>(ctx_impl->pipe_provider.runtime())->state;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Seam B: PipeRuntime
+// ---------------------------------------------------------------------------------------------------------------
+static BLResult BL_CDECL runtime_lookup(Pipeline::PipeRuntime* self, uint32_t signature, Pipeline::DispatchData* out, Pipeline::PipeLookupCache* cache, bool is_test) noexcept {
+  State* st = static_cast<Runtime*>(self)->state;
+  b2dgpu_dispatch_data dd;
+  b2dgpu_result r = is_test ? b2dgpu_runtime_test(st->rt, signature, &dd, nullptr) : b2dgpu_runtime_get(st->rt, signature, &dd, nullptr);
+  if (r != B2DGPU_SUCCESS)
+    return bl_make_error(BLResult(r));            // BL_ERROR_NOT_IMPLEMENTED / BL_ERROR_NO_ENTRY, like fixedpiperuntime.cpp:314
+  out->init(Pipeline::FillFunc(dd.fill_func), Pipeline::FetchFunc(dd.fetch_func));
+  if (cache)
+    cache->store(signature, out);                 // fixedpiperuntime.cpp:319-320
+  return BL_SUCCESS;
+}
+
+static BLResult BL_CDECL runtime_test(Pipeline::PipeRuntime* self, uint32_t signature, Pipeline::DispatchData* out, Pipeline::PipeLookupCache* cache) noexcept {
+  return runtime_lookup(self, signature, out, cache, true);
+}
+
+static BLResult BL_CDECL runtime_get(Pipeline::PipeRuntime* self, uint32_t signature, Pipeline::DispatchData* out, Pipeline::PipeLookupCache* cache) noexcept {
+  return runtime_lookup(self, signature, out, cache, false);
+}
+
+static void BL_CDECL runtime_destroy(Pipeline::PipeRuntime* self) noexcept {
+  Runtime* rt = static_cast<Runtime*>(self);
+  State* st = rt->state;
+  if (st) {
+    if (st->rt) b2dgpu_sync(st->rt);
+    if (st->registered_pixels) b2dgpu_host_unregister(st->rt, st->registered_pixels);
+    if (st->target) b2dgpu_target_destroy(st->target);
+    if (st->rt) b2dgpu_runtime_destroy(st->rt);
+    delete st;
+  }
+  delete rt;
+}
+
+static const BLContextCreateInfo* adjust_create_info(const BLContextCreateInfo* options, BLContextCreateInfo* storage) noexcept {
+  if (!(options->flags & kCreateFlagGpuRuntime))
+    return options;
+  *storage = *options;
+  storage->thread_count = 1;                                        // workermanager.cpp:36-42: the user thread is the worker
+  storage->flags &= ~uint32_t(BL_CONTEXT_CREATE_FLAG_FALLBACK_TO_SYNC);
+  // b2dgpu_submit() is asynchronous and double buffered: shorter batches let the device start while the frontend is
+  // still recording (the reference's default is 10240 commands, rastercontext_p.h:62).
+  if (!storage->command_queue_limit)
+    storage->command_queue_limit = 2048;
+  return storage;
+}
+
+static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::PipeRuntime** runtime) noexcept {
+  if (*runtime && bl_test_flag((*runtime)->runtime_flags(), Pipeline::PipeRuntimeFlags::kIsolated))
+    (*runtime)->destroy();
+  *runtime = nullptr;
+
+  Runtime* rt = new (std::nothrow) Runtime();
+  State* st = new (std::nothrow) State();
+  if (!rt || !st) {
+    delete rt; delete st;
+    return bl_make_error(BL_ERROR_OUT_OF_MEMORY);
+  }
+
+  b2dgpu_create_info ci;
+  ci.struct_size = sizeof(ci);
+  ci.device = int32_t(options->reserved[0]);
+  ci.stream = nullptr;
+  ci.flags = 0;
+  b2dgpu_result r = b2dgpu_runtime_create(&ci, &st->rt);           // no CPU fallback: fails without a CUDA device
+  if (r != B2DGPU_SUCCESS) {
+    delete rt; delete st;
+    return bl_make_error(BLResult(r));
+  }
+
+  const char* e = getenv("B2DGPU_SHIM_CPU_EDGES");
+  st->cpu_edges = e && e[0] == '1';
+  e = getenv("B2DGPU_SHIM_PIN");
+  st->pin_images = !(e && e[0] == '0');
+
+  rt->_runtime_type = Pipeline::PipeRuntimeType(kPipeRuntimeTypeGpu);
+  rt->_runtime_flags = Pipeline::PipeRuntimeFlags::kIsolated;
+  rt->_runtime_size = uint16_t(sizeof(Runtime));
+  rt->_destroy = runtime_destroy;
+  rt->_funcs.test = runtime_test;
+  rt->_funcs.get = runtime_get;
+  rt->state = st;
+  *runtime = rt;
+  return BL_SUCCESS;
+}
+
+// The device canvas is created on first use from ctx_impl->dst_data (known only at the end of attach()) and
+// initialised with the image's current pixels.
+static BLResult ensure_target(BLRasterContextImpl* ctx_impl, State* st) noexcept {
+  if (st->target)
+    return BL_SUCCESS;
+  const BLImageData& d = ctx_impl->dst_data;
+  b2dgpu_result r = b2dgpu_target_create(st->rt, d.size.w, d.size.h, d.format, &st->target);
+  if (r != B2DGPU_SUCCESS)
+    return bl_make_error(BLResult(r));
+  const size_t bytes = size_t(d.stride) * size_t(d.size.h);
+  if (st->pin_images && d.stride > 0 && bytes >= (size_t(1) << 20)) {
+    if (b2dgpu_host_register(st->rt, d.pixel_data, bytes) == B2DGPU_SUCCESS)
+      st->registered_pixels = d.pixel_data;
+  }
+  b2dgpu_image_data img = { d.pixel_data, d.stride, d.size.w, d.size.h, d.format, 0 };
+  r = b2dgpu_target_upload(st->target, &img);
+  return r == B2DGPU_SUCCESS ? BL_SUCCESS : bl_make_error(BLResult(r));
+}
+
+static BLResult sync_to_host(BLRasterContextImpl* ctx_impl) noexcept {
+  State* st = state_of(ctx_impl);
+  if (!st->target || !st->device_dirty)
+    return BL_SUCCESS;
+  const BLImageData& d = ctx_impl->dst_data;
+  b2dgpu_image_data img = { d.pixel_data, d.stride, d.size.w, d.size.h, d.format, 0 };
+  b2dgpu_result r = b2dgpu_target_download(st->target, &img);      // stream ordered, returns when the pixels are there
+  if (r != B2DGPU_SUCCESS)
+    return ctx_impl->accumulate_error(bl_make_error(BLResult(r)));
+  st->device_dirty = false;
+  return BL_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Geometry recording: BLPathView / polygons -> b2dgpu_segment[] + vertices (the K1 input format).
+// ---------------------------------------------------------------------------------------------------------------
+static BL_INLINE void push_segment(State* st, uint32_t p0, uint32_t p1, uint32_t kind) noexcept {
+  b2dgpu_segment s;
+  s.p0 = p0;
+  s.p1_kind = (p1 << 2) | kind;
+  s.command = 0;                                  // patched in consume_batch()
+  st->segs.push_back(s);
+}
+
+static uint32_t add_state(State* st, const BLMatrix2D& m, BLTransformType transform_type, const BLBox& clip_fixed, double tolerance_fixed) noexcept {
+  b2dgpu_geometry_state gs;
+  memset(&gs, 0, sizeof(gs));
+  gs.m[0] = m.m00; gs.m[1] = m.m01; gs.m[2] = m.m10; gs.m[3] = m.m11; gs.m[4] = m.m20; gs.m[5] = m.m21;
+  gs.clip[0] = clip_fixed.x0; gs.clip[1] = clip_fixed.y0; gs.clip[2] = clip_fixed.x1; gs.clip[3] = clip_fixed.y1;
+  gs.tolerance_sq = Math::square(tolerance_fixed);
+  gs.transform_type = uint32_t(transform_type);
+  if (!st->states.empty() && memcmp(&st->states.back(), &gs, sizeof(gs)) == 0)
+    return uint32_t(st->states.size() - 1);
+  st->states.push_back(gs);
+  return uint32_t(st->states.size() - 1);
+}
+
+// EdgeSourcePath + EdgeBuilder::add_from_source (edgebuilder_p.h:165-281, 1032-1070): a figure starts at a MOVE, curve
+// commands need all of their vertices, and a figure is closed when `closed` or when a CLOSE command follows.
+static void append_path(State* st, const BLPathView& view, bool closed) noexcept {
+  const uint8_t* cmd = view.command_data;
+  const size_t n = view.size;
+  if (!n) return;
+  const uint32_t base = uint32_t(st->vtx.size() / 2);
+  const double* src = reinterpret_cast<const double*>(view.vertex_data);
+  st->vtx.insert(st->vtx.end(), src, src + n * 2);
+
+  size_t i = 0;
+  while (i < n) {
+    if (cmd[i] != BL_PATH_CMD_MOVE) { i++; continue; }
+    const size_t start = i;
+    size_t cur = i;
+    i++;
+    for (;;) {
+      if (i < n && cmd[i] == BL_PATH_CMD_ON) { push_segment(st, base + uint32_t(cur), base + uint32_t(i), B2DGPU_SEG_LINE); cur = i; i++; }
+      else if (i + 2 <= n && cmd[i] == BL_PATH_CMD_QUAD) { push_segment(st, base + uint32_t(cur), base + uint32_t(i), B2DGPU_SEG_QUAD); cur = i + 1; i += 2; }
+      else if (i + 2 < n && cmd[i] == BL_PATH_CMD_CUBIC) { push_segment(st, base + uint32_t(cur), base + uint32_t(i), B2DGPU_SEG_CUBIC); cur = i + 2; i += 3; }
+      else if (i + 2 < n && cmd[i] == BL_PATH_CMD_CONIC) { push_segment(st, base + uint32_t(cur), base + uint32_t(i), B2DGPU_SEG_CONIC); cur = i + 2; i += 2; }
+      else {
+        if (closed || (i < n && cmd[i] == BL_PATH_CMD_CLOSE))
+          push_segment(st, base + uint32_t(cur), base + uint32_t(start), B2DGPU_SEG_LINE);
+        break;
+      }
+    }
+  }
+}
+
+// EdgeSourceReversePathFromStrokeSink (edgebuilder_p.h:286-406): the stroker's `b` path, walked from its end.  The
+// vertices are stored reversed, so a reversed curve is an ordinary ascending segment of the reversed array.
+static void append_reverse_path_from_stroke_sink(State* st, const BLPathView& view) noexcept {
+  const uint8_t* cmd = view.command_data;
+  size_t n = view.size;
+  const bool must_close = n > 0 && cmd[n - 1] == BL_PATH_CMD_CLOSE;
+  n -= size_t(must_close);
+  if (!n || cmd[n - 1] != BL_PATH_CMD_ON)
+    return;
+
+  const uint32_t base = uint32_t(st->vtx.size() / 2);
+  for (size_t k = 0; k < n; k++) {                // reversed[k] = vertex[n - 1 - k]
+    st->vtx.push_back(view.vertex_data[n - 1 - k].x);
+    st->vtx.push_back(view.vertex_data[n - 1 - k].y);
+  }
+  // Position p in the original array corresponds to n - 1 - p in the reversed one; `pos` is the original index of
+  // the current point (the source's _cmd_ptr).
+  size_t pos = n - 1;
+  const uint32_t start = base;
+  uint32_t cur = base;
+  while (pos != 0) {
+    const uint8_t c = cmd[pos - 1];
+    const uint32_t r = base + uint32_t(n - pos);  // reversed index of original vertex pos - 1
+    if (c <= BL_PATH_CMD_ON) { push_segment(st, cur, r, B2DGPU_SEG_LINE); cur = r; pos -= 1; }
+    else if (c == BL_PATH_CMD_QUAD && pos >= 2) { push_segment(st, cur, r, B2DGPU_SEG_QUAD); cur = r + 1; pos -= 2; }
+    else if (c == BL_PATH_CMD_CUBIC && pos >= 3) { push_segment(st, cur, r, B2DGPU_SEG_CUBIC); cur = r + 2; pos -= 3; }
+    else break;                                   // conics never come out of the stroker; the reference's source stops too
+  }
+  if (must_close)
+    push_segment(st, cur, start, B2DGPU_SEG_LINE);
+}
+
+template<typename PointType>
+static void append_poly(State* st, const PointType* pts, size_t n) noexcept {
+  const uint32_t base = uint32_t(st->vtx.size() / 2);
+  for (size_t i = 0; i < n; i++) {
+    st->vtx.push_back(double(pts[i].x));
+    st->vtx.push_back(double(pts[i].y));
+  }
+  for (size_t i = 1; i < n; i++)
+    push_segment(st, base + uint32_t(i - 1), base + uint32_t(i), B2DGPU_SEG_LINE);
+  push_segment(st, base + uint32_t(n - 1), base, B2DGPU_SEG_LINE);
+}
+
+// Tagged pointer stored in RenderCommand::_payload.analytic.edges for commands whose geometry was recorded at call
+// time: (index into State::direct << 1) | 1.  Real EdgeVector pointers are 8-byte aligned.
+static BL_INLINE const EdgeVector<int>* direct_tag(size_t index) noexcept { return reinterpret_cast<const EdgeVector<int>*>((uintptr_t(index) << 1) | 1u); }
+static BL_INLINE bool is_direct_tag(const EdgeVector<int>* p) noexcept { return (uintptr_t(p) & 1u) != 0; }
+static BL_INLINE size_t direct_index(const EdgeVector<int>* p) noexcept { return size_t(uintptr_t(p) >> 1); }
+
+// Enqueues a FillAnalytic command whose geometry is segments [seg_begin, end) recorded just now.
+static BLResult enqueue_direct(BLRasterContextImpl* ctx_impl, DispatchInfo di, DispatchStyle ds, BLFillRule fill_rule,
+                               size_t seg_begin, size_t vtx_begin, const BLMatrix2D& transform, BLTransformType transform_type) noexcept {
+  State* st = state_of(ctx_impl);
+  if (st->segs.size() == seg_begin) {
+    st->vtx.resize(vtx_begin);
+    return BL_SUCCESS;
+  }
+
+  RenderCommand* command = ctx_impl->worker_mgr->current_command();
+  di.add_fill_type(Pipeline::FillType::kAnalytic);
+  command->init_command(di.alpha);
+  command->init_fill_analytic(const_cast<EdgeVector<int>*>(direct_tag(st->direct.size())), 0, fill_rule);
+
+  BLResult result = ensure_fetch_and_dispatch_data(ctx_impl, di.signature, ds.fetch_data, command->pipe_dispatch_data());
+  if (BL_UNLIKELY(result != BL_SUCCESS)) {
+    st->segs.resize(seg_begin);
+    st->vtx.resize(vtx_begin);
+    return result;
+  }
+
+  DirectGeometry dg;
+  dg.seg_begin = uint32_t(seg_begin);
+  dg.seg_count = uint32_t(st->segs.size() - seg_begin);
+  dg.state_index = add_state(st, transform, transform_type, ctx_impl->final_clip_box_fixed_d(), ctx_impl->internal_state.toleranceFixedD);
+  st->direct.push_back(dg);
+
+  return enqueue_command(ctx_impl, command, kInvalidQuantizedCoordinate, ds.fetch_data, [&](RenderCommand* command) noexcept {
+    command->_payload.analytic.state_slot_index = ctx_impl->worker_mgr().next_state_slot_index();
+  });
+}
+
+//! True when paths / polygons are recorded as segments for the GPU edge builder instead of being flattened here.
+static BL_INLINE bool records_geometry(const BLRasterContextImpl* ctx_impl) noexcept {
+  return is_gpu(ctx_impl) && !state_of(ctx_impl)->cpu_edges;
+}
+
+//! fill_unclipped_path<kAsync>() on a GPU context (rastercontext.cpp:2787-2797).
+static BLResult record_path(BLRasterContextImpl* ctx_impl, DispatchInfo di, DispatchStyle ds, const BLPathView& view,
+                            BLFillRule fill_rule, const BLMatrix2D& transform, BLTransformType transform_type) noexcept {
+  State* st = state_of(ctx_impl);
+  const size_t seg_begin = st->segs.size(), vtx_begin = st->vtx.size();
+  append_path(st, view, true);
+  return enqueue_direct(ctx_impl, di, ds, fill_rule, seg_begin, vtx_begin, transform, transform_type);
+}
+
+//! fill_unclipped_polygon_t<kAsync>() on a GPU context (rastercontext.cpp:2848-2858).
+template<typename PointType>
+static BLResult record_poly(BLRasterContextImpl* ctx_impl, DispatchInfo di, DispatchStyle ds, const PointType* pts, size_t size,
+                            BLFillRule fill_rule, const BLMatrix2D& transform, BLTransformType transform_type) noexcept {
+  State* st = state_of(ctx_impl);
+  const size_t seg_begin = st->segs.size(), vtx_begin = st->vtx.size();
+  if (size)
+    append_poly(st, pts, size);
+  return enqueue_direct(ctx_impl, di, ds, fill_rule, seg_begin, vtx_begin, transform, transform_type);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Job pass (renderjobproc_p.h:114-270 with the EdgeBuilder replaced by segment recording)
+// ---------------------------------------------------------------------------------------------------------------
+struct SegmentSink {
+  State* st;
+  // Stroke only:
+  BLPath* paths;
+  const BLStrokeOptions* stroke_options;
+  const BLApproximationOptions* approximation_options;
+};
+
+static BLResult BL_CDECL fill_glyph_run_segment_sink(BLPathCore* path, const void* info, void* user_data) noexcept {
+  bl_unused(info);
+  SegmentSink* sink = static_cast<SegmentSink*>(user_data);
+  append_path(sink->st, path->dcast().view(), true);                // fill_glyph_run_sink, rastercontextops.cpp:51-59
+  return path->dcast().clear();
+}
+
+static BLResult BL_CDECL stroke_geometry_segment_sink(BLPathCore* a, BLPathCore* b, BLPathCore* c, size_t figure_start, size_t figure_end, void* user_data) noexcept {
+  bl_unused(figure_start, figure_end);
+  SegmentSink* sink = static_cast<SegmentSink*>(user_data);
+  append_path(sink->st, a->dcast().view(), false);                  // stroke_geometry_sink, rastercontextops.cpp:61-74
+  append_reverse_path_from_stroke_sink(sink->st, b->dcast().view());
+  if (!c->dcast().is_empty())
+    append_path(sink->st, c->dcast().view(), false);
+  return a->dcast().clear();
+}
+
+static BLResult BL_CDECL stroke_glyph_run_segment_sink(BLPathCore* path, const void* info, void* user_data) noexcept {
+  bl_unused(info);
+  SegmentSink* sink = static_cast<SegmentSink*>(user_data);
+  BLPath& a = sink->paths[0];
+  BLPath& b = sink->paths[1];
+  BLPath& c = sink->paths[2];
+  a.clear();
+  BLResult result = PathInternal::stroke_path(path->dcast().view(), *sink->stroke_options, *sink->approximation_options,
+                                              a, b, c, stroke_geometry_segment_sink, sink);
+  bl_path_clear(path);                                              // stroke_glyph_run_sink, rastercontextops.cpp:76-96
+  return result;
+}
+
+struct JobGeometry {
+  bool valid;
+  uint32_t seg_begin, seg_count, state_index;
+};
+
+static BL_INLINE const BLGlyphRun* job_glyph_run(WorkData* work_data, RenderJob_TextOp* job, BLResult& result) noexcept {
+  const uint32_t data_type = job->text_data_type();
+  if (data_type == RenderJob::kTextDataGlyphRun)
+    return &job->_glyph_run;
+  BLGlyphBuffer* glyph_buffer;
+  if (data_type != RenderJob::kTextDataGlyphBuffer) {
+    glyph_buffer = &work_data->glyph_buffer;
+    glyph_buffer->set_text(job->text_data(), job->text_size(), (BLTextEncoding)data_type);
+  }
+  else {
+    glyph_buffer = &job->_glyph_buffer.dcast();
+  }
+  result = job->_font.dcast().shape(*glyph_buffer);
+  return &glyph_buffer->glyph_run();
+}
+
+static JobGeometry process_job(State* st, WorkData* work_data, RenderJob* base_job) noexcept {
+  JobGeometry out = { false, uint32_t(st->segs.size()), 0, 0 };
+  const size_t vtx_begin = st->vtx.size();
+  BLResult result = BL_SUCCESS;
+  BLMatrix2D state_transform;
+  BLTransformType state_transform_type = BL_TRANSFORM_TYPE_IDENTITY;
+  const SharedFillState* fill_state = static_cast<RenderJob_BaseOp*>(base_job)->fill_state();
+
+  switch (base_job->job_type()) {
+    case RenderJobType::kFillGeometry: {
+      RenderJob_GeometryOp* job = static_cast<RenderJob_GeometryOp*>(base_job);
+      JobProc::JobStateAccessor accessor(job);
+      BLPath* path = JobProc::get_geometry_as_path(work_data, job);
+      if (path) {
+        append_path(st, path->view(), true);
+        state_transform = accessor.final_transform_fixed(job->origin_fixed());
+        state_transform_type = accessor.final_transform_fixed_type();
+      }
+      else result = BL_ERROR_INVALID_GEOMETRY;
+      JobProc::finalize_geometry_data(work_data, job);
+      break;
+    }
+
+    case RenderJobType::kStrokeGeometry: {
+      // add_stroked_path_edges (rastercontextops_p.h:100-146) with a segment sink.
+      RenderJob_GeometryOp* job = static_cast<RenderJob_GeometryOp*>(base_job);
+      JobProc::JobStateAccessor accessor(job);
+      const BLPath* path = JobProc::get_geometry_as_path(work_data, job);
+      if (path) {
+        SegmentSink sink = { st, st->tmp_path, nullptr, nullptr };
+        BLPath* a = &st->tmp_path[0];
+        BLPath* b = &st->tmp_path[1];
+        BLPath* c = &st->tmp_path[2];
+        state_transform = accessor.final_transform_fixed(job->origin_fixed());
+        state_transform_type = accessor.final_transform_fixed_type();
+        if (accessor.stroke_options().transform_order != BL_STROKE_TRANSFORM_ORDER_AFTER) {
+          BLPath* in = &st->tmp_path[3];
+          in->clear();
+          result = in->add_path(*path, accessor.user_transform());
+          path = in;
+          state_transform = accessor.meta_transform_fixed(job->origin_fixed());
+          state_transform_type = accessor.meta_transform_fixed_type();
+        }
+        if (result == BL_SUCCESS) {
+          a->clear();
+          result = PathInternal::stroke_path(path->view(), accessor.stroke_options(), accessor.approximation_options(),
+                                             *a, *b, *c, stroke_geometry_segment_sink, &sink);
+        }
+      }
+      else result = BL_ERROR_INVALID_GEOMETRY;
+      JobProc::finalize_geometry_data(work_data, job);
+      break;
+    }
+
+    case RenderJobType::kFillText: {
+      // add_filled_glyph_run_edges (rastercontextops_p.h:76-98): outlines arrive already transformed to 24.8 space.
+      RenderJob_TextOp* job = static_cast<RenderJob_TextOp*>(base_job);
+      JobProc::JobStateAccessor accessor(job);
+      const BLGlyphRun* glyph_run = job_glyph_run(work_data, job, result);
+      if (result == BL_SUCCESS) {
+        BLMatrix2D transform(accessor.final_transform_fixed(job->origin_fixed()));
+        BLPath* path = &st->tmp_path[4];
+        path->clear();
+        SegmentSink sink = { st, st->tmp_path, nullptr, nullptr };
+        result = bl_font_get_glyph_run_outlines(&job->_font, glyph_run, &transform, path, fill_glyph_run_segment_sink, &sink);
+        state_transform.reset();
+        state_transform_type = BL_TRANSFORM_TYPE_IDENTITY;
+      }
+      job->destroy();
+      break;
+    }
+
+    case RenderJobType::kStrokeText: {
+      // add_stroked_glyph_run_edges (rastercontextops_p.h:148-195).
+      RenderJob_TextOp* job = static_cast<RenderJob_TextOp*>(base_job);
+      JobProc::JobStateAccessor accessor(job);
+      const BLGlyphRun* glyph_run = job_glyph_run(work_data, job, result);
+      if (result == BL_SUCCESS) {
+        SegmentSink sink = { st, st->tmp_path, &accessor.stroke_options(), &accessor.approximation_options() };
+        BLMatrix2D glyph_run_transform;
+        if (accessor.stroke_options().transform_order == BL_STROKE_TRANSFORM_ORDER_AFTER) {
+          glyph_run_transform.reset();
+          state_transform = accessor.final_transform_fixed(job->origin_fixed());
+          state_transform_type = accessor.final_transform_fixed_type();
+        }
+        else {
+          glyph_run_transform = accessor.user_transform();
+          state_transform = accessor.meta_transform_fixed(job->origin_fixed());
+          state_transform_type = accessor.meta_transform_fixed_type();
+        }
+        BLPath* path = &st->tmp_path[4];
+        path->clear();
+        result = bl_font_get_glyph_run_outlines(&job->_font, glyph_run, &glyph_run_transform, path, stroke_glyph_run_segment_sink, &sink);
+      }
+      job->destroy();
+      break;
+    }
+
+    default:
+      result = BL_ERROR_INVALID_STATE;
+      break;
+  }
+
+  if (result != BL_SUCCESS) {
+    work_data->accumulate_error(result);
+    st->segs.resize(out.seg_begin);
+    st->vtx.resize(vtx_begin);
+    return out;
+  }
+
+  out.seg_count = uint32_t(st->segs.size()) - out.seg_begin;
+  if (!out.seg_count) {
+    st->vtx.resize(vtx_begin);
+    return out;
+  }
+  out.state_index = add_state(st, state_transform, state_transform_type, fill_state->final_clip_box_fixed_d, fill_state->toleranceFixedD);
+  out.valid = true;
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Seam A: batch consumer
+// ---------------------------------------------------------------------------------------------------------------
+static BL_INLINE uint32_t fill_rule_mask(uint32_t fill_rule) noexcept {
+  return fill_rule == BL_FILL_RULE_NON_ZERO ? B2DGPU_FILL_RULE_MASK_NON_ZERO : B2DGPU_FILL_RULE_MASK_EVEN_ODD;
+}
+
+// CPU-built edges (EdgeVector lists, edgestorage_p.h:38-60) -> one record per line in its original direction.
+static void append_edge_vectors(State* st, const EdgeVector<int>* ev) noexcept {
+  for (; ev; ev = ev->next) {
+    const size_t count = ev->count();
+    const bool flipped = ev->sign_bit() != 0;
+    for (size_t i = 1; i < count; i++) {
+      b2dgpu_edge e;
+      if (!flipped) { e.x0 = ev->pts[i - 1].x; e.y0 = ev->pts[i - 1].y; e.x1 = ev->pts[i].x; e.y1 = ev->pts[i].y; }
+      else { e.x0 = ev->pts[i].x; e.y0 = ev->pts[i].y; e.x1 = ev->pts[i - 1].x; e.y1 = ev->pts[i - 1].y; }
+      st->edges.push_back(e);
+    }
+  }
+}
+
+static uint32_t add_fetch_data(State* st, const void* key, const void* pipeline_data) noexcept {
+  // Consecutive commands usually share their style: look at the most recent entries first.
+  const size_t n = st->fetch_keys.size();
+  for (size_t k = 0; k < n && k < 4; k++)
+    if (st->fetch_keys[n - 1 - k] == key)
+      return uint32_t(n - 1 - k);
+  b2dgpu_fetch_data fd;
+  memcpy(&fd, pipeline_data, sizeof(fd));
+  st->fetch.push_back(fd);
+  st->fetch_keys.push_back(key);
+  return uint32_t(n);
+}
+
+static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, RenderBatch* batch) noexcept {
+  State* st = state_of(ctx_impl);
+  BL_STATIC_ASSERT(sizeof(b2dgpu_fetch_data) == sizeof(Pipeline::FetchData));
+
+  BLResult result = ensure_target(ctx_impl, st);
+  if (result != BL_SUCCESS)
+    work_data->accumulate_error(result);
+
+  const uint32_t command_count = batch->command_count();
+  st->cmds.clear();
+  st->cmds.resize(command_count);
+  st->fetch.clear();
+  st->fetch_keys.clear();
+  st->edges.clear();
+
+  // Queues are chained; a job addresses its command as (queue, index).
+  struct QueueBase { const RenderCommandQueue* queue; uint32_t base; };
+  std::vector<QueueBase> queue_bases;
+
+  // ---- pass 1: jobs ----
+  struct PendingJob { RenderJob* job; uint32_t command; };
+  std::vector<JobGeometry> job_geometry(command_count, JobGeometry{ false, 0, 0, 0 });
+  {
+    uint32_t base = 0;
+    for (const RenderCommandQueue* q = batch->command_list().first(); q; q = q->next()) {
+      queue_bases.push_back(QueueBase{ q, base });
+      base += uint32_t(q->size());
+    }
+  }
+  auto global_index = [&](const RenderCommandQueue* q, size_t index) noexcept -> uint32_t {
+    for (const QueueBase& qb : queue_bases)
+      if (qb.queue == q) return qb.base + uint32_t(index);
+    return 0xFFFFFFFFu;
+  };
+
+  if (batch->job_count()) {
+    size_t remaining = batch->job_count();
+    for (const RenderJobQueue* jq = batch->job_list().first(); jq && remaining; jq = jq->next()) {
+      for (size_t i = 0; i < jq->size() && remaining; i++, remaining--) {
+        RenderJob* job = jq->at(i);
+        if (st->cpu_edges) {
+          JobProc::process_job(work_data, job);                     // reference EdgeBuilder; the command gets its edges
+          continue;
+        }
+        const uint32_t ci = global_index(job->command_queue(), job->command_index());
+        JobGeometry g = process_job(st, work_data, job);
+        if (ci < command_count)
+          job_geometry[ci] = g;
+      }
+    }
+  }
+
+  // ---- pass 2: commands ----
+  bool ok = result == BL_SUCCESS;
+  uint32_t out_count = 0;
+  uint32_t ci = 0;
+  for (const RenderCommandQueue* q = batch->command_list().first(); q && ok; q = q->next()) {
+    for (size_t i = 0; i < q->size(); i++, ci++) {
+      const RenderCommand& rc = q->at(i);
+      const Pipeline::DispatchData* dd = rc.pipe_dispatch_data();
+      if (!B2DGPU_DISPATCH_IS_GPU(dd)) { work_data->accumulate_error(BL_ERROR_INVALID_STATE); continue; }
+
+      b2dgpu_command c;
+      memset(&c, 0, sizeof(c));
+      c.signature = B2DGPU_DISPATCH_SIGNATURE(dd);
+      c.alpha = rc.alpha();
+
+      switch (rc.type()) {
+        case RenderCommandType::kFillBoxA:
+        case RenderCommandType::kFillBoxU: {
+          c.type = rc.type() == RenderCommandType::kFillBoxA ? B2DGPU_CMD_FILL_BOX_A : B2DGPU_CMD_FILL_BOX_U;
+          const BLBoxI& b = rc.box_i();
+          c.box[0] = b.x0; c.box[1] = b.y0; c.box[2] = b.x1; c.box[3] = b.y1;
+          if (!(b.x0 < b.x1 && b.y0 < b.y1)) continue;
+          break;
+        }
+
+        case RenderCommandType::kFillAnalytic: {
+          c.fill_rule_mask = fill_rule_mask(rc.analytic_fill_rule());
+          const EdgeVector<int>* ev = rc.analytic_edges();
+          if (is_direct_tag(ev)) {
+            const DirectGeometry& dg = st->direct[direct_index(ev)];
+            c.type = B2DGPU_CMD_FILL_GEOMETRY;
+            c.data_offset = dg.seg_begin; c.data_count = dg.seg_count; c.state_index = dg.state_index;
+          }
+          else if (ev) {
+            c.type = B2DGPU_CMD_FILL_ANALYTIC;
+            c.data_offset = uint32_t(st->edges.size());
+            append_edge_vectors(st, ev);
+            c.data_count = uint32_t(st->edges.size()) - c.data_offset;
+            if (!c.data_count) continue;
+          }
+          else if (job_geometry[ci].valid) {
+            const JobGeometry& g = job_geometry[ci];
+            c.type = B2DGPU_CMD_FILL_GEOMETRY;
+            c.data_offset = g.seg_begin; c.data_count = g.seg_count; c.state_index = g.state_index;
+          }
+          else continue;                                            // everything clipped out / failed job
+          if (c.type == B2DGPU_CMD_FILL_GEOMETRY)
+            for (uint32_t s = 0; s < c.data_count; s++)
+              st->segs[c.data_offset + s].command = out_count;
+          break;
+        }
+
+        case RenderCommandType::kFillBoxMaskA: {
+          const RenderCommand::FillBoxMaskA& p = rc._payload.box_mask_a;
+          const BLImageImpl* mask = p.mask_image_i.ptr;
+          if (mask->depth != 8) { work_data->accumulate_error(BL_ERROR_NOT_IMPLEMENTED); continue; }
+          c.type = B2DGPU_CMD_FILL_BOX_MASK_A;
+          c.box[0] = p.box_i.x0; c.box[1] = p.box_i.y0; c.box[2] = p.box_i.x1; c.box[3] = p.box_i.y1;
+          if (!(p.box_i.x0 < p.box_i.x1 && p.box_i.y0 < p.box_i.y1)) continue;
+          b2dgpu_fetch_data fd;
+          memset(&fd, 0, sizeof(fd));
+          fd.pattern.src.pixel_data = static_cast<const uint8_t*>(mask->pixel_data) + intptr_t(p.mask_offset_i.y) * mask->stride + p.mask_offset_i.x;
+          fd.pattern.src.stride = mask->stride;
+          fd.pattern.src.w = p.box_i.x1 - p.box_i.x0;
+          fd.pattern.src.h = p.box_i.y1 - p.box_i.y0;
+          c.reserved[0] = uint32_t(st->fetch.size());
+          st->fetch.push_back(fd);
+          st->fetch_keys.push_back(nullptr);
+          break;
+        }
+
+        default:
+          work_data->accumulate_error(BL_ERROR_NOT_IMPLEMENTED);
+          continue;
+      }
+
+      if (rc.has_style_fetch_data())
+        c.fetch_index = add_fetch_data(st, rc._source.fetch_data, &rc._source.fetch_data->pipeline_data);
+      else
+        c.solid_prgb32 = rc._source.solid.prgb32;
+      st->cmds[out_count++] = c;
+    }
+  }
+
+  if (ok && out_count) {
+    b2dgpu_batch_view v;
+    memset(&v, 0, sizeof(v));
+    v.struct_size = sizeof(v);
+    v.command_count = out_count;
+    v.commands = st->cmds.data();
+    v.fetch_data = st->fetch.data();        v.fetch_count = uint32_t(st->fetch.size());
+    v.edges = st->edges.data();             v.edge_count = uint32_t(st->edges.size());
+    v.vertices = st->vtx.data();            v.vertex_count = uint32_t(st->vtx.size() / 2);
+    v.segments = st->segs.data();           v.segment_count = uint32_t(st->segs.size());
+    v.geometry_states = st->states.data();  v.geometry_state_count = uint32_t(st->states.size());
+    v.pixel_origin_x = work_data->ctx_data.pixel_origin.x;
+    v.pixel_origin_y = work_data->ctx_data.pixel_origin.y;
+    // Copies everything it needs before returning (rastercontext.cpp:1060-1063 frees the batch right after).
+    b2dgpu_result r = b2dgpu_submit(st->rt, st->target, &v);
+    if (r != B2DGPU_SUCCESS)
+      work_data->accumulate_error(bl_make_error(BLResult(r)));
+    else
+      st->device_dirty = true;
+  }
+
+  st->clear_geometry();
+}
+
+} // {GpuShim}
+
+#endif // B2DGPU_SHIM_IMPL_H_INCLUDED

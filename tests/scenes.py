@@ -233,3 +233,99 @@ def masked_fills(count, W, H, op=SRC_OVER, style="solid"):
         ctx.set_global_alpha(1.0)
         ctx._keep_masks = masks
     return scene
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Strokes (bl_bench Stroke* tests, bl_bench_backend_blend2d.cpp:288-500 with render_op == kStroke): the reference's
+# stroker runs on the host, its output paths enter the edge builder.  Only on Blend2D-API bindings.
+# ---------------------------------------------------------------------------------------------------------------------
+def strokes(count, W, H, style="solid", op=SRC_OVER):
+    def scene(api, ctx, rng):
+        ctx.set_comp_op(op)
+        for i in range(count):
+            size = float(rng.choice([8, 16, 32, 64, 128, 256]))
+            x, y = float(rng.uniform(-10, W - size)), float(rng.uniform(-10, H - size))
+            ctx.set_stroke_width(float(rng.choice([0.5, 1.0, 2.0, 5.0, 11.5])))
+            ctx.set_stroke_join(int(rng.integers(0, 5)))
+            ctx.set_stroke_caps(int(rng.integers(0, 6)))
+            ctx.set_stroke_alpha(float(rng.choice([1.0, 0.5])))
+            if style == "solid":
+                ctx.set_stroke_style(rand_rgba32(rng))
+            else:
+                gtype = {"linear": LINEAR, "radial": RADIAL, "conic": CONIC}[style]
+                ctx.set_stroke_style(make_gradient(api, rng, gtype, int(rng.integers(0, 3)), x, y, size, size))
+            kind = i % 6
+            if kind == 0:
+                ctx.stroke_rect_d(x, y, size, size)
+            elif kind == 1:
+                n = int(rng.choice([3, 10, 20]))
+                ctx.stroke_polygon(np.stack([rng.uniform(x, x + size, n), rng.uniform(y, y + size, n)], 1))
+            elif kind == 2:
+                n = int(rng.choice([2, 5, 12]))
+                ctx.stroke_polyline(np.stack([rng.uniform(x, x + size, n), rng.uniform(y, y + size, n)], 1))
+            elif kind == 3:
+                xs, ys = rng.uniform(x, x + size, 7), rng.uniform(y, y + size, 7)
+                p = api.Path()
+                p.move_to(xs[0], ys[0]); p.quad_to(xs[1], ys[1], xs[2], ys[2]); p.cubic_to(xs[3], ys[3], xs[4], ys[4], xs[5], ys[5])
+                if rng.integers(0, 2):
+                    p.close()
+                ctx.stroke_path(p)
+            elif kind == 4:
+                ctx.stroke_geometry(7, [x, y, size, size, min(size / 2, 12.0), min(size / 2, 7.0)])      # round rect
+            else:
+                ctx.rotate(float(rng.uniform(0, 6.28)), W / 2, H / 2)
+                ctx.set_stroke_transform_order(int(rng.integers(0, 2)))
+                ctx.stroke_geometry(6, [x + size / 2, y + size / 2, size / 2, size / 3])                  # ellipse
+                ctx.reset_transform()
+                ctx.set_stroke_transform_order(0)
+    return scene
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Config 3: text (tester: 4-character strings from an 84-character alphabet, font size 20, ABeeZee -
+# blend2d-testing/tests/bl_test_context_utilities.h:1160-1222).  Only on Blend2D-API bindings.
+# ---------------------------------------------------------------------------------------------------------------------
+ALPHABET = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789!@#$%^&*()_+-=[]{};:,.<>?/"
+
+
+def font_path():
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ABeeZee-Regular.ttf")
+
+
+def text_runs(count, W, H, size=20.0, chars=4, style="solid", stroke=False, op=SRC_OVER):
+    def scene(api, ctx, rng):
+        face = api.FontFace(font_path())
+        font = api.Font(face, size)
+        ctx._scene_keep = (face, font)
+        ctx.set_comp_op(op)
+        if stroke:
+            ctx.set_stroke_width(1.5)
+        for _ in range(count):
+            text = "".join(ALPHABET[int(k)] for k in rng.integers(0, len(ALPHABET), chars))
+            x, y = float(rng.uniform(-10, W - 10)), float(rng.uniform(0, H + 10))
+            if stroke:
+                ctx.set_stroke_style(rand_rgba32(rng))
+                ctx.stroke_utf8_text(x, y, font, text)
+            else:
+                style_for(api, ctx, rng, style, x, y - size, size * chars * 0.6, size)
+                ctx.fill_utf8_text(x, y, font, text)
+    return scene
+
+
+def geometries(count, W, H, op=SRC_OVER):
+    """fill_geometry() with the simple BLGeometryType shapes (circle, ellipse, round rect, chord, pie, triangle)."""
+    def scene(api, ctx, rng):
+        ctx.set_comp_op(op)
+        for i in range(count):
+            ctx.set_fill_style(rand_rgba32(rng))
+            s = float(rng.choice([8, 32, 100, 300]))
+            x, y = float(rng.uniform(-20, W)), float(rng.uniform(-20, H))
+            k = i % 6
+            if k == 0: ctx.fill_geometry(5, [x, y, s / 2])
+            elif k == 1: ctx.fill_geometry(6, [x, y, s / 2, s / 3])
+            elif k == 2: ctx.fill_geometry(7, [x, y, s, s * 0.7, s * 0.2, s * 0.1])
+            elif k == 3: ctx.fill_geometry(9, [x, y, s / 2, s / 2, float(rng.uniform(0, 6)), float(rng.uniform(0.5, 5))])
+            elif k == 4: ctx.fill_geometry(10, [x, y, s / 2, s / 3, float(rng.uniform(0, 6)), float(rng.uniform(0.5, 5))])
+            else: ctx.fill_geometry(12, [x, y, x + s, y + s / 3, x + s / 4, y + s])
+    return scene

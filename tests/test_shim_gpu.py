@@ -1,0 +1,136 @@
+"""The real drop-in: Blend2D's own frontend with the rastercontext.cpp overlay (shim/), its PipeRuntime
+selected through BLContextCreateInfo.flags |= 0x10000000.
+
+Every test creates two contexts through the reference's `bl_context_init_as` of the SAME library - one with
+BL_CONTEXT_CREATE_FLAG_DISABLE_JIT (portable CPU pipeline), one with the GPU flag - replays one command stream into both
+and compares the images, the way bl_test_context_jit does for JIT vs portable
+(blend2d-testing/tests/bl_test_context_jit.cpp:174-258).  Tolerance 0; 1 where conic gradients are in the scene.
+"""
+import types
+
+import numpy as np
+import pytest
+
+from tests import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def B():
+    from blend2d_b200 import blend2d_gpu as B
+    if not B.available():
+        pytest.fail(f"{B.LIB_PATH} is missing: run `make -C shim` where /root/reference exists (it travels with gpurun)")
+    return B
+
+
+def both(B, scene, W, H, fmt=1, seed=1, backdrop=None, **kw):
+    out = []
+    for gpu in (False, True):
+        img = B.Image(W, H, fmt)
+        if backdrop is not None:
+            img.from_numpy(backdrop)
+        ctx = B.Context(img, **kw) if gpu else B.cpu_context(img)
+        scene(B, ctx, np.random.default_rng(seed))
+        ctx.end()
+        err = ctx.accumulated_error_flags()
+        out.append(img.to_numpy())
+        ctx.close()
+        assert err == 0, f"accumulated_error_flags = {err:#x} ({'gpu' if gpu else 'cpu'})"
+    return out
+
+
+def assert_same(cpu, gpu, tol=0):
+    n, d = S.channel_diff(cpu, gpu)
+    assert d <= tol, f"{n} pixels differ, max channel diff {d}"
+    assert (cpu != 0).any(), "the scene drew nothing"
+
+
+@pytest.mark.parametrize("fmt", [1, 2, 3])
+def test_mixed_scene(B, fmt):
+    cpu, gpu = both(B, S.mixed(150, 400, 300), 400, 300, fmt, seed=11)
+    assert_same(cpu, gpu, 1)
+
+
+@pytest.mark.parametrize("kind", ["A", "U"])
+def test_bl_bench_rects(B, kind):
+    cpu, gpu = both(B, S.rects(kind, 300, 32, 512, 600), 512, 600)
+    assert_same(cpu, gpu)
+
+
+@pytest.mark.parametrize("style,tol", [("solid", 0), ("linear", 0), ("radial", 0), ("conic", 1)])
+def test_polygons_and_curves(B, style, tol):
+    cpu, gpu = both(B, S.polygons(60, 128, 20, 640, 480, rule=1, style=style, extend=2), 640, 480)
+    assert_same(cpu, gpu, tol)
+    cpu, gpu = both(B, S.curve_paths("cubic", 40, 640, 480, style=style, extend=1), 640, 480)
+    assert_same(cpu, gpu, tol)
+
+
+@pytest.mark.parametrize("kind,quality", [("rot", 0), ("rot", 1), ("round", 0), ("round", 1)])
+def test_patterns(B, kind, quality):
+    cpu, gpu = both(B, S.pattern_shapes(kind, 60, 64, 640, 480, quality=quality), 640, 480)
+    assert_same(cpu, gpu)
+
+
+def test_fill_mask(B):
+    cpu, gpu = both(B, S.masked_fills(60, 300, 200), 300, 200)
+    assert_same(cpu, gpu)
+
+
+@pytest.mark.parametrize("style,tol", [("solid", 0), ("linear", 0), ("conic", 1)])
+def test_strokes(B, style, tol):
+    """the reference's stroker on the host, its a/b/c paths through the device edge builder."""
+    cpu, gpu = both(B, S.strokes(120, 640, 480, style=style), 640, 480, seed=5)
+    assert_same(cpu, gpu, tol)
+
+
+def test_text(B):
+    """Config 3: bl_context_fill_utf8_text_d / stroke_utf8_text_d with the bundled font."""
+    cpu, gpu = both(B, S.text_runs(300, 640, 360), 640, 360)
+    assert_same(cpu, gpu)
+    cpu, gpu = both(B, S.text_runs(60, 640, 360, size=33.0, chars=7, style="linear"), 640, 360)
+    assert_same(cpu, gpu)
+    cpu, gpu = both(B, S.text_runs(80, 640, 360, size=40.0, stroke=True), 640, 360)
+    assert_same(cpu, gpu)
+
+
+def test_geometries(B):
+    cpu, gpu = both(B, S.geometries(120, 640, 480), 640, 480)
+    assert_same(cpu, gpu)
+
+
+def test_blit_image(B):
+    def scene(api, ctx, rng):
+        tex = S.make_texture(api, 96, 64, 1, 9)
+        ctx._scene_keep = tex
+        for i in range(40):
+            ctx.set_global_alpha(1.0 if i % 2 else 0.6)
+            ctx.set_comp_op(S.SRC_OVER if i % 3 else S.SRC_COPY)
+            x, y = float(rng.uniform(-40, 500)), float(rng.uniform(-30, 400))
+            if i % 4 == 0:
+                ctx.blit_image(int(x), int(y), tex)
+            elif i % 4 == 1:
+                ctx.blit_image(x, y, tex, (5, 7, 60, 40))
+            else:
+                ctx.blit_scaled_image(x, y, float(rng.uniform(10, 200)), float(rng.uniform(10, 200)), tex)
+    cpu, gpu = both(B, scene, 512, 400)
+    assert_same(cpu, gpu)
+
+
+def test_existing_pixels_and_incremental_flush(B):
+    """The canvas starts from the image's pixels; flush(SYNC) in the middle makes the host image coherent."""
+    rng = np.random.default_rng(2)
+    backdrop = rng.integers(0, 256, (200, 333)).astype(np.uint32) * 0x01010101
+
+    def scene(api, ctx, rng):
+        S.polygons(20, 64, 10, 333, 200)(api, ctx, rng)
+        ctx.flush(sync=True)
+        assert (ctx.image.to_numpy() != backdrop).any()
+        S.curve_paths("quad", 20, 333, 200, alpha=0.5)(api, ctx, rng)
+    cpu, gpu = both(B, scene, 333, 200, backdrop=backdrop)
+    assert_same(cpu, gpu)
+
+
+def test_many_small_batches(B):
+    cpu, gpu = both(B, S.mixed(200, 256, 256), 256, 256, seed=3, command_queue_limit=16)
+    assert_same(cpu, gpu, 1)
