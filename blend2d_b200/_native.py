@@ -114,6 +114,13 @@ _SIGS = {
     "b2dgpu_debug_build_edges": (_R, [_P, C.POINTER(BatchView), C.POINTER(Edge), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "b2dgpu_last_error_message": (C.c_char_p, []),
     "b2dgpu_abi_version": (C.c_uint32, []),
+    "b2dgpu_global_stats": (_R, [C.POINTER(Stats), C.c_int]),
+    "b2dgpu_global_set_profiling": (_R, [C.c_int]),
+    "b2dgpu_capture_begin": (_R, []),
+    "b2dgpu_capture_end": (_R, [C.POINTER(_P)]),
+    "b2dgpu_capture_info": (_R, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "b2dgpu_capture_replay": (_R, [_P, C.c_uint32, C.POINTER(C.c_float)]),
+    "b2dgpu_capture_destroy": (_R, [_P]),
     # b2d_host.h
     "b2d_image_create": (_R, [C.c_int32, C.c_int32, C.c_uint32, C.POINTER(_P)]),
     "b2d_image_destroy": (_R, [_P]),

@@ -20,6 +20,9 @@ extern "C" B2DGPU_API b2dgpu_result b2d_scene_replay(b2d_context* ctx, const b2d
   uint32_t end = first + count < sc->fill_count ? first + count : sc->fill_count;
   for (uint32_t i = first; i < end && !r; i++) {
     const b2d_scene_fill& f = sc->fills[i];
+    // The host mirror has no font engine and no stroker: text and strokes only exist behind the real Blend2D frontend
+    // (shim/), which feeds this same runtime.
+    if (f.geom == B2D_SCENE_GEOM_TEXT || f.stroke_width > 0.0) { r = B2DGPU_ERROR_NOT_IMPLEMENTED; break; }
     b2d_gradient* g = nullptr;
     b2d_pattern* p = nullptr;
     b2d_context_set_comp_op(ctx, f.comp_op);

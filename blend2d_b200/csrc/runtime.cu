@@ -160,6 +160,36 @@ struct b2dgpu_batch {
 static const uint32_t kRuntimeMagic = 0xB2D09B00u;
 
 // ---------------------------------------------------------------------------------------------------------------
+// Process-wide registry: an application that reaches the runtime only through Blend2D (shim/) never sees the
+// b2dgpu_runtime objects its contexts own; b2dgpu_global_* and b2dgpu_capture_* address all of them.
+// ---------------------------------------------------------------------------------------------------------------
+struct CaptureEntry { b2dgpu_runtime* rt; b2dgpu_target* target; b2dgpu_batch* batch; };
+struct b2dgpu_capture { std::vector<CaptureEntry> entries; };
+
+static std::mutex g_registry_mutex;
+static std::vector<b2dgpu_runtime*> g_runtimes;
+static std::vector<b2dgpu_target*> g_targets;
+static b2dgpu_stats g_retired_stats;                 // totals of destroyed runtimes
+static bool g_profiling_default = false;
+static b2dgpu_capture* g_capture = nullptr;          // non-null while b2dgpu_capture_begin() .. _end()
+
+template<typename T>
+static void registry_remove(std::vector<T*>& v, T* p) {
+  for (size_t i = 0; i < v.size(); i++) if (v[i] == p) { v[i] = v.back(); v.pop_back(); return; }
+}
+template<typename T>
+static bool registry_has(const std::vector<T*>& v, T* p) {
+  for (T* q : v) if (q == p) return true;
+  return false;
+}
+
+static void stats_add(b2dgpu_stats& a, const b2dgpu_stats& b) {
+  a.kernel_launches += b.kernel_launches; a.pixels_composited += b.pixels_composited; a.commands += b.commands;
+  a.edges += b.edges; a.h2d_bytes += b.h2d_bytes; a.d2h_bytes += b.d2h_bytes;
+  a.tile_kernel_ms += b.tile_kernel_ms; a.build_kernels_ms += b.build_kernels_ms; a.tile_kernel_launches += b.tile_kernel_launches;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Seam B
 // ---------------------------------------------------------------------------------------------------------------
 static void fill_func_token(void*, const void*, const void*) {
@@ -288,6 +318,11 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
       return cuda_fail(e, "b2dgpu_runtime_create: cudaStreamCreate(prep)");
     }
   }
+  {
+    std::lock_guard<std::mutex> g(g_registry_mutex);
+    g_runtimes.push_back(rt);
+    rt->profiling = g_profiling_default;
+  }
   *out = rt;
   return B2DGPU_SUCCESS;
 }
@@ -296,6 +331,19 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_runtime_destroy: invalid runtime");
   cudaSetDevice(rt->device);
   cudaStreamSynchronize(rt->stream);
+  {
+    bool registered;
+    { std::lock_guard<std::mutex> g(g_registry_mutex); registered = registry_has(g_runtimes, rt); }
+    if (registered) {
+      b2dgpu_stats last;
+      if (b2dgpu_get_stats(rt, &last, 0) == B2DGPU_SUCCESS) {
+        std::lock_guard<std::mutex> g(g_registry_mutex);
+        stats_add(g_retired_stats, last);
+      }
+      std::lock_guard<std::mutex> g(g_registry_mutex);
+      registry_remove(g_runtimes, rt);
+    }
+  }
   if (rt->prep_stream) { cudaStreamSynchronize(rt->prep_stream); cudaStreamDestroy(rt->prep_stream); }
   for (int i = 0; i < 2; i++) if (rt->slot_done[i]) cudaEventDestroy(rt->slot_done[i]);
   if (rt->prep_ready) cudaEventDestroy(rt->prep_ready);
@@ -387,6 +435,7 @@ extern "C" b2dgpu_result b2dgpu_target_create_slab(b2dgpu_runtime* rt, int32_t w
   if (e != cudaSuccess) { delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMalloc(canvas)"); }
   e = cudaMemsetAsync(t->d_pixels, 0, t->stride * t->padded_h, rt->stream);
   if (e != cudaSuccess) { cudaFree(t->d_pixels); delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMemset"); }
+  { std::lock_guard<std::mutex> g(g_registry_mutex); g_targets.push_back(t); }
   *out = t;
   return B2DGPU_SUCCESS;
 }
@@ -397,6 +446,7 @@ extern "C" b2dgpu_result b2dgpu_target_create(b2dgpu_runtime* rt, int32_t w, int
 
 extern "C" b2dgpu_result b2dgpu_target_destroy(b2dgpu_target* t) {
   if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_destroy: null");
+  { std::lock_guard<std::mutex> g(g_registry_mutex); registry_remove(g_targets, t); }
   cudaSetDevice(t->rt->device);
   cudaStreamSynchronize(t->rt->stream);
   cudaFree(t->d_pixels);
@@ -904,9 +954,28 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   return B2DGPU_SUCCESS;
 }
 
+static b2dgpu_result submit_impl(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view);
+
 extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view) {
   if (!rt || rt->magic != kRuntimeMagic || !target || target->rt != rt) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: invalid argument");
   if (!view || view->command_count == 0) return view ? B2DGPU_SUCCESS : fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: view is null");
+  b2dgpu_result r = submit_impl(rt, target, view);
+  if (r) return r;
+  // Capture (b2dgpu_capture_begin): keep a device-resident copy of the batch so it can be replayed with its inputs in HBM.
+  bool capturing;
+  { std::lock_guard<std::mutex> g(g_registry_mutex); capturing = g_capture != nullptr; }
+  if (capturing) {
+    b2dgpu_batch* copy = nullptr;
+    r = b2dgpu_batch_upload(rt, view, &copy);
+    if (r) return r;
+    std::lock_guard<std::mutex> g(g_registry_mutex);
+    if (g_capture) g_capture->entries.push_back(CaptureEntry{ rt, target, copy });
+    else b2dgpu_batch_destroy(copy);
+  }
+  return B2DGPU_SUCCESS;
+}
+
+static b2dgpu_result submit_impl(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view) {
   std::lock_guard<std::mutex> lock(rt->mutex);
   cudaSetDevice(rt->device);
 
@@ -1015,6 +1084,107 @@ extern "C" b2dgpu_result b2dgpu_batch_render_multi(b2dgpu_runtime* rt, b2dgpu_ta
 
 extern "C" b2dgpu_result b2dgpu_batch_render(b2dgpu_runtime* rt, b2dgpu_target* target, b2dgpu_batch* b) {
   return b2dgpu_batch_render_multi(rt, &target, 1, b);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Process-wide statistics / profiling switch / capture
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" b2dgpu_result b2dgpu_global_stats(b2dgpu_stats* out, int reset) {
+  if (!out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_global_stats: out is null");
+  std::vector<b2dgpu_runtime*> live;
+  b2dgpu_stats total;
+  {
+    std::lock_guard<std::mutex> g(g_registry_mutex);
+    live = g_runtimes;
+    total = g_retired_stats;
+    if (reset) memset(&g_retired_stats, 0, sizeof(g_retired_stats));
+  }
+  for (b2dgpu_runtime* rt : live) {
+    b2dgpu_stats st;
+    b2dgpu_result r = b2dgpu_get_stats(rt, &st, reset);
+    if (r) return r;
+    stats_add(total, st);
+  }
+  *out = total;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_global_set_profiling(int enabled) {
+  std::vector<b2dgpu_runtime*> live;
+  { std::lock_guard<std::mutex> g(g_registry_mutex); g_profiling_default = enabled != 0; live = g_runtimes; }
+  for (b2dgpu_runtime* rt : live) b2dgpu_set_profiling(rt, enabled);
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_capture_begin(void) {
+  std::lock_guard<std::mutex> g(g_registry_mutex);
+  if (g_capture) return fail(B2DGPU_ERROR_INVALID_STATE, "b2dgpu_capture_begin: a capture is already open");
+  g_capture = new (std::nothrow) b2dgpu_capture();
+  return g_capture ? B2DGPU_SUCCESS : fail(B2DGPU_ERROR_OUT_OF_MEMORY, "b2dgpu_capture_begin: out of host memory");
+}
+
+extern "C" b2dgpu_result b2dgpu_capture_end(b2dgpu_capture** out) {
+  std::lock_guard<std::mutex> g(g_registry_mutex);
+  if (!g_capture || !out) return fail(B2DGPU_ERROR_INVALID_STATE, "b2dgpu_capture_end: no capture is open");
+  *out = g_capture;
+  g_capture = nullptr;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_capture_info(const b2dgpu_capture* c, uint32_t* batches, uint64_t* commands) {
+  if (!c) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_capture_info: null");
+  uint64_t n = 0;
+  for (const CaptureEntry& e : c->entries) n += e.batch->command_count;
+  if (batches) *batches = uint32_t(c->entries.size());
+  if (commands) *commands = n;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_capture_replay(b2dgpu_capture* c, uint32_t times, float* ms_out) {
+  if (!c) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_capture_replay: null");
+  if (ms_out) *ms_out = 0.f;
+  if (c->entries.empty() || !times) return B2DGPU_SUCCESS;
+  {
+    std::lock_guard<std::mutex> g(g_registry_mutex);
+    for (const CaptureEntry& e : c->entries)
+      if (!registry_has(g_runtimes, e.rt) || !registry_has(g_targets, e.target))
+        return fail(B2DGPU_ERROR_INVALID_STATE, "b2dgpu_capture_replay: the context that was captured has been destroyed");
+  }
+  b2dgpu_runtime* rt0 = c->entries[0].rt;
+  cudaSetDevice(rt0->device);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CU_TRY(cudaEventCreate(&e0));
+  if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return fail(B2DGPU_ERROR_UNKNOWN, "cudaEventCreate"); }
+  cudaEventRecord(e0, rt0->stream);
+  b2dgpu_result r = B2DGPU_SUCCESS;
+  for (uint32_t t = 0; t < times && !r; t++)
+    for (const CaptureEntry& e : c->entries) {
+      r = b2dgpu_batch_render(e.rt, e.target, e.batch);
+      if (r) break;
+    }
+  cudaEventRecord(e1, rt0->stream);
+  for (const CaptureEntry& e : c->entries) cudaStreamSynchronize(e.rt->stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (ms_out) *ms_out = ms;
+  return r;
+}
+
+extern "C" b2dgpu_result b2dgpu_capture_destroy(b2dgpu_capture* c) {
+  if (!c) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_capture_destroy: null");
+  {
+    std::lock_guard<std::mutex> g(g_registry_mutex);
+    if (g_capture == c) g_capture = nullptr;
+  }
+  for (const CaptureEntry& e : c->entries) {
+    bool live;
+    { std::lock_guard<std::mutex> g(g_registry_mutex); live = registry_has(g_runtimes, e.rt); }
+    if (live) b2dgpu_batch_destroy(e.batch);
+    else { e.batch->block.release(); e.batch->edges.release(); delete e.batch; }
+  }
+  delete c;
+  return B2DGPU_SUCCESS;
 }
 
 extern "C" b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_edge* edges_out,

@@ -12,12 +12,14 @@ Two partitions, both taken from the reference's own threading model (SURVEY.md s
 """
 import ctypes as C
 
-TILE_ROWS = 32         # kTileH in csrc/dev_common.cuh: slabs are cut on tile boundaries so no tile is shared by two ranks
+TILE_ROWS = 32         # the largest tile height the compositor picks (csrc/kernels.cu choose_tile_height): slabs are
+                       # cut on multiples of it so no tile is shared by two ranks whatever height a launch chooses
 
 
 def slab_table(height, world, align=TILE_ROWS):
     """[(y0, y1)] per rank: contiguous, disjoint, covering [0, height), every boundary a multiple of `align`.
-    Ranks that would get nothing (more ranks than row groups) receive an empty slab (y0 == y1)."""
+    Ranks that would get nothing (more ranks than row groups) receive an empty slab (y0 == y1): such a rank creates no
+    target (b2dgpu_target_create_slab rejects y0 >= y1) and contributes nothing to the gather - see `StripeGather`."""
     if height <= 0 or world <= 0:
         raise ValueError("height and world must be positive")
     groups = (height + align - 1) // align
@@ -67,6 +69,93 @@ def gather_stripes(local_stripes, height, stripes_per_rank, dst=0, group=None):
     for j, (a, b) in enumerate(table):
         parts.append(recv[j % world][j // world, : b - a])
     return torch.cat(parts, dim=0)
+
+
+class StripeGather:
+    """The one exchange of a band-sharded frame: every stripe goes STRAIGHT into its rows of the final image on rank
+    `dst` - no padded staging buffer, no concatenation - and stripe by stripe, so the transfer of stripe i overlaps the
+    render of stripe i + 1:
+
+        g = StripeGather(height, stripes_per_rank, rank, world, device)
+        g.begin()
+        for i, stripe in enumerate(my_stripes):      # canvas order
+            render(stripe)                           # enqueued on `stream`
+            g.stripe_ready(i, rows_of(stripe), stream)
+        image = g.finish(stream)                     # [height, row_bytes] on dst, None elsewhere
+
+    Point-to-point NCCL send/recv (gloo on CPU): the owner of stripe j = rank j mod world sends it, `dst` receives into
+    image[y0:y1].  `dst` posts the receives of round i (one stripe from every peer) as one group when its own stripe i
+    is ready, so the peers' transfers run concurrently over NVSwitch.  Empty stripes (more stripes than tile rows) are
+    skipped on both sides."""
+
+    def __init__(self, height, stripes_per_rank, rank, world, device=None, dst=0, group=None):
+        self.height, self.k, self.rank, self.world, self.dst, self.group, self.device = height, stripes_per_rank, rank, world, dst, group, device
+        self.table = stripe_table(height, world, stripes_per_rank)
+        self.full = None
+        self.works = []
+        self._copy_stream = None
+
+    def _rows(self, r, i):
+        return self.table[r + i * self.world]
+
+    def begin(self):
+        self.works = []
+
+    def stripe_ready(self, i, tensor, stream=None):
+        import contextlib
+        import torch
+        import torch.distributed as dist
+        y0, y1 = self._rows(self.rank, i)
+        cuda = tensor.is_cuda
+        ctx = torch.cuda.stream(stream) if (cuda and stream is not None) else contextlib.nullcontext()
+        with ctx:
+            if self.rank != self.dst:
+                if y1 > y0:
+                    t = tensor[: y1 - y0]
+                    if not t.is_contiguous():
+                        t = t.contiguous()                  # padded row stride: one staging copy
+                    self.works.append((dist.isend(t, self.dst, group=self.group), t))
+                return
+            if self.full is None:
+                self.full = torch.empty((self.height, tensor.shape[1]), dtype=tensor.dtype, device=tensor.device)
+            ops = []
+            for r in range(self.world):
+                if r == self.dst:
+                    continue
+                a, b = self._rows(r, i)
+                if b > a:
+                    ops.append(dist.P2POp(dist.irecv, self.full[a:b], r, group=self.group))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    self.works.append((w, None))
+            if y1 > y0:
+                if cuda:
+                    if self._copy_stream is None:
+                        self._copy_stream = torch.cuda.Stream(device=tensor.device)
+                    self._copy_stream.wait_stream(stream if stream is not None else torch.cuda.current_stream())
+                    with torch.cuda.stream(self._copy_stream):
+                        self.full[y0:y1].copy_(tensor[: y1 - y0], non_blocking=True)
+                else:
+                    self.full[y0:y1].copy_(tensor[: y1 - y0])
+
+    def finish(self, stream=None):
+        import contextlib
+        import torch
+        cuda = self.device is not None and torch.device(self.device).type == "cuda"
+        ctx = torch.cuda.stream(stream) if (cuda and stream is not None) else contextlib.nullcontext()
+        with ctx:
+            for w, _keep in self.works:
+                w.wait()
+            if cuda and self._copy_stream is not None:
+                (stream if stream is not None else torch.cuda.current_stream()).wait_stream(self._copy_stream)
+        self.works = []
+        return self.full if self.rank == self.dst else None
+
+    def run(self, local_stripes, stream=None):
+        self.begin()
+        for i, t in enumerate(local_stripes):
+            self.stripe_ready(i, t, stream)
+        return self.finish(stream)
 
 
 def frames_of(rank, world, frame_count):

@@ -367,6 +367,25 @@ B2DGPU_API b2dgpu_result b2dgpu_get_stats(b2dgpu_runtime* rt, b2dgpu_stats* out,
 /* Enables (1) / disables (0) per-kernel CUDA-event timing; adds two event records per phase and render. */
 B2DGPU_API b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Process-wide access.  A Blend2D application that selects this runtime through BLContextCreateInfo (shim/)
+ * never holds a b2dgpu_runtime*: its contexts own them.  These entry points address every runtime of the process.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* Sum of b2dgpu_get_stats() over all runtimes created so far (destroyed ones included). */
+B2DGPU_API b2dgpu_result b2dgpu_global_stats(b2dgpu_stats* out, int reset);
+/* b2dgpu_set_profiling() for every live runtime and for the ones created later. */
+B2DGPU_API b2dgpu_result b2dgpu_global_set_profiling(int enabled);
+/* Capture: between begin and end every b2dgpu_submit() of the process also keeps a device-resident copy of its batch
+ * (b2dgpu_batch_upload).  b2dgpu_capture_replay() renders the captured batches again, `times` times, into the targets
+ * they were submitted to - inputs already in HBM, nothing crosses PCIe - and returns the device time of the replay
+ * (CUDA events on the runtime's stream; synchronous).  The contexts that were captured must still be alive. */
+typedef struct b2dgpu_capture b2dgpu_capture;
+B2DGPU_API b2dgpu_result b2dgpu_capture_begin(void);
+B2DGPU_API b2dgpu_result b2dgpu_capture_end(b2dgpu_capture** out);
+B2DGPU_API b2dgpu_result b2dgpu_capture_info(const b2dgpu_capture* c, uint32_t* batches, uint64_t* commands);
+B2DGPU_API b2dgpu_result b2dgpu_capture_replay(b2dgpu_capture* c, uint32_t times, float* ms_out);
+B2DGPU_API b2dgpu_result b2dgpu_capture_destroy(b2dgpu_capture* c);
+
 /* Debug/KAT access used by the parity tests: runs only the edge builder and returns the flattened edges. */
 B2DGPU_API b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dgpu_batch_view* batch,
                                                   b2dgpu_edge* edges_out, uint32_t capacity, uint32_t* count_out,

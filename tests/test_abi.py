@@ -67,7 +67,7 @@ int main(void) {
     got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
     # FetchData 176 (Pattern.simple @32, Gradient.linear @16), RenderCommand-sized command 64, EdgePoint pair 16,
     # DispatchData 16 - SURVEY.md section 8 "ABI sizes [probe, x86-64]"
-    assert got == [176, 64, 16, 12, 96, 16, 32, 16, 152]
+    assert got == [176, 64, 16, 12, 96, 16, 32, 16, 160]
 
 
 def test_signature_queries_work_without_a_device():

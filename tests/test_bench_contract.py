@@ -16,7 +16,7 @@ def run_bench(*args):
 
 
 def test_reference_arm_json_line(ref):
-    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--fills", "300", "--cpu-sample", "60", "--width", "640", "--height", "360")
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", "--fills", "300", "--width", "640", "--height", "360")
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -27,7 +27,7 @@ def test_reference_arm_json_line(ref):
     assert d["impl"] == "reference" and d["metric"] == "Mpix/s" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["fills_per_step"] == 300      # the whole step, not a sample
 
 
 def test_scene_generator_is_deterministic():

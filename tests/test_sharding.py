@@ -68,6 +68,19 @@ def worker(rank, world, port, out_dir):
         striped = SH.gather_stripes(mine, H, 2, dst=0)
         if rank == 0:
             assert np.array_equal(striped.numpy().view(np.uint32), full_img)
+        # the same exchange stripe by stripe, straight into the final image rows (what bench.py's band-sharded leg uses);
+        # 3 stripes per rank on 90 rows = more stripes than tile rows: the empty ones are skipped on both sides
+        for k in (2, 3):
+            mine_k = [torch.from_numpy(full_img[a:b].copy().view(np.uint8)) for a, b in SH.stripes_of(rank, world, k, H)]
+            g = SH.StripeGather(H, k, rank, world)
+            g.begin()
+            for i, t in enumerate(mine_k):
+                g.stripe_ready(i, t)
+            direct = g.finish()
+            if rank == 0:
+                assert np.array_equal(direct.numpy().view(np.uint32), full_img)
+            else:
+                assert direct is None
         # frame sharding: independent frames, only a checksum of checksums is reduced for the report
         sums = torch.zeros(6, dtype=torch.int64)
         for i in SH.frames_of(rank, world, 6):
