@@ -300,6 +300,8 @@ class GpuBench:
         self.barrier()
         self.stats(reset=True)
         N.check(lib.b2dgpu_global_set_profiling(1), "set_profiling")
+        # pixels_per_step was measured by the capture pass; the statistic is not maintained inside the timed steps
+        N.check(lib.b2dgpu_global_set_pixel_counting(0), "set_pixel_counting")
         step_ms = []
         for _ in range(steps):
             cap_sess.clear()
@@ -310,6 +312,7 @@ class GpuBench:
         self.barrier()
         st = self.stats(reset=True)
         N.check(lib.b2dgpu_global_set_profiling(0), "set_profiling")
+        N.check(lib.b2dgpu_global_set_pixel_counting(1), "set_pixel_counting")
         # the clears between the steps are single solid fills (k_stream_solid): they add launches and pixels that are
         # not part of the step, so both are taken from the capture pass, which held exactly one step
         total_ms = float(sum(step_ms))
@@ -361,11 +364,13 @@ def tile_kernel_ms_per_step(gb, scene, n_fills, W, H, steps):
     N.check(lib.b2dgpu_capture_replay(cap, 2, C.byref(ms)), "capture_replay")
     gb.stats(reset=True)
     N.check(lib.b2dgpu_global_set_profiling(1), "set_profiling")
+    N.check(lib.b2dgpu_global_set_pixel_counting(0), "set_pixel_counting")
     for _ in range(steps):
         gb.flush_l2()
         N.check(lib.b2dgpu_capture_replay(cap, 1, C.byref(ms)), "capture_replay")
     st = gb.stats(reset=True)
     N.check(lib.b2dgpu_global_set_profiling(0), "set_profiling")
+    N.check(lib.b2dgpu_global_set_pixel_counting(1), "set_pixel_counting")
     N.check(lib.b2dgpu_capture_destroy(cap), "capture_destroy")
     sess.close()
     n = max(1, int(st["tile_kernel_launches"]))

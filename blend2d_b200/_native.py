@@ -116,6 +116,8 @@ _SIGS = {
     "b2dgpu_abi_version": (C.c_uint32, []),
     "b2dgpu_global_stats": (_R, [C.POINTER(Stats), C.c_int]),
     "b2dgpu_global_set_profiling": (_R, [C.c_int]),
+    "b2dgpu_set_pixel_counting": (_R, [_P, C.c_int]),
+    "b2dgpu_global_set_pixel_counting": (_R, [C.c_int]),
     "b2dgpu_capture_begin": (_R, []),
     "b2dgpu_capture_end": (_R, [C.POINTER(_P)]),
     "b2dgpu_capture_info": (_R, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),

@@ -5,13 +5,17 @@
 //                                    give every command a contiguous, deterministic edge range.
 //   K1b k_scan_*                     exclusive prefix sum of the per-segment edge counts.
 //   K1c k_analytic_bbox / k_finalize_commands   per-command pixel bounding boxes used for tile culling.
-//   K2+K3 k_tile_render<BPP>         one CTA per 128x8 destination tile.  The tile's pixels are loaded ONCE into
-//                                    registers (16-byte vector loads, one warp per row), every command whose bounding
-//                                    box touches the tile is replayed in submission order - coverage accumulation into
-//                                    shared-memory cells with atomics, warp-shuffle prefix scan, mask, fetch, composite -
-//                                    and the tile is stored ONCE.  This is the GPU form of the reference's per-band
-//                                    command replay (blend2d/raster/workerproc.cpp:166-299) fused with its FillBoxA /
-//                                    FillMask / FillAnalytic pipelines (pipeline/reference/fillgeneric_p.h:22-388).
+//   K1d k_band_extents               per (tile row, command) column extents of the command's edges (tile culling).
+//   K2+K3 k_tile_render<BPP,TH>      one CTA of TH warps per 128 x TH destination tile, a warp per block of 32 columns x
+//                                    4 rows.  The tile's pixels are loaded ONCE into registers (16-byte vector loads),
+//                                    every command that touches the tile is replayed in submission order - phase 1: a
+//                                    warp per command classifies its edges against the tile and rasterizes the (edge,
+//                                    row) crossings into per-row entry lists in shared memory; phase 2: every warp builds
+//                                    the masks of its block from the backdrop and the entries, fetches, composites - and
+//                                    the tile is stored ONCE.  This is the GPU form of the reference's per-band command
+//                                    replay (blend2d/raster/workerproc.cpp:166-299) fused with its FillBoxA / FillMask /
+//                                    FillAnalytic pipelines (pipeline/reference/fillgeneric_p.h:22-388).
+//   K3s k_box_stream / k_stream_solid  persistent streaming compositors for batches of a few large box fills.
 //
 // No tensor cores: nothing on this path is a dense contraction.  Compile with -fmad=false (see dev_flatten.cuh).
 #include "kernels.h"
@@ -297,18 +301,29 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
 
 // =================================================================================================================
 // K2 + K3 - tile compositor
+//
+// One CTA of TH warps per 128 x TH destination tile.  A WARP owns a block of 32 columns x 4 rows of the tile (8 lanes
+// per row, 4 consecutive pixels = one 16-byte vector per lane): warp w -> row group w / 4 (rows 4g .. 4g + 3), column
+// block w % 4.  The block's pixels are loaded ONCE into registers, every command that touches the tile is replayed in
+// submission order and the block is stored ONCE.  Blocks are what the work is decided on: phase 1 leaves, per command,
+// one bit per warp ("this block can receive coverage"), the backdrop of every row at the start of each block, and one
+// bit per (row, block) that says whether an edge crosses it - so a warp whose block lies outside a shape skips the
+// command in a handful of instructions, a warp whose block lies inside takes the constant-mask path, and only the warps
+// that really contain a crossing walk the row's entry list (the reference's FillAnalytic does the same with its bit
+// vector of 4-pixel groups and its CMask / VMask spans, fillgeneric_p.h:174-388).
 // =================================================================================================================
 
 // Shared-memory cell row used by the slow path (u32 wrap-around adds: order independent).
 struct SmemRowStore {
-  uint32_t* cells;      // kTileW cells of ONE row (warp private)
+  uint32_t* cells;      // kTileW cells of ONE row (warp private while it is being rasterized)
   uint32_t* carry;      // that row's backdrop accumulator
   __device__ __forceinline__ void add_cell(int, int rel, uint32_t v) { atomicAdd(cells + rel, v); }
   __device__ __forceinline__ void add_carry(int, uint32_t v) { atomicAdd(carry, v); }
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kEntCap = 4, kRing = 2048, kLanePx = kTileW / 32 };
+enum : int { kEntCap = 4, kRing = 2048, kBlockW = 32, kBlocks = kTileW / kBlockW, kBlockRows = 4 };
+static_assert(kBlocks == 4, "a warp is addressed as (row group, one of four column blocks)");
 // Per tile height TH (= warps per CTA): commands per phase-1 round, chained-entry pool size.
 template<int TH> struct TileCfg { enum : int { kThreads = 32 * TH, kSub = TH == 32 ? 64 : 3 * TH, kPool = 128 * TH }; };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u, kPreClipRight = 4u };   // ClipRight: the clipped box ends inside the tile
@@ -317,16 +332,17 @@ enum : uint32_t { kDenseItemsPerRow = 8u };        // (edge, row) crossings per 
 template<int TH>
 struct PreCmdT {
   uint32_t carry_left[TH];      // backdrop per tile row from the edges entirely left of the tile
-  uint32_t carry_st[TH];        // backdrop per tile row from straddling edges (their cells left of the tile)
+  uint4 carry4[TH];             // .x: backdrop from straddling edges' cells left of the tile; .y/.z/.w: what the entries
+                                // that lie entirely left of block 1 / 2 / 3 add to the backdrop from that block on
   uint32_t nent[TH];            // number of cell entries appended per row (beyond kEntCap: chained in the pool)
   uint32_t ovf_head[TH];        // 1 + pool index of the row's last chained entry, 0 = none
+  uint32_t blk_has[(TH + 7) / 8]; // 4 bits per row: block b of the row holds an entry (or the spill of its left neighbour)
   uint32_t flags;
-  uint32_t active;                  // 0: the command leaves this tile untouched (skipped by the replay)
-  uint2 ent[TH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
-  // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B) and the right end of
-  // its clipped box.  (Staging the 176-byte FetchData as well was measured slower than reading it through L1.)
+  uint32_t warp_mask;           // bit w: warp w's block can receive coverage from this command (0: skipped by the replay)
   int bx1;
-  uint32_t pad_[5];
+  uint32_t pad_[(4 - ((TH + 7) / 8 + 3) % 4) % 4];
+  uint2 ent[TH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
+  // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B).
   uint32_t cmd_words[sizeof(b2dgpu_command) / 4];
 };
 static_assert(sizeof(PreCmdT<8>) % 16 == 0 && sizeof(PreCmdT<16>) % 16 == 0 && sizeof(PreCmdT<32>) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
@@ -356,8 +372,18 @@ struct EntrySink {
         pool[pi] = en;
         pool_link[pi] = uint16_t(prev);
       }
-      else atomicOr(&pre->flags, kPreOverflow);         // pool exhausted: the row re-rasterizes itself (slow_row_cells)
+      else atomicOr(&pre->flags, kPreOverflow);         // pool exhausted: the row re-rasterizes itself (slow path)
     }
+    // Block bookkeeping.  The entry changes the coverage from pixel `rel` on (v0) and from pixel rel + 1 on (area): the
+    // block that holds `rel` - and the next one when rel is a block's last pixel - applies it pixel by pixel, every
+    // block further right just sees v0 + area = cover << 9 more backdrop.
+    const int bi = rel >> 5;
+    const bool spill = (rel & 31) == 31;
+    uint32_t bits = 1u << bi;
+    if (spill && bi < kBlocks - 1) bits |= 2u << bi;
+    atomicOr(&pre->blk_has[row >> 3], bits << ((row & 7) * 4));
+    const int first_full = bi + 1 + int(spill);
+    if (first_full < kBlocks) atomicAdd(reinterpret_cast<uint32_t*>(&pre->carry4[row]) + first_full, v0 + area);
   }
   __device__ __forceinline__ void merge(int x, uint32_t cover, uint32_t area) {
     const uint32_t v0 = (cover << 9) - area;
@@ -366,39 +392,48 @@ struct EntrySink {
     if (rel >= 0) append(rel, v0, area);
     else {
       // cell x is left of the tile: it only feeds the row's backdrop; cell x + 1 may be the tile's first column
-      if (rel == -1) { if (v0) atomicAdd(&pre->carry_st[row], v0); if (area) append(0, area, 0u); }
-      else atomicAdd(&pre->carry_st[row], v0 + area);
+      if (rel == -1) { if (v0) atomicAdd(&pre->carry4[row].x, v0); if (area) append(0, area, 0u); }
+      else atomicAdd(&pre->carry4[row].x, v0 + area);
     }
   }
 };
 
-// Masks of a lane's eight pixels for a FillBoxMaskA command (image masks are not in the bench's configurations: cold).
-struct Mask8 { uint4 lo, hi; };
-__device__ __noinline__ Mask8 box_mask_a_row(const b2dgpu_command& cmd, const b2dgpu_pattern_source& ms, int x_lo, int x_hi, int y) {
-  Mask8 m;
-  m.lo = make_uint4(box_mask_a(cmd, ms, x_lo, y), box_mask_a(cmd, ms, x_lo + 1, y), box_mask_a(cmd, ms, x_lo + 2, y), box_mask_a(cmd, ms, x_lo + 3, y));
-  m.hi = make_uint4(box_mask_a(cmd, ms, x_hi, y), box_mask_a(cmd, ms, x_hi + 1, y), box_mask_a(cmd, ms, x_hi + 2, y), box_mask_a(cmd, ms, x_hi + 3, y));
-  return m;
+// Masks of a lane's four pixels for a FillBoxMaskA command (image masks are not in the bench's configurations: cold).
+__device__ __noinline__ uint4 box_mask_a_row(const b2dgpu_command& cmd, const b2dgpu_pattern_source& ms, int x, int y) {
+  return make_uint4(box_mask_a(cmd, ms, x, y), box_mask_a(cmd, ms, x + 1, y), box_mask_a(cmd, ms, x + 2, y), box_mask_a(cmd, ms, x + 3, y));
 }
 
-// Slow path of the replay (a row with more cells than an entry list holds, e.g. a nearly horizontal edge): the warp
-// rasterizes its own row into its private shared-memory cell row.  Out of line: it is rare and large.
-__device__ __noinline__ void slow_row_cells(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int py, int row,
-                                            int lane, uint32_t* cells_row, uint32_t* carry_row, int tile_h) {
-  #pragma unroll
-  for (int i = 0; i < kLanePx / 4; i++)
-    *reinterpret_cast<uint4*>(cells_row + lane * kLanePx + i * 4) = make_uint4(0, 0, 0, 0);
+// Slow path of the replay (a command with more crossings in this tile than the entry lists hold: dense polygons,
+// nearly horizontal edges).  Called by the four warps of a row group together: warp `b` rasterizes row 4g + b of the
+// tile into that row's shared-memory cells and turns them, in place, into the running coverage of the reference's
+// scanline walk (fillgeneric_p.h:285-297); after the group's barrier every warp reads its own block of all four rows.
+// Out of line: it is rare and large.
+__device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int row, int lane,
+                                             uint32_t* cells_row, uint32_t* carry_row, uint32_t base, int tile_h, int group) {
+  *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(0, 0, 0, 0);
   if (lane == 0) *carry_row = 0;
   __syncwarp();
   SmemRowStore store{ cells_row, carry_row };
   TileSink<SmemRowStore> sink(store, tx0);
   sink.row = row;
+  const int py = ty0 + row;
   for (uint32_t e = lane; e < er.y; e += 32) {
     NormEdge ne = load_edge(edges, er.x + e);
     if (tile_edge_class(ne, tx0, ty0, tile_h) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
       tile_rasterize_edge_row(ne, py, sink);
   }
   __syncwarp();
+  uint4 c = *reinterpret_cast<uint4*>(cells_row + lane * 4);
+  c.y += c.x; c.z += c.y; c.w += c.z;
+  uint32_t inc = c.w;
+  #pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const uint32_t add = base + *carry_row + (inc - c.w);
+  *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(c.x + add, c.y + add, c.z + add, c.w + add);
+  asm volatile("bar.sync %0, 128;" :: "r"(group + 1) : "memory");
 }
 
 template<int BPP, int TH>
@@ -412,55 +447,47 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   PreCmd* const s_pre = reinterpret_cast<PreCmd*>(s_dynamic);
   uint2* const s_pool = reinterpret_cast<uint2*>(s_dynamic + sizeof(PreCmd) * kSub);      // kPool chained entries
   uint16_t* const s_pool_link = reinterpret_cast<uint16_t*>(s_pool + kPool);
+  __shared__ uint32_t s_wmask[kSub];                               // copy of PreCmd::warp_mask, densely packed
   __shared__ uint32_t s_wcount[TH];
   __shared__ uint32_t s_next;
   __shared__ uint32_t s_pool_next;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const int row = tid >> 5;
+  const int warp = tid >> 5;
   const int tile_x = blockIdx.x % P.tiles_x;
   const int tile_y = blockIdx.x / P.tiles_x;
   const int tx0 = tile_x * kTileW;
   const int ty0 = P.y_begin + tile_y * TH;          // absolute y of the tile's first row
-  // A lane owns two groups of 4 consecutive pixels: `lo` in the left half of the row (px .. px + 3) and `hi` in the
-  // right half (px + kTileW/2 ..).  Each half is one perfectly coalesced 512-byte run per warp, and a half without
-  // coverage is skipped as a whole.
-  const int px = tx0 + lane * 4;
-  constexpr bool kTwoHalves = kTileW == 256;              // 8 pixels per lane; kTileW == 128: 4 pixels, no `hi` group
-  constexpr int kHalf = kTwoHalves ? kTileW / 2 : 0;
+  // Replay geometry of this lane: block (grp, blk) of the tile, row `row` of the tile, pixels px .. px + 3.
+  const int grp = warp >> 2, blk = warp & 3;
+  const int row = grp * kBlockRows + (lane >> 3);
+  const int bx0 = tx0 + blk * kBlockW;              // first column of the warp's block
+  const int px = bx0 + (lane & 7) * 4;
   const int py = ty0 + row;
   const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
 
-  // Load the destination once: kLanePx (8) consecutive pixels per lane, kept in registers for the whole command list.
-  // `lo` = pixels 0..3, `hi` = pixels 4..7.
+  // Load the destination once: 4 consecutive pixels per lane, kept in registers for the whole command list.
   uint8_t* dst_row = P.dst + size_t(py - P.y_begin) * P.dst_stride;
-  uint32_t d_lo[4], d_hi[4];
+  uint32_t d[4];
   if (BPP == 4) {
     uint4 v0 = *reinterpret_cast<const uint4*>(dst_row + size_t(px) * 4);
-    uint4 v1 = make_uint4(0, 0, 0, 0);
-    if (kTwoHalves) v1 = *reinterpret_cast<const uint4*>(dst_row + size_t(px + kHalf) * 4);
-    d_lo[0] = v0.x; d_lo[1] = v0.y; d_lo[2] = v0.z; d_lo[3] = v0.w;
-    d_hi[0] = v1.x; d_hi[1] = v1.y; d_hi[2] = v1.z; d_hi[3] = v1.w;
+    d[0] = v0.x; d[1] = v0.y; d[2] = v0.z; d[3] = v0.w;
   }
   else {
-    uint2 v;
-    v.x = *reinterpret_cast<const uint32_t*>(dst_row + px);
-    v.y = kTwoHalves ? *reinterpret_cast<const uint32_t*>(dst_row + px + kHalf) : 0u;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(dst_row + px);
     #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      d_lo[i] = ((v.x >> (8 * i)) & 0xFFu) * 0x01010101u;
-      d_hi[i] = ((v.y >> (8 * i)) & 0xFFu) * 0x01010101u;
-    }
+    for (int i = 0; i < 4; i++) d[i] = ((v >> (8 * i)) & 0xFFu) * 0x01010101u;
   }
   bool dirty = false;
   uint32_t px_written = 0;
+  const bool count_pixels = P.pixel_counter != nullptr;
 
   // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
   // pending (or the command list ends) they are classified (phase 1) and replayed (phase 2).
   uint32_t ring_head = 0, ring_tail = 0;                // block-uniform
   for (uint32_t base = 0; base < P.command_count || ring_head != ring_tail; base += kThreads) {
-    // ---- cull: which of the next 256 commands touch this tile? (order preserving compaction) ----
+    // ---- cull: which of the next kThreads commands touch this tile? (order preserving compaction) ----
     if (base < P.command_count) {
       uint32_t c = base + tid;
       bool hit = false;
@@ -474,13 +501,13 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       }
       uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
       __syncthreads();                                  // everybody is done reading s_wcount of the previous chunk
-      if (lane == 0) s_wcount[row] = __popc(ballot);
+      if (lane == 0) s_wcount[warp] = __popc(ballot);
       __syncthreads();
       uint32_t wbase = 0, total = 0;
       #pragma unroll
       for (int w = 0; w < TH; w++) {
         uint32_t cnt = s_wcount[w];
-        if (w < row) wbase += cnt;
+        if (w < warp) wbase += cnt;
         total += cnt;
       }
       if (hit) s_list[(ring_tail + wbase + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1)] = c;
@@ -497,11 +524,13 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
-      for (uint32_t k = row; k < sub_n; ) {
+      for (uint32_t k = warp; k < sub_n; ) {
         const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
         PreCmd* pre = &s_pre[k];
-        if (lane < TH) { pre->carry_st[lane] = 0; pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
-        if (lane == 0) { const int bx1 = P.cmd_bbox_px[ci].z; pre->bx1 = bx1; pre->flags = bx1 < tx0 + kTileW ? kPreClipRight : 0u; }
+        if (lane < TH) { pre->carry4[lane] = make_uint4(0, 0, 0, 0); pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
+        if (lane < (TH + 7) / 8) pre->blk_has[lane] = 0;
+        const int4 bbp = P.cmd_bbox_px[ci];
+        if (lane == 0) { pre->bx1 = bbp.z; pre->flags = bbp.z < tx0 + kTileW ? kPreClipRight : 0u; }
         {
           // stage the command (one coalesced 64-byte load)
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.commands + ci);
@@ -556,7 +585,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             const uint32_t chunk_items = __shfl_sync(0xFFFFFFFFu, inc, 31);
             items += chunk_items;
             // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
-            // row of the replay rasterizes itself (slow_row_cells).
+            // row of the replay is rasterized as a whole (slow_group_rows).
             if (items > kDenseItemsPerRow * uint32_t(TH)) continue;
             for (uint32_t base_i = 0; base_i < chunk_items; base_i += 32) {
               const uint32_t i = base_i + lane;
@@ -578,11 +607,31 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             }
           }
         }
-        const bool any_left = __any_sync(0xFFFFFFFFu, left_acc != 0u);
         if (lane < TH) pre->carry_left[lane] = left_acc;
-        if (lane == 0) {
-          if (nstr) atomicOr(&pre->flags, items > kDenseItemsPerRow * uint32_t(TH) ? (kPreStraddle | kPreOverflow) : kPreStraddle);
-          pre->active = (is_box || nstr || any_left) ? 1u : 0u;
+        const bool dense = nstr && items > kDenseItemsPerRow * uint32_t(TH);
+        if (lane == 0 && nstr) atomicOr(&pre->flags, dense ? (kPreStraddle | kPreOverflow) : kPreStraddle);
+        __syncwarp();
+
+        // Which warps of the replay does this command concern?  Lane w answers for warp w = block (w / 4, w % 4).
+        {
+          bool any = false;
+          if (lane < TH) {
+            const int g = lane >> 2, b = lane & 3;
+            const int r0 = g * kBlockRows;
+            const bool rows_in = bbp.y < ty0 + r0 + kBlockRows && bbp.w > ty0 + r0;
+            if (is_box) any = rows_in && bbp.x < tx0 + (b + 1) * kBlockW && bbp.z > tx0 + b * kBlockW;
+            else if (pre->flags & kPreOverflow) any = rows_in;          // the four warps of a group meet at a barrier: same answer for all
+            else if (rows_in && bbp.z > tx0 + b * kBlockW) {
+              #pragma unroll
+              for (int r = r0; r < r0 + kBlockRows; r++) {
+                const uint4 c4 = pre->carry4[r];
+                const uint32_t carry = pre->carry_left[r] + c4.x + (b >= 1 ? c4.y : 0u) + (b >= 2 ? c4.z : 0u) + (b >= 3 ? c4.w : 0u);
+                any = any || carry != 0u || ((pre->blk_has[r >> 3] >> ((r & 7) * 4 + b)) & 1u);
+              }
+            }
+          }
+          const uint32_t wm = __ballot_sync(0xFFFFFFFFu, any);
+          if (lane == 0) { pre->warp_mask = wm; s_wmask[k] = wm; }
         }
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
         uint32_t nk = 0;
@@ -591,11 +640,11 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       }
       __syncthreads();
 
-      // ---- phase 2 (K3): every warp replays the commands in order for ITS row; warps never wait for each other ----
-      // Commands that leave the tile untouched (bounding box hit only) are compacted away first.
+      // ---- phase 2 (K3): every warp replays, in order, the commands that concern ITS block; warps never wait for each
+      //      other (except the four warps of a row group inside the slow path) ----
       #pragma unroll 1
       for (uint32_t kb = 0; kb < sub_n; kb += 32) {
-      uint32_t act = __ballot_sync(0xFFFFFFFFu, kb + uint32_t(lane) < sub_n && s_pre[kb + lane].active != 0);
+      uint32_t act = __ballot_sync(0xFFFFFFFFu, kb + uint32_t(lane) < sub_n && ((s_wmask[min(kb + uint32_t(lane), uint32_t(kSub - 1))] >> warp) & 1u));
       while (act) {
         const uint32_t k = kb + uint32_t(__ffs(act) - 1);
         act &= act - 1;
@@ -603,112 +652,90 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         const b2dgpu_command& cmd = *reinterpret_cast<const b2dgpu_command*>(pre.cmd_words);
         const uint32_t type = cmd.type;
         const uint32_t alpha = cmd.alpha;
-        uint32_t m_lo[4] = { 0, 0, 0, 0 }, m_hi[4] = { 0, 0, 0, 0 };
+        uint32_t m[4] = { 0, 0, 0, 0 };
 
         if (type == B2DGPU_CMD_FILL_BOX_A) {
           // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
           if (py >= cmd.box[1] && py < cmd.box[3]) {
             #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              m_lo[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
-              m_hi[i] = (px + kHalf + i >= cmd.box[0] && px + kHalf + i < cmd.box[2]) ? alpha : 0u;
-            }
+            for (int i = 0; i < 4; i++) m[i] = (px + i >= cmd.box[0] && px + i < cmd.box[2]) ? alpha : 0u;
           }
         }
         else if (type == B2DGPU_CMD_FILL_BOX_U) {
           BoxUParams bu = box_u_setup(cmd.box, alpha);
           #pragma unroll
-          for (int i = 0; i < 4; i++) { m_lo[i] = box_u_mask(bu, px + i, py); m_hi[i] = box_u_mask(bu, px + kHalf + i, py); }
+          for (int i = 0; i < 4; i++) m[i] = box_u_mask(bu, px + i, py);
         }
         else if (type == B2DGPU_CMD_FILL_BOX_MASK_A) {
-          const Mask8 mk = box_mask_a_row(cmd, P.fetch_data[cmd.reserved[0]].pattern.src, px, px + kHalf, py);
-          m_lo[0] = mk.lo.x; m_lo[1] = mk.lo.y; m_lo[2] = mk.lo.z; m_lo[3] = mk.lo.w;
-          m_hi[0] = mk.hi.x; m_hi[1] = mk.hi.y; m_hi[2] = mk.hi.z; m_hi[3] = mk.hi.w;
+          const uint4 mk = box_mask_a_row(cmd, P.fetch_data[cmd.reserved[0]].pattern.src, px, py);
+          m[0] = mk.x; m[1] = mk.y; m[2] = mk.z; m[3] = mk.w;
         }
         else {
           const uint32_t flags = pre.flags;
-          uint32_t carry = pre.carry_left[row];
-          if (!(flags & kPreStraddle)) {
-            // No edge inside the tile: coverage is constant along the row (FillAnalytic's CMask spans).
-            if (!carry) continue;
-            const uint32_t mm = calc_mask((256u << 9) + carry, cmd.fill_rule_mask, alpha);
-            #pragma unroll
-            for (int i = 0; i < 4; i++) { m_lo[i] = mm; m_hi[i] = mm; }
-          }
-          else {
-            uint32_t cov[kLanePx];
-            const uint32_t rule = cmd.fill_rule_mask;
-            const uint32_t n = pre.nent[row];
-            if (!(flags & kPreOverflow)) {
-              // Fast path: the row's cells are the handful of entries phase 1 recorded.  The running sum of
-              // fillgeneric_p.h:285-297 at pixel x is the backdrop plus every entry at or left of x (u32 adds commute),
-              // so no prefix scan is needed: each entry is added to the pixels from its cell onwards.
-              carry += pre.carry_st[row] + (256u << 9);
-              #pragma unroll
-              for (int i = 0; i < kLanePx; i++) cov[i] = carry;
-              const uint32_t n_inline = min(n, uint32_t(kEntCap));
-              uint32_t chain = n > uint32_t(kEntCap) ? pre.ovf_head[row] : 0u;
-              for (uint32_t j = 0; j < n_inline || chain; j++) {
-                uint2 en;
-                if (j < n_inline) en = pre.ent[row][j];
-                else { en = s_pool[chain - 1u]; chain = s_pool_link[chain - 1u]; }
-                const int first = int(en.x & 0xFFu) - lane * 4;     // first pixel of the lo group that the crossing reaches
-                const uint32_t area = uint32_t(int32_t(en.x) >> 8);
-                // pixel i gets v0 from cell `first` on and `area` from cell `first + 1` on: i > first <=> i - 1 >= first,
-                // so five comparisons serve the eight selects of the group
-                const bool pm = first < 0, p0 = first <= 0, p1 = first <= 1, p2 = first <= 2, p3 = first <= 3;
-                cov[0] += (p0 ? en.y : 0u) + (pm ? area : 0u);
-                cov[1] += (p1 ? en.y : 0u) + (p0 ? area : 0u);
-                cov[2] += (p2 ? en.y : 0u) + (p1 ? area : 0u);
-                cov[3] += (p3 ? en.y : 0u) + (p2 ? area : 0u);
-                if (kTwoHalves) {
-                  #pragma unroll
-                  for (int i = 0; i < 4; i++)
-                    cov[4 + i] += ((i + kHalf >= first) ? en.y : 0u) + ((i + kHalf > first) ? area : 0u);
-                }
-              }
+          const uint32_t rule = cmd.fill_rule_mask;
+          if (!(flags & kPreOverflow)) {
+            // Backdrop of the lane's row at the first pixel of the block.
+            const uint4 c4 = pre.carry4[row];
+            const uint32_t carry = (256u << 9) + pre.carry_left[row] + c4.x + (blk >= 1 ? c4.y : 0u) + (blk >= 2 ? c4.z : 0u) + (blk >= 3 ? c4.w : 0u);
+            const bool has = (pre.blk_has[row >> 3] >> ((row & 7) * 4 + blk)) & 1u;
+            if (!__any_sync(0xFFFFFFFFu, has)) {
+              // No edge inside the block: coverage is constant along each of its rows (FillAnalytic's CMask spans).
+              const uint32_t mm = calc_mask(carry, rule, alpha);
+              m[0] = mm; m[1] = mm; m[2] = mm; m[3] = mm;
             }
             else {
-              slow_row_cells(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, py, row, lane, &s_cells[row][0], &s_carry[row], TH);
-              {
-                uint4 c0 = *reinterpret_cast<uint4*>(&s_cells[row][lane * 4]);
-                uint4 c1 = *reinterpret_cast<uint4*>(&s_cells[row][kHalf + lane * 4]);
-                cov[0] = c0.x; cov[1] = c0.y; cov[2] = c0.z; cov[3] = c0.w;
-                cov[4] = c1.x; cov[5] = c1.y; cov[6] = c1.z; cov[7] = c1.w;
+              // The running sum of fillgeneric_p.h:285-297 at pixel x is the backdrop plus every entry at or left of x
+              // (u32 adds commute), so no prefix scan is needed: each entry of the row that belongs to this block is
+              // added to the pixels from its cell onwards; the entries left of the block are in `carry` already.
+              uint32_t cov0 = carry, cov1 = carry, cov2 = carry, cov3 = carry;
+              const uint32_t n = has ? pre.nent[row] : 0u;
+              const uint32_t n_inline = min(n, uint32_t(kEntCap));
+              uint32_t chain = n > uint32_t(kEntCap) ? pre.ovf_head[row] : 0u;
+              const int lo = blk * kBlockW - 1;                       // cells from here on are applied pixel by pixel
+              const int lane_x = blk * kBlockW + (lane & 7) * 4;      // the lane's first pixel, relative to the tile
+              for (uint32_t j = 0; __any_sync(0xFFFFFFFFu, j < n_inline || chain != 0u); j++) {
+                uint2 en = make_uint2(0u, 0u);
+                bool valid = false;
+                if (j < n_inline) { en = pre.ent[row][j]; valid = true; }
+                else if (chain) { en = s_pool[chain - 1u]; chain = s_pool_link[chain - 1u]; valid = true; }
+                const int rel = int(en.x & 0xFFu);
+                valid = valid && rel >= lo;
+                const uint32_t v0 = valid ? en.y : 0u;
+                const uint32_t area = valid ? uint32_t(int32_t(en.x) >> 8) : 0u;
+                const int first = rel - lane_x;                       // first pixel of the lane that the crossing reaches
+                // pixel i gets v0 from cell `first` on and `area` from cell `first + 1` on: i > first <=> i - 1 >= first,
+                // so five comparisons serve the eight selects
+                const bool pm = first < 0, p0 = first <= 0, p1 = first <= 1, p2 = first <= 2, p3 = first <= 3;
+                cov0 += (p0 ? v0 : 0u) + (pm ? area : 0u);
+                cov1 += (p1 ? v0 : 0u) + (p0 ? area : 0u);
+                cov2 += (p2 ? v0 : 0u) + (p1 ? area : 0u);
+                cov3 += (p3 ? v0 : 0u) + (p2 ? area : 0u);
               }
-              carry += s_carry[row];
-              __syncwarp();
-              // Prefix-sum of the row's cells: in the lane's groups, then across the warp, left half first.
-              #pragma unroll
-              for (int i = 1; i < 4; i++) { cov[i] += cov[i - 1]; cov[4 + i] += cov[4 + i - 1]; }
-              uint32_t inc_lo = cov[3], inc_hi = cov[7];
-              #pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t0 = __shfl_up_sync(0xFFFFFFFFu, inc_lo, o), t1 = __shfl_up_sync(0xFFFFFFFFu, inc_hi, o);
-                if (lane >= o) { inc_lo += t0; inc_hi += t1; }
-              }
-              const uint32_t total_lo = __shfl_sync(0xFFFFFFFFu, inc_lo, 31);
-              const uint32_t base_lo = (256u << 9) + carry + (inc_lo - cov[3]);
-              const uint32_t base_hi = (256u << 9) + carry + total_lo + (inc_hi - cov[7]);
-              #pragma unroll
-              for (int i = 0; i < 4; i++) { cov[i] += base_lo; cov[4 + i] += base_hi; }
+              m[0] = calc_mask(cov0, rule, alpha); m[1] = calc_mask(cov1, rule, alpha);
+              m[2] = calc_mask(cov2, rule, alpha); m[3] = calc_mask(cov3, rule, alpha);
             }
-            #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              m_lo[i] = calc_mask(cov[i], rule, alpha);
-              m_hi[i] = calc_mask(cov[4 + i], rule, alpha);
-            }
+          }
+          else {
+            // Slow path: the group's four warps rasterize one row each, then read their blocks of all four rows.
+            const int my_row = grp * kBlockRows + blk;
+            slow_group_rows(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, my_row, lane, &s_cells[my_row][0], &s_carry[my_row],
+                            (256u << 9) + pre.carry_left[my_row], TH, grp);
+            const uint4 c = *reinterpret_cast<const uint4*>(&s_cells[row][blk * kBlockW + (lane & 7) * 4]);
+            asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");      // the cells may be overwritten after this
+            m[0] = calc_mask(c.x, rule, alpha); m[1] = calc_mask(c.y, rule, alpha);
+            m[2] = calc_mask(c.z, rule, alpha); m[3] = calc_mask(c.w, rule, alpha);
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
           if (flags & kPreClipRight) {
             const int bx1 = pre.bx1;
             #pragma unroll
-            for (int i = 0; i < 4; i++) { if (px + i >= bx1) m_lo[i] = 0; if (px + kHalf + i >= bx1) m_hi[i] = 0; }
+            for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
           }
         }
 
-        // ---- fetch + composite, one half of the row at a time ----
+        // ---- fetch + composite ----
         // The votes keep every branch warp-uniform, so the lanes stay converged for the next iteration.
+        if (!__any_sync(0xFFFFFFFFu, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
         const uint32_t sig = cmd.signature;
         FetchEnv env;
         env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
@@ -718,53 +745,31 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         env.bayer = P.bayer;
         env.origin_x = P.origin_x; env.origin_y = P.origin_y;
         const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
-
-        // Both halves go through ONE copy of the fetch / composite code (the loop is not unrolled; lo and hi swap places
-        // after each pass and are back where they started after the second).
-        #pragma unroll 1
-        for (int h = 0; h < (kTwoHalves ? 2 : 1); h++) {
-          if (__any_sync(0xFFFFFFFFu, (m_lo[0] | m_lo[1] | m_lo[2] | m_lo[3]) != 0u)) {
-            const uint32_t not_opaque = ((m_lo[0] + 1u) | (m_lo[1] + 1u) | (m_lo[2] + 1u) | (m_lo[3] + 1u)) & 0xFEu;
-            const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
-            uint32_t s[4] = { 0, 0, 0, 0 };
-            fetch4(env, uint32_t(px + kHalf * h), uint32_t(py), m_lo, s);
-            if (BPP == 1) {
-              #pragma unroll
-              for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
-            }
-            composite4(comp_op, d_lo, s, m_lo, opaque);
-            px_written += (m_lo[0] != 0) + (m_lo[1] != 0) + (m_lo[2] != 0) + (m_lo[3] != 0);
-            dirty = true;
-          }
-          if (kTwoHalves) {
-            #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              uint32_t t = d_lo[i]; d_lo[i] = d_hi[i]; d_hi[i] = t;
-              t = m_lo[i]; m_lo[i] = m_hi[i]; m_hi[i] = t;
-            }
-          }
+        const uint32_t not_opaque = ((m[0] + 1u) | (m[1] + 1u) | (m[2] + 1u) | (m[3] + 1u)) & 0xFEu;
+        const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
+        uint32_t s[4] = { 0, 0, 0, 0 };
+        fetch4(env, uint32_t(px), uint32_t(py), m, s);
+        if (BPP == 1) {
+          #pragma unroll
+          for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
         }
+        composite4(comp_op, d, s, m, opaque);
+        if (count_pixels) px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
+        dirty = true;
       }
       }
     }
   }
 
   if (dirty) {
-    if (BPP == 4) {
-      *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d_lo[0], d_lo[1], d_lo[2], d_lo[3]);
-      if (kTwoHalves) *reinterpret_cast<uint4*>(dst_row + size_t(px + kHalf) * 4) = make_uint4(d_hi[0], d_hi[1], d_hi[2], d_hi[3]);
-    }
-    else {
-      uint2 v;
-      v.x = (d_lo[0] >> 24) | ((d_lo[1] >> 24) << 8) | ((d_lo[2] >> 24) << 16) | ((d_lo[3] >> 24) << 24);
-      v.y = (d_hi[0] >> 24) | ((d_hi[1] >> 24) << 8) | ((d_hi[2] >> 24) << 16) | ((d_hi[3] >> 24) << 24);
-      *reinterpret_cast<uint32_t*>(dst_row + px) = v.x;
-      if (kTwoHalves) *reinterpret_cast<uint32_t*>(dst_row + px + kHalf) = v.y;
-    }
+    if (BPP == 4) *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d[0], d[1], d[2], d[3]);
+    else *reinterpret_cast<uint32_t*>(dst_row + px) = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
   }
 
-  px_written = __reduce_add_sync(0xFFFFFFFFu, px_written);
-  if (lane == 0 && px_written) atomicAdd(P.pixel_counter, (unsigned long long)px_written);
+  if (count_pixels) {
+    px_written = __reduce_add_sync(0xFFFFFFFFu, px_written);
+    if (lane == 0 && px_written) atomicAdd(P.pixel_counter, (unsigned long long)px_written);
+  }
 }
 
 // =================================================================================================================
@@ -864,8 +869,10 @@ __global__ void __launch_bounds__(256) k_box_stream(TileParams P, int rows, int 
       else *reinterpret_cast<uint32_t*>(ptr[u]) = (d[0] >> 24) | ((d[1] >> 24) << 8) | ((d[2] >> 24) << 16) | ((d[3] >> 24) << 24);
     }
   }
-  written = __reduce_add_sync(0xFFFFFFFFu, written);
-  if ((threadIdx.x & 31) == 0 && written) atomicAdd(P.pixel_counter, (unsigned long long)written);
+  if (P.pixel_counter) {
+    written = __reduce_add_sync(0xFFFFFFFFu, written);
+    if ((threadIdx.x & 31) == 0 && written) atomicAdd(P.pixel_counter, (unsigned long long)written);
+  }
 }
 
 // =================================================================================================================
@@ -938,7 +945,7 @@ __global__ void __launch_bounds__(256) k_stream_solid(SolidStreamParams P, int c
       *ptr[u] = o;
     }
   }
-  if (tid == 0) atomicAdd(P.pixel_counter, P.pixels);
+  if (tid == 0 && P.pixel_counter) atomicAdd(P.pixel_counter, P.pixels);
 }
 
 // =================================================================================================================

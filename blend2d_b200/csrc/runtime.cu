@@ -115,6 +115,7 @@ struct b2dgpu_runtime {
 
   b2dgpu_stats stats;
   bool profiling;
+  bool count_pixels;                        // b2dgpu_stats::pixels_composited is maintained (a few instructions per composited group)
   int sm_count;
   std::vector<cudaEvent_t> prof_events;     // triples: start, after build kernels, after tile kernel
 };
@@ -171,6 +172,7 @@ static std::vector<b2dgpu_runtime*> g_runtimes;
 static std::vector<b2dgpu_target*> g_targets;
 static b2dgpu_stats g_retired_stats;                 // totals of destroyed runtimes
 static bool g_profiling_default = false;
+static bool g_count_pixels_default = true;
 static b2dgpu_capture* g_capture = nullptr;          // non-null while b2dgpu_capture_begin() .. _end()
 
 template<typename T>
@@ -284,6 +286,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
   rt->profiling = false;
+  rt->count_pixels = true;
   rt->sm_count = 148;
   { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) rt->sm_count = v; }
   memset(&rt->stats, 0, sizeof(rt->stats));
@@ -322,6 +325,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
     std::lock_guard<std::mutex> g(g_registry_mutex);
     g_runtimes.push_back(rt);
     rt->profiling = g_profiling_default;
+    rt->count_pixels = g_count_pixels_default;
   }
   *out = rt;
   return B2DGPU_SUCCESS;
@@ -401,6 +405,13 @@ extern "C" b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled) {
   if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_set_profiling: invalid runtime");
   std::lock_guard<std::mutex> lock(rt->mutex);
   rt->profiling = enabled != 0;
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_set_pixel_counting(b2dgpu_runtime* rt, int enabled) {
+  if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_set_pixel_counting: invalid runtime");
+  std::lock_guard<std::mutex> lock(rt->mutex);
+  rt->count_pixels = enabled != 0;
   return B2DGPU_SUCCESS;
 }
 
@@ -898,7 +909,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   T.bayer = rt->d_bayer;
   T.origin_x = in.origin_x;
   T.origin_y = in.origin_y;
-  T.pixel_counter = rt->d_pixel_counter;
+  T.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
   T.band_ext = nullptr;
   // Per (band, command) x-extents: only worth building when some command has edges (a box's bounding box is exact) and
   // while the table stays small (8 B per cell; 10 000 commands on a 4K canvas = 21.6 MB).
@@ -933,7 +944,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
         S.src = t->bpp == 4 ? in.solid.prgb32 : (in.solid.prgb32 >> 24) * 0x01010101u;
         S.mask = in.solid.alpha;
         S.pixels = (unsigned long long)(box[2] - box[0]) * (unsigned long long)(box[3] - box[1]);
-        S.pixel_counter = rt->d_pixel_counter;
+        S.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
         launches += launch_stream_solid(S, rt->sm_count, s);
       }
       else launches += launch_box_stream(T, t->bpp, box, rt->sm_count, s);
@@ -1113,6 +1124,13 @@ extern "C" b2dgpu_result b2dgpu_global_set_profiling(int enabled) {
   std::vector<b2dgpu_runtime*> live;
   { std::lock_guard<std::mutex> g(g_registry_mutex); g_profiling_default = enabled != 0; live = g_runtimes; }
   for (b2dgpu_runtime* rt : live) b2dgpu_set_profiling(rt, enabled);
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_global_set_pixel_counting(int enabled) {
+  std::vector<b2dgpu_runtime*> live;
+  { std::lock_guard<std::mutex> g(g_registry_mutex); g_count_pixels_default = enabled != 0; live = g_runtimes; }
+  for (b2dgpu_runtime* rt : live) b2dgpu_set_pixel_counting(rt, enabled);
   return B2DGPU_SUCCESS;
 }
 

@@ -366,6 +366,9 @@ typedef struct b2dgpu_stats {
 B2DGPU_API b2dgpu_result b2dgpu_get_stats(b2dgpu_runtime* rt, b2dgpu_stats* out, int reset);
 /* Enables (1) / disables (0) per-kernel CUDA-event timing; adds two event records per phase and render. */
 B2DGPU_API b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled);
+/* b2dgpu_stats::pixels_composited is maintained by the compositing kernels themselves (a vote and a few adds per
+ * composited group of pixels).  On by default; a caller that does not read the statistic can switch it off. */
+B2DGPU_API b2dgpu_result b2dgpu_set_pixel_counting(b2dgpu_runtime* rt, int enabled);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Process-wide access.  A Blend2D application that selects this runtime through BLContextCreateInfo (shim/)
@@ -375,6 +378,8 @@ B2DGPU_API b2dgpu_result b2dgpu_set_profiling(b2dgpu_runtime* rt, int enabled);
 B2DGPU_API b2dgpu_result b2dgpu_global_stats(b2dgpu_stats* out, int reset);
 /* b2dgpu_set_profiling() for every live runtime and for the ones created later. */
 B2DGPU_API b2dgpu_result b2dgpu_global_set_profiling(int enabled);
+/* b2dgpu_set_pixel_counting() for every live runtime and for the ones created later. */
+B2DGPU_API b2dgpu_result b2dgpu_global_set_pixel_counting(int enabled);
 /* Capture: between begin and end every b2dgpu_submit() of the process also keeps a device-resident copy of its batch
  * (b2dgpu_batch_upload).  b2dgpu_capture_replay() renders the captured batches again, `times` times, into the targets
  * they were submitted to - inputs already in HBM, nothing crosses PCIe - and returns the device time of the replay
