@@ -335,9 +335,34 @@ B2D_HD_COLD uint32_t fetch_pixel_cold(const FetchEnv& env, uint32_t x, uint32_t 
   return fetch_pixel(env, rc, x, y);
 }
 
-// Fetches the (up to) 4 consecutive pixels x..x+3 of row y whose mask is non-zero.  The fetch-type dispatch is hoisted
+// Per-row state of the nearest-neighbour gradient fetchers as three 32-bit words, so that it can be computed once per
+// (command, row) and kept in shared memory: linear = the 64-bit row origin pt0 + y * dy (a, b), radial = RadialRow,
+// conic = ConicRow (float bits).
+struct RowCtx3 { uint32_t a, b, c; };
+
+B2D_HD float f32_from_bits(uint32_t u) { union { float f; uint32_t u; } c; c.u = u; return c.f; }
+
+B2D_HD RowCtx3 fetch_row_ctx(uint32_t ft, const b2dgpu_fetch_data& fd, uint32_t y) {
+  RowCtx3 o; o.a = o.b = o.c = 0;
+  if (ft <= B2DGPU_FETCH_GRADIENT_LINEAR_DITHER_ROR) {
+    const uint64_t pt = fd.gradient.linear.pt[0].u64 + uint64_t(y) * fd.gradient.linear.dy.u64;
+    o.a = uint32_t(pt); o.b = uint32_t(pt >> 32);
+  }
+  else if (ft <= B2DGPU_FETCH_GRADIENT_RADIAL_DITHER_ROR) {
+    const RadialRow r = radial_row(fd.gradient.radial, y);
+    o.a = f32_bits(r.b); o.b = f32_bits(r.d); o.c = f32_bits(r.dd);
+  }
+  else {
+    const ConicRow r = conic_row(fd.gradient.conic, y);
+    o.a = f32_bits(r.tx); o.b = f32_bits(r.ay); o.c = f32_bits(r.by);
+  }
+  return o;
+}
+
+// Fetches the (up to) 4 consecutive pixels x..x+3 of row y whose mask is non-zero.  `rowctx` (optional) = the result of
+// fetch_row_ctx() for this command and row.  The fetch-type dispatch is hoisted
 // out of the pixel loop: a command is uniform over the whole CTA, so every warp takes the same branch.
-B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* m, uint32_t* s) {
+B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* m, uint32_t* s, const RowCtx3* rowctx = nullptr) {
   const uint32_t ft = env.fetch_type;
   if (ft == B2DGPU_FETCH_SOLID) {
     s[0] = s[1] = s[2] = s[3] = env.solid;
@@ -353,7 +378,7 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     const bool pad = ft == B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD;
     const uint32_t maxi = l.maxi, rori = l.rori;
     const uint64_t dt = l.dt.u64;
-    uint64_t pt = l.pt[0].u64 + uint64_t(y) * l.dy.u64 + uint64_t(x) * dt;
+    uint64_t pt = (rowctx ? (uint64_t(rowctx->a) | (uint64_t(rowctx->b) << 32)) : l.pt[0].u64 + uint64_t(y) * l.dy.u64) + uint64_t(x) * dt;
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       uint32_t idx = uint32_t(pt >> 32);
@@ -367,7 +392,9 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
     const b2dgpu_gradient_radial& r = g.radial;
     const bool pad = ft == B2DGPU_FETCH_GRADIENT_RADIAL_NN_PAD;
-    const RadialRow row = radial_row(r, y);
+    RadialRow row;
+    if (rowctx) { row.b = f32_from_bits(rowctx->a); row.d = f32_from_bits(rowctx->b); row.dd = f32_from_bits(rowctx->c); }
+    else row = radial_row(r, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) {
       uint32_t idx = radial_index(r, row, x + i);
@@ -378,7 +405,9 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
   }
   if (ft == B2DGPU_FETCH_GRADIENT_CONIC_NN) {
     const b2dgpu_fetch_gradient& g = env.fd->gradient;
-    const ConicRow row = conic_row(g.conic, y);
+    ConicRow row;
+    if (rowctx) { row.tx = f32_from_bits(rowctx->a); row.ay = f32_from_bits(rowctx->b); row.by = f32_from_bits(rowctx->c); }
+    else row = conic_row(g.conic, y);
     #pragma unroll
     for (int i = 0; i < 4; i++) s[i] = lut_fetch_nn(g, conic_index(g.conic, row, x + i));
     return;

@@ -303,8 +303,8 @@ __global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __res
 // K2 + K3 - tile compositor
 //
 // One CTA of TH warps per 128 x TH destination tile.  A WARP owns a block of 32 columns x 4 rows of the tile (8 lanes
-// per row, 4 consecutive pixels = one 16-byte vector per lane): warp w -> row group w / 4 (rows 4g .. 4g + 3), column
-// block w % 4.  The block's pixels are loaded ONCE into registers, every command that touches the tile is replayed in
+// per row, 4 consecutive pixels = one 16-byte vector per lane): warp w -> row group w % (TH / 4) (rows 4g .. 4g + 3),
+// column block w / (TH / 4).  The block's pixels are loaded ONCE into registers, every command that touches the tile is replayed in
 // submission order and the block is stored ONCE.  Blocks are what the work is decided on: phase 1 leaves, per command,
 // one bit per warp ("this block can receive coverage"), the backdrop of every row at the start of each block, and one
 // bit per (row, block) that says whether an edge crosses it - so a warp whose block lies outside a shape skips the
@@ -337,12 +337,18 @@ struct PreCmdT {
   uint32_t nent[TH];            // number of cell entries appended per row (beyond kEntCap: chained in the pool)
   uint32_t ovf_head[TH];        // 1 + pool index of the row's last chained entry, 0 = none
   uint32_t blk_has[(TH + 7) / 8]; // 4 bits per row: block b of the row holds an entry (or the spill of its left neighbour)
-  uint32_t flags;
+  uint32_t flags;               // phase 1 only (atomically updated); the replay reads hdr
   uint32_t warp_mask;           // bit w: warp w's block can receive coverage from this command (0: skipped by the replay)
-  int bx1;
-  uint32_t pad_[(4 - ((TH + 7) / 8 + 3) % 4) % 4];
+  uint32_t pad_[(4 - ((TH + 7) / 8 + 2) % 4) % 4];
+  // What the replay needs of the command, decoded once by phase 1 (two 16-byte shared-memory loads per iteration):
+  //   [0] type | flags << 8   [1] alpha   [2] fill rule mask   [3] solid colour
+  //   [4] fetch type | comp op << 8 | source format << 16   [5] right end of the clipped box   [6,7] FetchData pointer
+  uint32_t hdr[8];
   uint2 ent[TH][kEntCap];       // edge crossings: (cell relative to the tile | area << 8, (cover << 9) - area)
-  // Staged by phase 1 so that the replay does not chase global pointers: the command (64 B).
+  // Per-row state of the gradient fetchers (fetch_row_ctx: 64-bit row origin of a linear gradient, the three floats of
+  // a radial / conic row), computed once per (command, row) by the lane that owns the row in phase 1.
+  uint32_t rowctx[TH][3];
+  // The command itself (64 B): box coordinates and the mask index of the box fills.
   uint32_t cmd_words[sizeof(b2dgpu_command) / 4];
 };
 static_assert(sizeof(PreCmdT<8>) % 16 == 0 && sizeof(PreCmdT<16>) % 16 == 0 && sizeof(PreCmdT<32>) % 16 == 0, "PreCmd must keep 16-byte alignment of the staged blocks");
@@ -460,7 +466,11 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   const int tx0 = tile_x * kTileW;
   const int ty0 = P.y_begin + tile_y * TH;          // absolute y of the tile's first row
   // Replay geometry of this lane: block (grp, blk) of the tile, row `row` of the tile, pixels px .. px + 3.
-  const int grp = warp >> 2, blk = warp & 3;
+  // Warp w -> row group w % G, column block w / G (G = TH / 4 groups): the warp schedulers take warps round robin
+  // (w % 4), so each of them gets blocks from all four columns of the tile and from row groups that lie apart -
+  // whatever part of the tile a shape covers, its work is spread over the four schedulers.
+  constexpr int kGroups = TH / kBlockRows;
+  const int grp = warp % kGroups, blk = warp / kGroups;
   const int row = grp * kBlockRows + (lane >> 3);
   const int bx0 = tx0 + blk * kBlockW;              // first column of the warp's block
   const int px = bx0 + (lane & 7) * 4;
@@ -530,7 +540,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         if (lane < TH) { pre->carry4[lane] = make_uint4(0, 0, 0, 0); pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
         if (lane < (TH + 7) / 8) pre->blk_has[lane] = 0;
         const int4 bbp = P.cmd_bbox_px[ci];
-        if (lane == 0) { pre->bx1 = bbp.z; pre->flags = bbp.z < tx0 + kTileW ? kPreClipRight : 0u; }
+        if (lane == 0) pre->flags = bbp.z < tx0 + kTileW ? kPreClipRight : 0u;
         {
           // stage the command (one coalesced 64-byte load)
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.commands + ci);
@@ -611,12 +621,28 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         const bool dense = nstr && items > kDenseItemsPerRow * uint32_t(TH);
         if (lane == 0 && nstr) atomicOr(&pre->flags, dense ? (kPreStraddle | kPreOverflow) : kPreStraddle);
         __syncwarp();
+        {
+          const b2dgpu_command& c = *reinterpret_cast<const b2dgpu_command*>(pre->cmd_words);
+          const uint32_t sig = c.signature;
+          const uint32_t ft = B2DGPU_SIG_FETCH_TYPE(sig);
+          const b2dgpu_fetch_data* fd = P.fetch_data + c.fetch_index;
+          if (lane == 0) {
+            pre->hdr[0] = c.type | (pre->flags << 8); pre->hdr[1] = c.alpha; pre->hdr[2] = c.fill_rule_mask; pre->hdr[3] = c.solid_prgb32;
+            pre->hdr[4] = ft | (B2DGPU_SIG_COMP_OP(sig) << 8) | (B2DGPU_SIG_SRC_FORMAT(sig) << 16);
+            pre->hdr[5] = uint32_t(bbp.z);
+            pre->hdr[6] = uint32_t(uintptr_t(fd)); pre->hdr[7] = uint32_t(uintptr_t(fd) >> 32);
+          }
+          if (lane < TH && ft >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD) {
+            const RowCtx3 rc = fetch_row_ctx(ft, *fd, uint32_t(ty0 + lane));
+            pre->rowctx[lane][0] = rc.a; pre->rowctx[lane][1] = rc.b; pre->rowctx[lane][2] = rc.c;
+          }
+        }
 
         // Which warps of the replay does this command concern?  Lane w answers for warp w = block (w / 4, w % 4).
         {
           bool any = false;
           if (lane < TH) {
-            const int g = lane >> 2, b = lane & 3;
+            const int g = lane % kGroups, b = lane / kGroups;
             const int r0 = g * kBlockRows;
             const bool rows_in = bbp.y < ty0 + r0 + kBlockRows && bbp.w > ty0 + r0;
             if (is_box) any = rows_in && bbp.x < tx0 + (b + 1) * kBlockW && bbp.z > tx0 + b * kBlockW;
@@ -650,8 +676,10 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         act &= act - 1;
         const PreCmd& pre = s_pre[k];
         const b2dgpu_command& cmd = *reinterpret_cast<const b2dgpu_command*>(pre.cmd_words);
-        const uint32_t type = cmd.type;
-        const uint32_t alpha = cmd.alpha;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(&pre.hdr[0]);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(&pre.hdr[4]);
+        const uint32_t type = h0.x & 0xFFu;
+        const uint32_t alpha = h0.y;
         uint32_t m[4] = { 0, 0, 0, 0 };
 
         if (type == B2DGPU_CMD_FILL_BOX_A) {
@@ -671,8 +699,8 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           m[0] = mk.x; m[1] = mk.y; m[2] = mk.z; m[3] = mk.w;
         }
         else {
-          const uint32_t flags = pre.flags;
-          const uint32_t rule = cmd.fill_rule_mask;
+          const uint32_t flags = h0.x >> 8;
+          const uint32_t rule = h0.z;
           if (!(flags & kPreOverflow)) {
             // Backdrop of the lane's row at the first pixel of the block.
             const uint4 c4 = pre.carry4[row];
@@ -727,7 +755,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           }
           // Pixels outside the command's clipped box never composite (FillData::Analytic::box clamps x1 to the width).
           if (flags & kPreClipRight) {
-            const int bx1 = pre.bx1;
+            const int bx1 = int(h1.y);
             #pragma unroll
             for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
           }
@@ -736,19 +764,20 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         // ---- fetch + composite ----
         // The votes keep every branch warp-uniform, so the lanes stay converged for the next iteration.
         if (!__any_sync(0xFFFFFFFFu, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
-        const uint32_t sig = cmd.signature;
         FetchEnv env;
-        env.fetch_type = B2DGPU_SIG_FETCH_TYPE(sig);
-        env.src_format = B2DGPU_SIG_SRC_FORMAT(sig);
-        env.solid = cmd.solid_prgb32;
-        env.fd = P.fetch_data + cmd.fetch_index;
+        env.fetch_type = h1.x & 0xFFu;
+        env.src_format = h1.x >> 16;
+        env.solid = h0.w;
+        env.fd = reinterpret_cast<const b2dgpu_fetch_data*>(uintptr_t(h1.z) | (uintptr_t(h1.w) << 32));
         env.bayer = P.bayer;
         env.origin_x = P.origin_x; env.origin_y = P.origin_y;
-        const uint32_t comp_op = B2DGPU_SIG_COMP_OP(sig);
+        const uint32_t comp_op = (h1.x >> 8) & 0xFFu;
         const uint32_t not_opaque = ((m[0] + 1u) | (m[1] + 1u) | (m[2] + 1u) | (m[3] + 1u)) & 0xFEu;
         const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
         uint32_t s[4] = { 0, 0, 0, 0 };
-        fetch4(env, uint32_t(px), uint32_t(py), m, s);
+        RowCtx3 rc3;
+        rc3.a = pre.rowctx[row][0]; rc3.b = pre.rowctx[row][1]; rc3.c = pre.rowctx[row][2];
+        fetch4(env, uint32_t(px), uint32_t(py), m, s, &rc3);
         if (BPP == 1) {
           #pragma unroll
           for (int i = 0; i < 4; i++) s[i] = (s[i] >> 24) * 0x01010101u;
@@ -1070,6 +1099,7 @@ int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaSt
 // configuration the 4K bench runs) when they give every SM a couple of tiles, shorter tiles for small canvases.
 int choose_tile_height(int tiles_x, int rows, int sm_count) {
   const int heights[3] = { 32, 16, 8 };
+  if (const char* e = getenv("B2D_TILE_H")) { const int v = atoi(e); if (v == 8 || v == 16 || v == 32) return v; }   // experiment knob
   for (int i = 0; i < 3; i++)
     if (tiles_x * ((rows + heights[i] - 1) / heights[i]) >= 2 * sm_count) return heights[i];
   return 8;
