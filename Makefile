@@ -12,13 +12,16 @@ all: $(OUT)
 $(CSRC)/kernels.o: $(CSRC)/kernels.cu $(DEVHDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(CSRC)/kernels.ptxas.log || (cat $(CSRC)/kernels.ptxas.log; false)
 
+$(CSRC)/stream.o: $(CSRC)/stream.cu $(DEVHDR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(CSRC)/stream.ptxas.log || (cat $(CSRC)/stream.ptxas.log; false)
+
 $(CSRC)/runtime.o: $(CSRC)/runtime.cu $(DEVHDR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
 $(CSRC)/host/%.o: $(CSRC)/host/%.cpp $(wildcard $(CSRC)/host/*.h) include/b2dgpu.h
 	g++ -std=c++17 -O2 -fPIC -fvisibility=hidden -ffp-contract=off -Iinclude -c $< -o $@
 
-$(OUT): $(CSRC)/kernels.o $(CSRC)/runtime.o $(HOSTSRC:.cpp=.o)
+$(OUT): $(CSRC)/kernels.o $(CSRC)/stream.o $(CSRC)/runtime.o $(HOSTSRC:.cpp=.o)
 	$(NVCC) -shared -o $@ $^ -cudart static -Xlinker --no-undefined -lpthread -ldl -lrt
 
 clean:

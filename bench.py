@@ -620,7 +620,7 @@ def run_reference_range(scene, first, count, W, H):
 
 def measure_full_canvas(gb):
     """One full-canvas SrcOver fill per launch: reads 4 B and writes 4 B per pixel; a PRGB32 pattern source
-    adds 4 B per pixel.  Solid -> k_stream_solid; gradient / pattern -> the generic streaming compositor k_box_stream."""
+    adds 4 B per pixel.  Solid -> k_stream_solid; gradient / pattern -> k_stream_one (stream.cu)."""
     import blend2d_b200 as G
     N, lib, torch = gb.N, gb.lib, gb.torch
     # The runtime runs on a torch stream and the L2 flush is enqueued on the same stream right before every launch, so
@@ -631,7 +631,7 @@ def measure_full_canvas(gb):
     tex = None
     for name, (W, H), style in (("4k", (3840, 2160), "solid"), ("16k", (16384, 16384), "solid"),
                                  ("16k_linear", (16384, 16384), "linear"), ("16k_radial", (16384, 16384), "radial"),
-                                 ("16k_pattern", (16384, 16384), "pattern")):
+                                 ("16k_conic", (16384, 16384), "conic"), ("16k_pattern", (16384, 16384), "pattern")):
         img = G.Image(W, H, G.FORMAT_PRGB32)
         rec = G.Context(img, record_only=True)
         extra = 0.0
@@ -641,18 +641,22 @@ def measure_full_canvas(gb):
         elif style == "linear":
             rec.set_fill_style(G.Gradient(G.GRADIENT_LINEAR, [0.0, 0.0, float(W), float(H)], G.EXTEND_PAD,
                                           [(0.0, 0x80FF0000), (0.5, 0xC000FF00), (1.0, 0x800000FF)]))
-            kernel = "k_box_stream<4> linear gradient"
+            kernel = "k_stream_one<linear> (stream.cu)"
         elif style == "radial":
             rec.set_fill_style(G.Gradient(G.GRADIENT_RADIAL, [W / 2.0, H / 2.0, W / 2.0 - 100.0, H / 2.0 - 50.0, W / 2.0, 0.0], G.EXTEND_PAD,
                                           [(0.0, 0x80FF0000), (0.5, 0xC000FF00), (1.0, 0x800000FF)]))
-            kernel = "k_box_stream<4> radial gradient"
+            kernel = "k_stream_one<radial> (stream.cu)"
+        elif style == "conic":
+            rec.set_fill_style(G.Gradient(G.GRADIENT_CONIC, [W / 2.0, H / 2.0, 0.0, 1.0], G.EXTEND_PAD,
+                                          [(0.0, 0x80FF0000), (0.33, 0xC000FF00), (0.66, 0x800000FF), (1.0, 0x80FF0000)]))
+            kernel = "k_stream_one<conic> (stream.cu)"
         else:
             tex = G.Image(4096, 4096, G.FORMAT_PRGB32)
             rng = np.random.default_rng(1)
             a = rng.integers(1, 255, (4096, 4096)).astype(np.uint32)
             tex.from_numpy((a << 24) | ((a // 2) << 16) | ((a // 3) << 8) | (a // 4))
             rec.set_fill_style(G.Pattern(tex, None, G.EXTEND_REPEAT, [1, 0, 0, 1, 0, 0]))
-            kernel = "k_box_stream<4> PRGB32 pattern (aligned, repeat), 64 MiB source"
+            kernel = "k_stream_one<pattern32> (stream.cu), PRGB32 pattern aligned + repeat, 64 MiB source"
             extra = 4.0
         rec.fill_all()
         batch = G.ResidentBatch(rt._h, rec.peek_batch())

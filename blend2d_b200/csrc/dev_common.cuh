@@ -13,7 +13,7 @@
 // Cold paths (rare operators, dithering, patterns, 64-bit dividers) are kept OUT of line on the device: the tile
 // compositor's hot loop has to fit the SM's 32 KB L1.5 instruction cache (ncu round 1: 43 % of its stall samples
 // were stall_no_inst while everything was inlined into an 11.7 K-instruction kernel).
-#  define B2D_HD_COLD __host__ __device__ __noinline__
+#  define B2D_HD_COLD inline __host__ __device__ __noinline__
 #else
 #  define B2D_HD inline
 #  define B2D_D  inline

@@ -1021,7 +1021,9 @@ uint32_t current_state(b2d_context* c, const Matrix& m, uint32_t transform_type)
 // 1032-1070): every figure starts at a MOVE, is implicitly closed, and curve commands need all of their vertices.
 b2dgpu_result fill_path_segments(b2d_context* c, const Resolved& r, const uint8_t* cmd, const double* vtx, uint32_t n,
                                  const Matrix& m, uint32_t transform_type, uint32_t fill_rule) {
-  if (c->vtx.size() / 2 + n > 0x3FFFFFF0u) { b2dgpu_result fr = flush_batch(c); if (fr) return fr; }
+  // The style was resolved into this batch already (r.fetch_index), so the batch cannot be flushed here; 2^30 vertices
+  // (16 GiB) in one batch is not a workload, it is an error.
+  if (c->vtx.size() / 2 + n > 0x3FFFFFF0u) return B2DGPU_ERROR_OUT_OF_MEMORY;
   uint32_t base = uint32_t(c->vtx.size() / 2);
   uint32_t seg_begin = uint32_t(c->segs.size());
   uint32_t cmd_index = uint32_t(c->cmds.size());

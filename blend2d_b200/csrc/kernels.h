@@ -65,6 +65,20 @@ struct SolidStreamParams {
   unsigned long long* pixel_counter;
 };
 
+// One FillBoxA with a gradient / pattern source over a large region of a 32-bit target: see stream.cu (k_stream_one).
+struct StreamOneParams {
+  uint8_t* dst;                           // first byte of row `y_begin`
+  intptr_t dst_stride;
+  int y_begin;
+  int x0, y0, x1, y1;                     // the box in pixels, clipped to the target (y absolute)
+  uint32_t fetch_type, src_format, comp_op, alpha;
+  const b2dgpu_fetch_data* fd;            // device copy of the command's FetchData
+  const uint8_t* bayer;
+  int origin_x, origin_y;
+  unsigned long long pixels;
+  unsigned long long* pixel_counter;
+};
+
 // Each launcher returns the number of kernels it launched.
 int launch_count_edges(const BuildParams& P, cudaStream_t s);
 int launch_write_edges(const BuildParams& P, cudaStream_t s);
@@ -78,5 +92,6 @@ int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaSt
 int launch_tile_render(const TileParams& P, int bpp, int tile_h, cudaStream_t s);
 int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
 int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s);
+int launch_stream_one(const StreamOneParams& P, int sm_count, cudaStream_t s);
 
 } // namespace b2d

@@ -140,7 +140,8 @@ struct BlockLayout {
 };
 
 // A batch that is a single solid box fill (fill_all, clear_all, one big FillRectA).
-struct SolidFill { bool ok; int box[4]; uint32_t comp_op, alpha, prgb32; };
+// `one`: the batch is a single FillBoxA with SrcOver / SrcCopy, any source (k_stream_one); `ok`: ... with a solid source.
+struct SolidFill { bool ok, one; int box[4]; uint32_t comp_op, alpha, prgb32, fetch_type, src_format, fetch_index; };
 
 struct b2dgpu_batch {
   b2dgpu_runtime* rt;
@@ -371,6 +372,13 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
 extern "C" b2dgpu_result b2dgpu_sync(b2dgpu_runtime* rt) {
   if (!rt || rt->magic != kRuntimeMagic) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_sync: invalid runtime");
   CU_TRY(cudaStreamSynchronize(rt->stream));
+  // The edge writer raises a flag instead of writing past the edge buffer (k_write_edges); surface it here.
+  uint32_t flag = 0;
+  CU_TRY(cudaMemcpy(&flag, rt->d_scalars + 1, 4, cudaMemcpyDeviceToHost));
+  if (flag) {
+    CU_TRY(cudaMemset(rt->d_scalars + 1, 0, 4));
+    return fail(B2DGPU_ERROR_INVALID_STATE, "b2dgpu_sync: the device edge builder ran out of edge storage; the last render is incomplete");
+  }
   return B2DGPU_SUCCESS;
 }
 
@@ -562,10 +570,13 @@ static SolidFill detect_solid_fill(const b2dgpu_batch_view* v) {
   if (v->command_count != 1) return f;
   const b2dgpu_command& c = v->commands[0];
   const uint32_t op = B2DGPU_SIG_COMP_OP(c.signature);
-  if (c.type != B2DGPU_CMD_FILL_BOX_A || B2DGPU_SIG_FETCH_TYPE(c.signature) != B2DGPU_FETCH_SOLID) return f;
+  if (c.type != B2DGPU_CMD_FILL_BOX_A) return f;
   if (op != 0u /* SrcOver */ && op != 1u /* SrcCopy */) return f;
   if (c.alpha == 0) return f;
-  f.ok = true; memcpy(f.box, c.box, sizeof(f.box)); f.comp_op = op; f.alpha = c.alpha; f.prgb32 = c.solid_prgb32;
+  memcpy(f.box, c.box, sizeof(f.box)); f.comp_op = op; f.alpha = c.alpha; f.prgb32 = c.solid_prgb32;
+  f.fetch_type = B2DGPU_SIG_FETCH_TYPE(c.signature); f.src_format = B2DGPU_SIG_SRC_FORMAT(c.signature); f.fetch_index = c.fetch_index;
+  f.ok = f.fetch_type == B2DGPU_FETCH_SOLID;
+  f.one = !f.ok;
   return f;
 }
 
@@ -574,6 +585,9 @@ struct FetchUse { uint32_t fetch_type; uint32_t src_format; bool used; };
 static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
   if (!v || v->struct_size < sizeof(b2dgpu_batch_view)) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: bad struct_size");
   if (v->command_count && !v->commands) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: commands is null");
+  if ((v->fetch_count && !v->fetch_data) || (v->edge_count && !v->edges) || (v->vertex_count && !v->vertices) ||
+      (v->segment_count && !v->segments) || (v->geometry_state_count && !v->geometry_states))
+    return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: a non-empty array is null");
   for (uint32_t i = 0; i < v->command_count; i++) {
     const b2dgpu_command& c = v->commands[i];
     if (c.type < B2DGPU_CMD_FILL_BOX_A || c.type > B2DGPU_CMD_FILL_BOX_MASK_A) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: unknown command type");
@@ -602,6 +616,11 @@ static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
     uint32_t extra = kind == B2DGPU_SEG_LINE ? 0u : kind == B2DGPU_SEG_QUAD ? 1u : 2u;
     if (s.p0 >= v->vertex_count || uint64_t(i1) + extra >= v->vertex_count || s.command >= v->command_count)
       return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment references out of range");
+    // The device edge builder reads the geometry state of the segment's command and accumulates the command's bounding
+    // box: the segment has to lie inside the range of a FILL_GEOMETRY command (whose state_index was checked above).
+    const b2dgpu_command& c = v->commands[s.command];
+    if (c.type != B2DGPU_CMD_FILL_GEOMETRY || i < c.data_offset || uint64_t(i) >= uint64_t(c.data_offset) + c.data_count)
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment does not belong to the geometry command it names");
   }
   return B2DGPU_SUCCESS;
 }
@@ -946,6 +965,17 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
         S.pixels = (unsigned long long)(box[2] - box[0]) * (unsigned long long)(box[3] - box[1]);
         S.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
         launches += launch_stream_solid(S, rt->sm_count, s);
+      }
+      else if (in.solid.one && t->bpp == 4) {
+        StreamOneParams S;
+        S.dst = t->d_pixels; S.dst_stride = intptr_t(t->stride); S.y_begin = t->y0;
+        S.x0 = box[0]; S.y0 = box[1]; S.x1 = box[2]; S.y1 = box[3];
+        S.fetch_type = in.solid.fetch_type; S.src_format = in.solid.src_format; S.comp_op = in.solid.comp_op; S.alpha = in.solid.alpha;
+        S.fd = T.fetch_data + in.solid.fetch_index;
+        S.bayer = rt->d_bayer; S.origin_x = in.origin_x; S.origin_y = in.origin_y;
+        S.pixels = (unsigned long long)(box[2] - box[0]) * (unsigned long long)(box[3] - box[1]);
+        S.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
+        launches += launch_stream_one(S, rt->sm_count, s);
       }
       else launches += launch_box_stream(T, t->bpp, box, rt->sm_count, s);
       streamed = true;

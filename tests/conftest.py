@@ -14,7 +14,11 @@ def pytest_configure(config):
     # every test at import time.  __graft_entry__.build() does the same and more.
     if not os.path.exists(os.path.join(ROOT, "blend2d_b200", "libb2dgpu.so")):
         import subprocess
-        subprocess.check_call(["make", "-s", "-C", ROOT])
+        try:
+            subprocess.check_call(["make", "-s", "-C", ROOT])
+        except (OSError, subprocess.CalledProcessError) as e:
+            # no nvcc here: the tests that load the library fail at their own import, the oracle / table tests still run
+            sys.stderr.write("conftest: could not build libb2dgpu.so (%s)\n" % e)
 
 
 @pytest.fixture(scope="session")

@@ -104,6 +104,40 @@ def test_streaming_box_fills(ref, gpu, style, tol, fmt, op):
     compare(ref, gpu, big_box_scene(style, op), 1403, 1001, fmt, max_diff=tol)
 
 
+def one_box_scene(style, extend, op, alpha, rect):
+    """Batches of ONE large box fill with a nearest-neighbour gradient or an aligned pattern: k_stream_one (stream.cu)."""
+    def scene(api, ctx, rng):
+        W, H = ctx.image.w, ctx.image.h
+        ctx.set_fill_style(0xFF203040); ctx.fill_all(); ctx.flush()
+        ctx.set_comp_op(op); ctx.set_global_alpha(alpha)
+        if style == "pattern":
+            tex = S.make_texture(api, 333, 217, 1, 11)
+            ctx._scene_keep = tex
+            ctx.set_fill_style(api.Pattern(tex, None, extend, [1, 0, 0, 1, 37.0, 21.0]))
+        elif style == "pattern_x":
+            tex = S.make_texture(api, 256, 128, 2, 12)
+            ctx._scene_keep = tex
+            ctx.set_fill_style(api.Pattern(tex, None, extend, [1, 0, 0, 1, -40.0, -9.0]))
+        else:
+            ctx.set_fill_style(S.make_gradient(api, rng, {"linear": 0, "radial": 1, "conic": 2}[style], extend, 100.0, 50.0, 700.0, 500.0))
+        if rect == "all":
+            ctx.fill_all()
+        else:
+            ctx.fill_rect_i(*rect)
+        ctx.flush()
+        ctx.set_global_alpha(1.0); ctx.set_comp_op(S.SRC_OVER)
+        ctx.set_fill_style(0x40808080); ctx.fill_rect_i(1, 2, W - 2, H - 3)
+    return scene
+
+
+@pytest.mark.parametrize("style,tol", [("linear", 0), ("radial", 0), ("conic", 1), ("pattern", 0), ("pattern_x", 0)])
+@pytest.mark.parametrize("extend", [0, 1, 2])
+@pytest.mark.parametrize("op,alpha", [(S.SRC_OVER, 1.0), (S.SRC_OVER, 0.4), (S.SRC_COPY, 1.0), (S.SRC_COPY, 0.7)])
+@pytest.mark.parametrize("rect", ["all", (5, 3, 1391, 995)])
+def test_streaming_one_box(ref, gpu, style, tol, extend, op, alpha, rect):
+    compare(ref, gpu, one_box_scene(style, extend, op, alpha, rect), 1403, 1001, 1, max_diff=tol)
+
+
 def solid_stream_scene(op, alpha, rect):
     """Batches of ONE solid box fill over > 1 Mpx, flushed one by one: the streaming solid kernel (k_stream_solid)."""
     def scene(api, ctx, rng):

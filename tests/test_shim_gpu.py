@@ -117,6 +117,22 @@ def test_blit_image(B):
     assert_same(cpu, gpu)
 
 
+def test_large_blit_streams(B):
+    """blit_image of a large image as its own batch (k_stream_one, FetchPatternAlignedBlit), at offsets that break the
+    16-byte alignment of the source rows, then with a global alpha and a sub-area."""
+    def scene(api, ctx, rng):
+        tex = S.make_texture(api, 1300, 900, 1, 5)
+        ctx._scene_keep = tex
+        ctx.set_fill_style(0xFF405060); ctx.fill_all(); ctx.flush()
+        ctx.blit_image(51, 33, tex); ctx.flush()
+        ctx.set_global_alpha(0.5)
+        ctx.blit_image(0, 0, tex, (4, 8, 1200, 880)); ctx.flush()
+        ctx.set_comp_op(S.SRC_COPY)
+        ctx.blit_image(64, 0, tex, (0, 0, 1296, 900)); ctx.flush()
+    cpu, gpu = both(B, scene, 1403, 1001)
+    assert_same(cpu, gpu)
+
+
 def test_existing_pixels_and_incremental_flush(B):
     """The canvas starts from the image's pixels; flush(SYNC) in the middle makes the host image coherent."""
     rng = np.random.default_rng(2)
