@@ -329,7 +329,15 @@ B2D_HD uint32_t fetch_pixel(const FetchEnv& env, const RowCtx& rc, uint32_t x, u
 
 // Everything that is not a solid colour or a nearest-neighbour gradient (dithered gradients, all patterns): kept out of
 // line so that the compositor's hot loop stays small (see B2D_HD_COLD).
-B2D_HD_COLD uint32_t fetch_pixel_cold(const FetchEnv& env, uint32_t x, uint32_t y) {
+// Every argument is a scalar: a FetchEnv passed by reference would have to live in local memory in the CALLER's hot
+// loop (ncu round 2: five STL per replayed command in k_tile_render just to keep it addressable).
+B2D_HD_COLD uint32_t fetch_pixel_cold(const b2dgpu_fetch_data* fd, const uint8_t* bayer, uint32_t type_and_format, int origin_x, int origin_y,
+                                      uint32_t x, uint32_t y) {
+  FetchEnv env;
+  env.fd = fd; env.bayer = bayer;
+  env.fetch_type = type_and_format & 0xFFu; env.src_format = type_and_format >> 8;
+  env.solid = 0;
+  env.origin_x = origin_x; env.origin_y = origin_y;
   RowCtx rc;
   fetch_row_init(env, y, rc);
   return fetch_pixel(env, rc, x, y);
@@ -423,7 +431,7 @@ B2D_HD void fetch4(const FetchEnv& env, uint32_t x, uint32_t y, const uint32_t* 
   }
   #pragma unroll
   for (int i = 0; i < 4; i++)
-    if (m[i]) s[i] = fetch_pixel_cold(env, x + i, y);
+    if (m[i]) s[i] = fetch_pixel_cold(env.fd, env.bayer, ft | (env.src_format << 8), env.origin_x, env.origin_y, x + i, y);
 }
 
 } // namespace b2d

@@ -339,7 +339,9 @@ struct PreCmdT {
   uint32_t blk_has[(TH + 7) / 8]; // 4 bits per row: block b of the row holds an entry (or the spill of its left neighbour)
   uint32_t flags;               // phase 1 only (atomically updated); the replay reads hdr
   uint32_t warp_mask;           // bit w: warp w's block can receive coverage from this command (0: skipped by the replay)
-  uint32_t pad_[(4 - ((TH + 7) / 8 + 2) % 4) % 4];
+  uint32_t wrec4[TH / 4];       // one byte per warp: the mask of EVERY pixel of the warp's block when it is the same for all
+                                // of them (interior of a shape, inside of a box), 0 when the block needs the general path
+  uint32_t pad_[(4 - ((TH + 7) / 8 + 2 + TH / 4) % 4) % 4];
   // What the replay needs of the command, decoded once by phase 1 (two 16-byte shared-memory loads per iteration):
   //   [0] type | flags << 8   [1] alpha   [2] fill rule mask   [3] solid colour
   //   [4] fetch type | comp op << 8 | source format << 16   [5] right end of the clipped box   [6,7] FetchData pointer
@@ -638,26 +640,43 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           }
         }
 
-        // Which warps of the replay does this command concern?  Lane w answers for warp w = block (w / 4, w % 4).
+        // Which warps of the replay does this command concern, and how?  Lane w answers for warp w = block (w / 4, w % 4):
+        // skipped (nothing to composite), uniform (every pixel of the block has the same mask: the inside of a shape or
+        // of a box - the replay then needs neither the backdrop nor the entries), or general.
         {
           bool any = false;
+          uint32_t uniform_mask = 0;
           if (lane < TH) {
+            const b2dgpu_command& c = *reinterpret_cast<const b2dgpu_command*>(pre->cmd_words);
             const int g = lane % kGroups, b = lane / kGroups;
             const int r0 = g * kBlockRows;
+            const int bxl = tx0 + b * kBlockW;
             const bool rows_in = bbp.y < ty0 + r0 + kBlockRows && bbp.w > ty0 + r0;
-            if (is_box) any = rows_in && bbp.x < tx0 + (b + 1) * kBlockW && bbp.z > tx0 + b * kBlockW;
+            if (is_box) {
+              any = rows_in && bbp.x < bxl + kBlockW && bbp.z > bxl;
+              if (any && c.type == B2DGPU_CMD_FILL_BOX_A && c.box[0] <= bxl && c.box[2] >= bxl + kBlockW &&
+                  c.box[1] <= ty0 + r0 && c.box[3] >= ty0 + r0 + kBlockRows) uniform_mask = c.alpha;
+            }
             else if (pre->flags & kPreOverflow) any = rows_in;          // the four warps of a group meet at a barrier: same answer for all
-            else if (rows_in && bbp.z > tx0 + b * kBlockW) {
+            else if (rows_in && bbp.z > bxl) {
+              bool uni = bbp.z >= bxl + kBlockW;                        // the clipped box does not end inside the block
+              uint32_t m0 = 0;
               #pragma unroll
               for (int r = r0; r < r0 + kBlockRows; r++) {
                 const uint4 c4 = pre->carry4[r];
                 const uint32_t carry = pre->carry_left[r] + c4.x + (b >= 1 ? c4.y : 0u) + (b >= 2 ? c4.z : 0u) + (b >= 3 ? c4.w : 0u);
-                any = any || carry != 0u || ((pre->blk_has[r >> 3] >> ((r & 7) * 4 + b)) & 1u);
+                const bool has = (pre->blk_has[r >> 3] >> ((r & 7) * 4 + b)) & 1u;
+                const uint32_t mr = calc_mask((256u << 9) + carry, c.fill_rule_mask, c.alpha);
+                any = any || has || mr != 0u;
+                uni = uni && !has && (r == r0 || mr == m0);
+                if (r == r0) m0 = mr;
               }
+              if (any && uni) uniform_mask = m0;
             }
           }
           const uint32_t wm = __ballot_sync(0xFFFFFFFFu, any);
           if (lane == 0) { pre->warp_mask = wm; s_wmask[k] = wm; }
+          if (lane < TH) reinterpret_cast<uint8_t*>(pre->wrec4)[lane] = uint8_t(uniform_mask);
         }
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
         uint32_t nk = 0;
@@ -671,6 +690,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       #pragma unroll 1
       for (uint32_t kb = 0; kb < sub_n; kb += 32) {
       uint32_t act = __ballot_sync(0xFFFFFFFFu, kb + uint32_t(lane) < sub_n && ((s_wmask[min(kb + uint32_t(lane), uint32_t(kSub - 1))] >> warp) & 1u));
+      dirty = dirty || act != 0u;                       // warp uniform: the block is stored if any command concerned it
       while (act) {
         const uint32_t k = kb + uint32_t(__ffs(act) - 1);
         act &= act - 1;
@@ -681,7 +701,15 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         const uint32_t type = h0.x & 0xFFu;
         const uint32_t alpha = h0.y;
         uint32_t m[4] = { 0, 0, 0, 0 };
+        bool opaque;
+        const uint32_t uniform_mask = reinterpret_cast<const uint8_t*>(pre.wrec4)[warp];
 
+        if (uniform_mask) {
+          // The whole block lies inside the shape (FillAnalytic's CMask spans, fillgeneric_p.h:300-330) or the box.
+          m[0] = m[1] = m[2] = m[3] = uniform_mask;
+          opaque = uniform_mask == 255u;
+        }
+        else {
         if (type == B2DGPU_CMD_FILL_BOX_A) {
           // FillBoxA_Base (fillgeneric_p.h:22-65): constant mask inside the box.
           if (py >= cmd.box[1] && py < cmd.box[3]) {
@@ -707,7 +735,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             const uint32_t carry = (256u << 9) + pre.carry_left[row] + c4.x + (blk >= 1 ? c4.y : 0u) + (blk >= 2 ? c4.z : 0u) + (blk >= 3 ? c4.w : 0u);
             const bool has = (pre.blk_has[row >> 3] >> ((row & 7) * 4 + blk)) & 1u;
             if (!__any_sync(0xFFFFFFFFu, has)) {
-              // No edge inside the block: coverage is constant along each of its rows (FillAnalytic's CMask spans).
+              // No edge inside the block: coverage is constant along each of its rows.
               const uint32_t mm = calc_mask(carry, rule, alpha);
               m[0] = mm; m[1] = mm; m[2] = mm; m[3] = mm;
             }
@@ -760,10 +788,13 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             for (int i = 0; i < 4; i++) if (px + i >= bx1) m[i] = 0;
           }
         }
-
-        // ---- fetch + composite ----
         // The votes keep every branch warp-uniform, so the lanes stay converged for the next iteration.
         if (!__any_sync(0xFFFFFFFFu, (m[0] | m[1] | m[2] | m[3]) != 0u)) continue;
+        const uint32_t not_opaque = ((m[0] + 1u) | (m[1] + 1u) | (m[2] + 1u) | (m[3] + 1u)) & 0xFEu;
+        opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
+        }
+
+        // ---- fetch + composite ----
         FetchEnv env;
         env.fetch_type = h1.x & 0xFFu;
         env.src_format = h1.x >> 16;
@@ -772,8 +803,6 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         env.bayer = P.bayer;
         env.origin_x = P.origin_x; env.origin_y = P.origin_y;
         const uint32_t comp_op = (h1.x >> 8) & 0xFFu;
-        const uint32_t not_opaque = ((m[0] + 1u) | (m[1] + 1u) | (m[2] + 1u) | (m[3] + 1u)) & 0xFEu;
-        const bool opaque = __all_sync(0xFFFFFFFFu, not_opaque == 0u);
         uint32_t s[4] = { 0, 0, 0, 0 };
         RowCtx3 rc3;
         rc3.a = pre.rowctx[row][0]; rc3.b = pre.rowctx[row][1]; rc3.c = pre.rowctx[row][2];
@@ -784,7 +813,6 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         }
         composite4(comp_op, d, s, m, opaque);
         if (count_pixels) px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
-        dirty = true;
       }
       }
     }
