@@ -5,7 +5,7 @@
 //                                    give every command a contiguous, deterministic edge range.
 //   K1b k_scan_*                     exclusive prefix sum of the per-segment edge counts.
 //   K1c k_analytic_bbox / k_finalize_commands   per-command pixel bounding boxes used for tile culling.
-//   K1d k_band_extents               per (tile row, command) column extents of the command's edges (tile culling).
+//   K1d k_bin_*                      per-band ordered command lists + per (band, command) column extents (tile culling).
 //   K2+K3 k_tile_render<BPP,TH>      one CTA of TH warps per 128 x TH destination tile, a warp per block of 32 columns x
 //                                    4 rows.  The tile's pixels are loaded ONCE into registers (16-byte vector loads),
 //                                    every command that touches the tile is replayed in submission order - phase 1: a
@@ -254,14 +254,21 @@ __global__ void k_finalize_commands(FinalizeParams P) {
 }
 
 // =================================================================================================================
-// K1d - per (command, band) x-extents
+// K1d - binning: per-band command lists with x-extents
 //
-// A band is one tile row (kTileH scanlines).  For every band a command's bounding box covers, the columns its edges
-// can touch inside that band are recorded as (min cell x, ~max cell x).  The compositor culls (tile, command) pairs
-// with it: a tile left of the extent sees nothing, a tile right of it sees every edge of the band on its left, and
-// the covers of a closed outline sum to zero on every scanline (EdgeBuilder closes figures and keeps clipped parts as
-// border lines, edgebuilder_p.h:1058-1062, 2546-2622) - so both are skipped.  This replaces the reference's per-band
-// edge lists (edgestorage_p.h:38-178) as the structure that keeps work proportional to the shape, not to its box.
+// A band is one tile row (tile_h scanlines).  Band b gets the ordered list of the commands whose pixel box covers it,
+// and every (band, command) cell records the columns the command can touch inside that band: a box fill its box, a
+// shape the union of its edges' extents there.  The compositor culls with it: a tile left of the extent sees nothing, a
+// tile right of it sees every edge of the band on its left, and the covers of a closed outline sum to zero on every
+// scanline (EdgeBuilder closes figures and keeps clipped parts as border lines, edgebuilder_p.h:1058-1062, 2546-2622)
+// - so both are skipped.  This is what the reference's per-band edge lists (edgestorage_p.h:38-178) and its band-by-
+// band command walk (workerproc.cpp:166-255) achieve on the CPU: a tile looks at the commands of its band, not at the
+// whole batch, and work follows the shape, not its bounding box.
+//
+//   k_bin_count    thread per command: bands covered -> cm_count, band_count (atomics)
+//   scans          cm_base, band_off; k_bin_check compares the total with the buffer capacity
+//   k_bin_fill     CTA per band: order-preserving compaction of the band's commands into its cells
+//   k_bin_extents  warp per command: (edge, band) extents into the cells (atomic min / max)
 // =================================================================================================================
 __device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, uint32_t index) {
   int4 ev = __ldg(edges + index);
@@ -269,30 +276,79 @@ __device__ __forceinline__ NormEdge load_edge(const int4* __restrict__ edges, ui
   return normalize_edge(raw);
 }
 
-__global__ void __launch_bounds__(256) k_band_extents(TileParams P, uint2* __restrict__ band_ext, int tile_h) {
+__global__ void __launch_bounds__(256) k_bin_count(BinParams B) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= B.command_count) return;
+  const int4 bb = B.cmd_bbox_px[c];
+  uint32_t nb = 0;
+  if (bb.x < bb.z && bb.y < bb.w) {
+    const int band0 = (bb.y - B.y_begin) / B.tile_h, band1 = (bb.w - 1 - B.y_begin) / B.tile_h;
+    nb = uint32_t(band1 - band0 + 1);
+    for (int b = band0; b <= band1; b++) atomicAdd(B.band_count + b, 1u);
+  }
+  B.cm_count[c] = nb;
+}
+
+__global__ void k_bin_check(BinParams B) {
+  const uint32_t total = B.cm_base[B.command_count];
+  B.state[0] = total;
+  B.state[1] = total <= B.capacity ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_bin_fill(BinParams B) {
+  if (!B.state[1]) return;
+  __shared__ uint32_t s_w[8];
+  const int b = blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int by0 = B.y_begin + b * B.tile_h, by1 = by0 + B.tile_h;
+  uint32_t run = B.band_off[b];
+  for (uint32_t base = 0; base < B.command_count; base += 256) {
+    const uint32_t c = base + threadIdx.x;
+    bool hit = false;
+    int4 bb = make_int4(0, 0, 0, 0);
+    if (c < B.command_count) {
+      bb = B.cmd_bbox_px[c];
+      hit = bb.x < bb.z && bb.y < by1 && bb.w > by0;
+    }
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+    if (lane == 0) s_w[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+    #pragma unroll
+    for (uint32_t w = 0; w < 8; w++) { const uint32_t n = s_w[w]; if (w < warp) wbase += n; total += n; }
+    if (hit) {
+      const uint32_t pos = run + wbase + __popc(ballot & ((1u << lane) - 1u));
+      B.cell_cmd[pos] = c;
+      // a box's pixel box is exact; a shape starts empty and k_bin_extents widens it
+      B.cell_ext[pos] = command_has_edges(B.commands[c].type) ? make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(uint32_t(bb.x), ~uint32_t(bb.z - 1));
+      B.cm_index[B.cm_base[c] + uint32_t(b - (bb.y - B.y_begin) / B.tile_h)] = pos;
+    }
+    run += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_extents(BinParams B) {
+  if (!B.state[1]) return;
   const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  if (c >= P.command_count) return;
-  const int4 bb = P.cmd_bbox_px[c];
+  if (c >= B.command_count) return;
+  const int4 bb = B.cmd_bbox_px[c];
   if (bb.x >= bb.z || bb.y >= bb.w) return;
-  const int band0 = (bb.y - P.y_begin) / tile_h, band1 = (bb.w - 1 - P.y_begin) / tile_h;
-  uint32_t* ext = reinterpret_cast<uint32_t*>(band_ext);
-  if (!command_has_edges(P.commands[c].type)) {
-    for (int b = band0 + int(lane); b <= band1; b += 32)
-      band_ext[size_t(b) * P.command_count + c] = make_uint2(0u, 0u);               // every column
-    return;
-  }
-  const uint2 er = P.cmd_edges[c];
-  const int4* __restrict__ edges = reinterpret_cast<const int4*>(P.edges);
+  if (!command_has_edges(B.commands[c].type)) return;
+  const int band0 = (bb.y - B.y_begin) / B.tile_h;
+  const uint32_t* __restrict__ index = B.cm_index + B.cm_base[c];
+  const uint2 er = B.cmd_edges[c];
+  const int4* __restrict__ edges = reinterpret_cast<const int4*>(B.edges);
   for (uint32_t e = lane; e < er.y; e += 32) {
     const NormEdge ne = load_edge(edges, er.x + e);
     if (ne.y0 == ne.y1) continue;
     const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
     if (row_first > row_last) continue;
-    for (int b = (row_first - P.y_begin) / tile_h; b <= (row_last - P.y_begin) / tile_h; b++) {
+    for (int b = (row_first - B.y_begin) / B.tile_h; b <= (row_last - B.y_begin) / B.tile_h; b++) {
       int lo, hi;
-      band_edge_extent(ne, P.y_begin + b * tile_h, lo, hi, tile_h);
-      uint32_t* cell = ext + (size_t(b) * P.command_count + c) * 2;
+      band_edge_extent(ne, B.y_begin + b * B.tile_h, lo, hi, B.tile_h);
+      uint32_t* cell = reinterpret_cast<uint32_t*>(B.cell_ext + index[b - band0]);
       atomicMin(cell, uint32_t(lo));
       atomicMin(cell + 1, ~uint32_t(hi));
     }
@@ -498,17 +554,25 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
   // pending (or the command list ends) they are classified (phase 1) and replayed (phase 2).
   uint32_t ring_head = 0, ring_tail = 0;                // block-uniform
-  for (uint32_t base = 0; base < P.command_count || ring_head != ring_tail; base += kThreads) {
-    // ---- cull: which of the next kThreads commands touch this tile? (order preserving compaction) ----
-    if (base < P.command_count) {
-      uint32_t c = base + tid;
+  // The commands to look at: the band's list (k_bin_*), or - when the lists were not built - every command.
+  const bool binned = P.bin_state != nullptr && P.bin_state[1] != 0u;
+  const uint32_t list_begin = binned ? P.band_off[tile_y] : 0u;
+  const uint32_t list_count = binned ? P.band_off[tile_y + 1] - list_begin : P.command_count;
+  for (uint32_t base = 0; base < list_count || ring_head != ring_tail; base += kThreads) {
+    // ---- cull: which of the next kThreads candidates touch this tile? (order preserving compaction) ----
+    if (base < list_count) {
+      uint32_t c = 0;
       bool hit = false;
-      if (c < P.command_count) {
-        int4 bb = P.cmd_bbox_px[c];
-        hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + TH && bb.w > ty0;
-        if (hit && P.band_ext) {
-          const uint2 ex = P.band_ext[size_t(tile_y) * P.command_count + c];
+      if (base + tid < list_count) {
+        if (binned) {
+          const uint2 ex = P.cell_ext[list_begin + base + tid];
           hit = uint32_t(tx0 + kTileW) > ex.x && uint32_t(tx0) <= ~ex.y;
+          c = P.cell_cmd[list_begin + base + tid];
+        }
+        else {
+          c = base + tid;
+          int4 bb = P.cmd_bbox_px[c];
+          hit = bb.x < tx0 + kTileW && bb.z > tx0 && bb.y < ty0 + TH && bb.w > ty0;
         }
       }
       uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
@@ -525,7 +589,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       if (hit) s_list[(ring_tail + wbase + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1)] = c;
       ring_tail += total;
     }
-    const bool last = base + kThreads >= P.command_count;
+    const bool last = base + kThreads >= list_count;
 
     while (ring_tail - ring_head >= uint32_t(kSub) || (last && ring_tail != ring_head)) {
       const uint32_t sub = ring_head;
@@ -1117,10 +1181,22 @@ int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s
   return 1;
 }
 
-int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaStream_t s) {
-  if (!P.command_count) return 0;
-  k_band_extents<<<div_up(P.command_count * 32, 256), 256, 0, s>>>(P, band_ext, tile_h);
-  return 1;
+size_t bin_scratch_items(uint32_t command_count, int tiles_y) {
+  return scan_scratch_items(command_count) + scan_scratch_items(uint32_t(tiles_y)) + 16;
+}
+
+int launch_binning(const BinParams& B, cudaStream_t s) {
+  if (!B.command_count || B.tiles_y <= 0) return 0;
+  int launches = 0;
+  cudaMemsetAsync(B.band_count, 0, sizeof(uint32_t) * (size_t(B.tiles_y) + 1), s);
+  k_bin_count<<<div_up(B.command_count, 256), 256, 0, s>>>(B);
+  launches += 1;
+  launches += launch_exclusive_scan(B.cm_count, B.cm_base, B.command_count, B.scan_scratch, nullptr, s);
+  launches += launch_exclusive_scan(B.band_count, B.band_off, uint32_t(B.tiles_y), B.scan_scratch + scan_scratch_items(B.command_count), nullptr, s);
+  k_bin_check<<<1, 1, 0, s>>>(B);
+  k_bin_fill<<<B.tiles_y, 256, 0, s>>>(B);
+  k_bin_extents<<<div_up(B.command_count * 32, 256), 256, 0, s>>>(B);
+  return launches + 3;
 }
 
 // Tile height for a target of `rows` rows and `tiles_x` tile columns: 32-row tiles (one 32-warp CTA per SM, the

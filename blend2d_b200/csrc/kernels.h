@@ -43,14 +43,41 @@ struct TileParams {
   uint32_t command_count;
   const int4* cmd_bbox_px;
   const uint2* cmd_edges;
-  const uint2* band_ext;                  // [tile row][command]: (min cell x, ~max cell x) of the command's edges in that
-                                          // band of 8 rows; nullptr = not built (cull by bounding box only)
+  // Per-band command lists (k_bin_*): band b owns cells [band_off[b], band_off[b + 1]) in submission order; a cell is
+  // (command index, (min cell x, ~max cell x) of what the command can touch in that band).  bin_state[1] == 0: the lists
+  // did not fit their buffer and were not built - the compositor then scans every command (bounding boxes only).
+  const uint32_t* band_off;
+  const uint32_t* cell_cmd;
+  const uint2* cell_ext;
+  const uint32_t* bin_state;              // [0] cells needed, [1] lists valid; nullptr = no lists
   const b2dgpu_edge* edges;
   const b2dgpu_fetch_data* fetch_data;
   const uint8_t* bayer;
   int origin_x, origin_y;
   unsigned long long* pixel_counter;
 };
+
+// Binning (K1d): per-band ordered command lists with x-extents, the GPU form of the reference's per-band edge lists
+// (raster/edgestorage_p.h:38-178) and of its band-by-band command walk (raster/workerproc.cpp:166-255).
+struct BinParams {
+  const b2dgpu_command* commands;
+  uint32_t command_count;
+  const int4* cmd_bbox_px;
+  const uint2* cmd_edges;
+  const b2dgpu_edge* edges;
+  int y_begin, tile_h, tiles_y;
+  uint32_t* cm_count;                     // per command: bands its pixel box covers           (command_count + 1)
+  uint32_t* cm_base;                      // exclusive scan of cm_count                        (command_count + 1)
+  uint32_t* band_count;                   // per band: commands whose pixel box covers it      (tiles_y + 1)
+  uint32_t* band_off;                     // exclusive scan of band_count                      (tiles_y + 1)
+  uint32_t* cm_index;                     // [cm_base[c] + band - first band of c] -> cell     (capacity)
+  uint32_t* cell_cmd;                     // band-major cells                                  (capacity)
+  uint2* cell_ext;                        //                                                   (capacity)
+  uint32_t capacity;
+  uint32_t* state;                        // [0] cells needed, [1] lists valid
+  uint32_t* scan_scratch;
+};
+size_t bin_scratch_items(uint32_t command_count, int tiles_y);
 
 // One solid box fill over a large region (fill_all / clear_all / big FillRectA): pure streaming, see k_stream_solid.
 struct SolidStreamParams {
@@ -88,7 +115,7 @@ int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
 int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);
 int choose_tile_height(int tiles_x, int rows, int sm_count);
-int launch_band_extents(const TileParams& P, uint2* band_ext, int tile_h, cudaStream_t s);
+int launch_binning(const BinParams& B, cudaStream_t s);
 int launch_tile_render(const TileParams& P, int bpp, int tile_h, cudaStream_t s);
 int launch_box_stream(const TileParams& P, int bpp, const int* box, int sm_count, cudaStream_t s);
 int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s);

@@ -110,7 +110,9 @@ struct b2dgpu_runtime {
   int slot_next;
   cudaEvent_t prep_ready;
   DevBuffer oneshot_edges;
-  DevBuffer band_ext;                       // [tile row][command] x-extents (k_band_extents), rebuilt by every render
+  DevBuffer bins;                           // per-band command lists (k_bin_*), rebuilt by every render
+  uint32_t bin_capacity;                    // cells the lists can hold; grown when a render reports that it needed more
+  uint32_t* h_bin_state;                    // pinned: [0] cells the last render needed, [1] whether its lists were built
   PinnedBuffer image_staging;
 
   b2dgpu_stats stats;
@@ -286,6 +288,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->slot_done[0] = rt->slot_done[1] = nullptr; rt->slot_busy[0] = rt->slot_busy[1] = false;
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
+  rt->bin_capacity = 0; rt->h_bin_state = nullptr;
   rt->profiling = false;
   rt->count_pixels = true;
   rt->sm_count = 148;
@@ -307,10 +310,12 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
       (e = cudaMemset(rt->d_pixel_counter, 0, 8)) != cudaSuccess ||
       (e = cudaMalloc((void**)&rt->d_scalars, 64)) != cudaSuccess ||
       (e = cudaMemset(rt->d_scalars, 0, 64)) != cudaSuccess ||
-      (e = cudaMallocHost((void**)&rt->h_scalars, 64)) != cudaSuccess) {
+      (e = cudaMallocHost((void**)&rt->h_scalars, 64)) != cudaSuccess ||
+      (e = cudaMallocHost((void**)&rt->h_bin_state, 16)) != cudaSuccess) {
     b2dgpu_runtime_destroy(rt);
     return cuda_fail(e, "b2dgpu_runtime_create: device allocation");
   }
+  rt->h_bin_state[0] = 0; rt->h_bin_state[1] = 1;
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
@@ -362,7 +367,8 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   rt->oneshot_block[0].release();
   rt->oneshot_block[1].release();
   rt->oneshot_edges.release();
-  rt->band_ext.release();
+  rt->bins.release();
+  if (rt->h_bin_state) cudaFreeHost(rt->h_bin_state);
   if (rt->own_stream) cudaStreamDestroy(rt->stream);
   rt->magic = 0;
   delete rt;
@@ -929,19 +935,54 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   T.origin_x = in.origin_x;
   T.origin_y = in.origin_y;
   T.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
-  T.band_ext = nullptr;
-  // Per (band, command) x-extents: only worth building when some command has edges (a box's bounding box is exact) and
-  // while the table stays small (8 B per cell; 10 000 commands on a 4K canvas = 21.6 MB).
-  const size_t band_cells = size_t(in.command_count) * size_t(T.tiles_y);
-  if ((in.has_analytic || in.segment_count) && band_cells <= (size_t(64) << 20)) {
-    const size_t need = band_cells * sizeof(uint2);
-    if (need > rt->band_ext.cap) {
+  T.band_off = nullptr; T.cell_cmd = nullptr; T.cell_ext = nullptr; T.bin_state = nullptr;
+  // Per-band command lists with x-extents (k_bin_*).  Their size is only known on the device: the buffer holds
+  // `bin_capacity` cells (the dense bound tiles_y * commands when that is small); a render that needed more renders
+  // without lists (every tile scans every command - slow but correct) and the buffer is grown for the next one.
+  {
+    const size_t dense = size_t(in.command_count) * size_t(T.tiles_y);
+    if (rt->h_bin_state[1] == 0u && rt->h_bin_state[0] > rt->bin_capacity)
+      rt->bin_capacity = rt->h_bin_state[0] + rt->h_bin_state[0] / 4u;                    // reported by an earlier render
+    size_t want = rt->bin_capacity;
+    const size_t floor_cells = size_t(4) << 20;
+    if (want < floor_cells) want = floor_cells;
+    if (want < size_t(256) * in.command_count) want = size_t(256) * in.command_count;
+    if (want > dense) want = dense;
+    if (want > 0xFFFFFF00u) want = 0xFFFFFF00u;
+    if (const char* e = getenv("B2DGPU_BIN_CAPACITY")) want = size_t(strtoull(e, nullptr, 10));   // test knob: force the fallback
+    if (want < 1) want = 1;
+    const uint32_t cap = uint32_t(want);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = align_up(off, 256); const size_t o = off; off += bytes; return o; };
+    const size_t o_state = take(16);
+    const size_t o_cm_count = take(sizeof(uint32_t) * (size_t(in.command_count) + 1));
+    const size_t o_cm_base = take(sizeof(uint32_t) * (size_t(in.command_count) + 1));
+    const size_t o_band_count = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 1));
+    const size_t o_band_off = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 1));
+    const size_t o_scratch = take(sizeof(uint32_t) * bin_scratch_items(in.command_count, T.tiles_y));
+    const size_t o_cm_index = take(sizeof(uint32_t) * size_t(cap));
+    const size_t o_cell_cmd = take(sizeof(uint32_t) * size_t(cap));
+    const size_t o_cell_ext = take(sizeof(uint2) * size_t(cap));
+    const size_t need = align_up(off, 256);
+    if (need > rt->bins.cap) {
       CU_TRY(cudaStreamSynchronize(s));
-      CU_TRY(rt->band_ext.ensure(need + need / 4));
+      CU_TRY(rt->bins.ensure(need + need / 4));
     }
-    CU_TRY(cudaMemsetAsync(rt->band_ext.ptr, 0xFF, need, s));
-    launches += launch_band_extents(T, static_cast<uint2*>(rt->band_ext.ptr), tile_h, s);
-    T.band_ext = static_cast<const uint2*>(rt->band_ext.ptr);
+    uint8_t* bp = static_cast<uint8_t*>(rt->bins.ptr);
+    BinParams Bn;
+    Bn.commands = d_cmds; Bn.command_count = in.command_count;
+    Bn.cmd_bbox_px = F.cmd_bbox_px; Bn.cmd_edges = F.cmd_edges; Bn.edges = B.edges;
+    Bn.y_begin = t->y0; Bn.tile_h = tile_h; Bn.tiles_y = T.tiles_y;
+    Bn.state = reinterpret_cast<uint32_t*>(bp + o_state);
+    Bn.cm_count = reinterpret_cast<uint32_t*>(bp + o_cm_count); Bn.cm_base = reinterpret_cast<uint32_t*>(bp + o_cm_base);
+    Bn.band_count = reinterpret_cast<uint32_t*>(bp + o_band_count); Bn.band_off = reinterpret_cast<uint32_t*>(bp + o_band_off);
+    Bn.scan_scratch = reinterpret_cast<uint32_t*>(bp + o_scratch);
+    Bn.cm_index = reinterpret_cast<uint32_t*>(bp + o_cm_index); Bn.cell_cmd = reinterpret_cast<uint32_t*>(bp + o_cell_cmd);
+    Bn.cell_ext = reinterpret_cast<uint2*>(bp + o_cell_ext);
+    Bn.capacity = cap;
+    launches += launch_binning(Bn, s);
+    CU_TRY(cudaMemcpyAsync(rt->h_bin_state, Bn.state, 8, cudaMemcpyDeviceToHost, s));    // read by a LATER render, never waited for
+    T.band_off = Bn.band_off; T.cell_cmd = Bn.cell_cmd; T.cell_ext = Bn.cell_ext; T.bin_state = Bn.state;
   }
   if (rt->profiling && ti == 0) CU_TRY(cudaEventRecord(ev[1], s));
   bool streamed = false;

@@ -99,3 +99,56 @@ def test_render_multi_equals_separate_slabs(gpu, scene):
     whole, _ = replay(gpu, scene, count)
     assert np.array_equal(whole.to_numpy(), multi.to_numpy())
     batch.close(); rt.close(); rec.close()
+
+
+def test_unbinned_fallback_equals_binned(gpu, scene, monkeypatch):
+    """The per-band command lists (k_bin_*) only decide which commands a tile looks at: when they do not fit their buffer
+    the compositor scans every command instead (runtime.cu render_block) and must produce the same frame."""
+    count = 1500
+    binned, _ = replay(gpu, scene, count)
+    a = binned.to_numpy().copy()
+    monkeypatch.setenv("B2DGPU_BIN_CAPACITY", "64")          # 64 cells: the lists cannot be built
+    plain, _ = replay(gpu, scene, count)
+    monkeypatch.delenv("B2DGPU_BIN_CAPACITY")
+    assert np.array_equal(a, plain.to_numpy())
+    regrown, _ = replay(gpu, scene, count)                   # the next render builds its lists again
+    assert np.array_equal(a, regrown.to_numpy())
+
+
+def test_many_commands_and_many_tiles(ref, gpu):
+    """SURVEY 8 hazard "work proportional to the shape": a 100 000-command 4K frame and a 16384 x 16384 frame (65 536 tiles)
+    render through the band lists (there is no dense tiles x commands table any more); the first is compared with the
+    reference, the second with a band-sharded render of itself."""
+    import bench
+    from blend2d_b200 import _native as N
+    from blend2d_b200 import sharding as SH
+    from tests import scenes as S
+    # (i) 100 000 small rectangles and polygons on 4K against the reference
+    def many(api, ctx, rng):
+        for i in range(100000):
+            ctx.set_fill_style(S.rand_rgba32(rng))
+            x, y = float(rng.uniform(-20, W)), float(rng.uniform(-20, H))
+            if i % 3 == 0:
+                ctx.fill_rect_d(x, y, float(rng.uniform(1, 40)), float(rng.uniform(1, 40)))
+            elif i % 3 == 1:
+                ctx.fill_rect_i(int(x), int(y), int(rng.integers(1, 40)), int(rng.integers(1, 40)))
+            else:
+                ctx.fill_polygon([x, y, x + float(rng.uniform(2, 50)), y + float(rng.uniform(0, 9)), x + float(rng.uniform(0, 9)), y + float(rng.uniform(2, 50))])
+    ri, _ = S.draw(ref, many, W, H, 1, 3)
+    gi, gc = S.draw(gpu, many, W, H, 1, 3)
+    n, d = S.channel_diff(ri.to_numpy(), gi.to_numpy())
+    gc.close()
+    assert n == 0 and d == 0, f"{n} pixels differ, max channel diff {d}"
+    # (ii) 2 000 config-1 fills on 16384^2: unsharded == union of 3 slabs
+    side = 16384
+    big, _keep = bench.make_config1_scene(2000, side, side, seed=77)
+    def rep(slab, image):
+        ctx = gpu.Context(image, command_queue_limit=65536, slab=slab)
+        N.check(N.lib.b2d_scene_replay(ctx._h, C.byref(big), 0, 2000), "b2d_scene_replay")
+        ctx.end(); ctx.close()
+    whole = gpu.Image(side, side, 1); rep(None, whole)
+    parts = gpu.Image(side, side, 1)
+    for rank in range(3):
+        rep(SH.slab_rows(side, 3, rank), parts)
+    assert np.array_equal(whole.to_numpy(), parts.to_numpy())
+    assert (whole.to_numpy() != 0).any()
