@@ -240,18 +240,27 @@ struct MonoCurve {
   P2 p[N];
   P2 stack[kFlattenRecursionLimit * N];
   int sp;
+  int base;          // stack level this walk started at (see begin_at)
   double tol_sq;
 
   struct Step { double value, limit; P2 a, b, c, d, e, mid; };
 
   B2D_HD void begin(const P2* src, uint32_t sign_bit) {
-    sp = 0;
+    sp = 0; base = 0;
     #pragma unroll
     for (int i = 0; i < N; i++) p[i] = sign_bit ? src[N - 1 - i] : src[i];
   }
+  // Starts a walk at a node INSIDE the subdivision tree of a monotone piece: `pending` = the number of second halves
+  // the reference's depth-first walk would hold on its stack when it reaches this node (one per "first half" step on
+  // the path from the root), so that can_push() fails at exactly the same nodes.  The walk never pops below it.
+  B2D_HD void begin_at(const P2* node, uint32_t pending) {
+    sp = base = int(pending) * N;
+    #pragma unroll
+    for (int i = 0; i < N; i++) p[i] = node[i];
+  }
   B2D_HD P2 first() const { return p[0]; }
   B2D_HD P2 last() const { return p[N - 1]; }
-  B2D_HD bool can_pop() const { return sp != 0; }
+  B2D_HD bool can_pop() const { return sp != base; }
   B2D_HD bool can_push() const { return sp != kFlattenRecursionLimit * N; }
 
   // bound_left_to_right()/bound_right_to_left(): keep control points inside the end-point box.
@@ -347,6 +356,26 @@ struct Chain {
 };
 
 // flatten_safe_mono_curve (:2029-2063).
+// The walk of flatten_safe_mono_curve from the current node of `mc` (the whole piece, or - device edge builder - one
+// node of its subdivision tree: consecutive nodes share their end point, so each walk opens its chain where the
+// previous one ended and the union of the emitted lines is the reference's chain).
+template<int N, typename Out>
+B2D_HD void safe_walk(MonoCurve<N>& mc, uint32_t sign_bit, Out& out) {
+  Chain<Out> chain(out, sign_bit);
+  chain.open_at(mc.first().x, mc.first().y);
+  for (;;) {
+    typename MonoCurve<N>::Step st;
+    if (!mc.is_flat(st) && mc.can_push()) {
+      mc.split(st);
+      mc.push(st);
+      continue;
+    }
+    chain.add_line(mc.last().x, mc.last().y);
+    if (!mc.can_pop()) break;
+    mc.pop();
+  }
+}
+
 template<int N, typename Out>
 B2D_HD void flatten_safe(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, Out& out) {
   mc.begin(src, sign_bit);
@@ -371,23 +400,26 @@ B2D_HD void flatten_safe(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, Out
 // right-to-left); here a right-to-left piece is reflected in x (x -> -x, clip x0/x1 swapped and negated), run through
 // the single left-to-right routine, and reflected back right before truncation.  Negation is exact in IEEE
 // arithmetic and every comparison/min/max in the reference's second branch is the mirror image of the first.
+// First half of flatten_unsafe_mono_curve: everything that looks at the WHOLE monotone piece - the early outs, the
+// "practically a vertical line" case, the reflection of a right-to-left piece and bound().  Returns false when the piece
+// is finished (nothing visible, or the vertical case emitted it); otherwise `mc` holds the piece in the left-to-right
+// frame and `ltr` says whether that frame is the original one.
 template<int N, typename Out>
-B2D_HD void flatten_unsafe(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, const ClipBox& c, Out& out) {
+B2D_HD bool unsafe_prepare(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, const ClipBox& c, Out& out, bool& ltr) {
   EdgeEmitter<Out> em(out, c);
   mc.begin(src, sign_bit);
 
   double y_start = mc.first().y;
   double y_end = tmin(mc.last().y, c.y1);
-  if ((y_start >= y_end) | (y_end <= c.y0)) return;
+  if ((y_start >= y_end) | (y_end <= c.y0)) return false;
 
   const double kDeltaLimit = 0.00390625;
   double x_delta = mc.first().x - mc.last().x;
   x_delta = x_delta < 0.0 ? -x_delta : x_delta;                       // bl_abs
 
-  Chain<Out> chain(out, sign_bit);
-
   if (x_delta <= kDeltaLimit) {
     // Practically a vertical line.
+    Chain<Out> chain(out, sign_bit);
     y_start = tmax(y_start, c.y0);
     double x_min = tmin(mc.first().x, mc.last().x);
     double x_max = tmax(mc.first().x, mc.last().x);
@@ -397,21 +429,37 @@ B2D_HD void flatten_unsafe(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, c
       chain.open_at(mc.first().x, y_start);
       chain.add_line(mc.last().x, y_end);
     }
-    return;
+    return false;
   }
 
-  const bool ltr = mc.first().x < mc.last().x;
-  const double sgn = ltr ? 1.0 : -1.0;       // reflection factor applied to every x that leaves this routine
-  double cx0 = c.x0, cx1 = c.x1;             // clip x range in the (possibly reflected) frame
+  ltr = mc.first().x < mc.last().x;
   if (!ltr) {
     #pragma unroll
     for (int i = 0; i < N; i++) mc.p[i].x = -mc.p[i].x;
-    cx0 = -c.x1; cx1 = -c.x0;
   }
+  mc.bound(true);
+  return true;
+}
+
+// Second half: the clipped walk from the current node of `mc` (in the left-to-right frame).  For the whole piece this
+// is the reference's walk.  The device edge builder also runs it on the nodes of the piece's subdivision tree one by
+// one: the piece is monotone in x and y, so the state the reference carries from one node to the next - which side of
+// the clip box it is on, where the open chain ends - is a function of the node's first point, which every walk
+// re-derives below; borders come out as one interval per node instead of one per piece (un-merged, see the top of
+// this file).  tests/hostsim checks the equivalence on random curves.
+template<int N, typename Out>
+B2D_HD void unsafe_walk(MonoCurve<N>& mc, bool ltr, uint32_t sign_bit, const ClipBox& c, Out& out) {
+  EdgeEmitter<Out> em(out, c);
+  double y_start = mc.first().y;
+  double y_end = tmin(mc.last().y, c.y1);
+  if ((y_start >= y_end) | (y_end <= c.y0)) return;
+
+  Chain<Out> chain(out, sign_bit);
+  const double sgn = ltr ? 1.0 : -1.0;       // reflection factor applied to every x that leaves this routine
+  double cx0 = c.x0, cx1 = c.x1;             // clip x range in the (possibly reflected) frame
+  if (!ltr) { cx0 = -c.x1; cx1 = -c.x0; }
   // In the reflected frame "x0 side" is the reference's x1 side: borders go to the opposite clip edge.
   const bool x0_is_left = ltr;
-
-  mc.bound(true);
 
   // 0 = not out, 1 = out on the frame's x0 side, 2 = out on the frame's x1 side.
   uint32_t out_side = 0;
@@ -557,6 +605,12 @@ Finish:
   }
 }
 
+template<int N, typename Out>
+B2D_HD void flatten_unsafe(MonoCurve<N>& mc, const P2* src, uint32_t sign_bit, const ClipBox& c, Out& out) {
+  bool ltr = true;
+  if (unsafe_prepare<N>(mc, src, sign_bit, c, out, ltr)) unsafe_walk<N>(mc, ltr, sign_bit, c, out);
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // Curve front-ends (quad_to :1618-1743, cubic_to :1757-1884, conic_to :1897-2022).
 // -----------------------------------------------------------------------------------------------------------------
@@ -586,18 +640,20 @@ B2D_HD int split_quad_at(const P2* curve, P2* outp, const double* ts, int n) {
   return pieces;
 }
 
+// quad_to up to the monotone pieces: the trivial reject / border case is emitted here (returns 0), otherwise
+// spline[0 .. 2 * pieces] holds the pieces and `any` tells whether a control point lies outside the clip box (unsafe).
 template<typename Out>
-B2D_HD void build_quad(P2 p0, P2 p1, P2 p2, const ClipBox& c, double tol_sq, Out& out) {
+B2D_HD int prepare_quad(P2 p0, P2 p1, P2 p2, const ClipBox& c, Out& out, P2* spline /* [7] */, uint32_t& any) {
   uint32_t f0 = clip_flags(p0, c), f1 = clip_flags(p1, c), f2 = clip_flags(p2, c);
   uint32_t common = f0 & f1 & f2;
+  any = f0 | f1 | f2;
   if (common) {
-    if (common & (kClipY0 | kClipY1)) return;
+    if (common & (kClipY0 | kClipY1)) return 0;
     EdgeEmitter<Out> em(out, c);
     em.border((common & kClipX0) != 0, tclamp(p0.y, c.y0, c.y1), tclamp(p2.y, c.y0, c.y1));
-    return;
+    return 0;
   }
 
-  P2 spline[7];
   spline[0] = p0; spline[1] = p1; spline[2] = p2;
 
   // Geometry::split_with_options<kExtremaXY> (bezier_p.h:366-400).
@@ -615,10 +671,17 @@ B2D_HD void build_quad(P2 p0, P2 p1, P2 p2, const ClipBox& c, double tol_sq, Out
     P2 src[3] = { p0, p1, p2 };
     pieces = split_quad_at(src, spline, ts, n);
   }
+  return pieces;
+}
+
+template<typename Out>
+B2D_HD void build_quad(P2 p0, P2 p1, P2 p2, const ClipBox& c, double tol_sq, Out& out) {
+  P2 spline[7];
+  uint32_t any;
+  const int pieces = prepare_quad(p0, p1, p2, c, out, spline, any);
 
   MonoCurve<3> mc;
   mc.tol_sq = tol_sq;
-  uint32_t any = f0 | f1 | f2;
   for (int i = 0; i < pieces; i++) {
     const P2* piece = spline + i * 2;
     uint32_t sign_bit = piece[0].y > piece[2].y;
@@ -643,18 +706,19 @@ B2D_HD int quad_roots(double* dst, double a, double b, double cc, double t_min, 
   return n;
 }
 
+// cubic_to up to the monotone pieces (see prepare_quad); spline[0 .. 3 * pieces].
 template<typename Out>
-B2D_HD void build_cubic(P2 p0, P2 p1, P2 p2, P2 p3, const ClipBox& c, double tol_sq, Out& out) {
+B2D_HD int prepare_cubic(P2 p0, P2 p1, P2 p2, P2 p3, const ClipBox& c, Out& out, P2* spline /* [25] */, uint32_t& any) {
   uint32_t f0 = clip_flags(p0, c), f1 = clip_flags(p1, c), f2 = clip_flags(p2, c), f3 = clip_flags(p3, c);
   uint32_t common = f0 & f1 & f2 & f3;
+  any = f0 | f1 | f2 | f3;
   if (common) {
-    if (common & (kClipY0 | kClipY1)) return;
+    if (common & (kClipY0 | kClipY1)) return 0;
     EdgeEmitter<Out> em(out, c);
     em.border((common & kClipX0) != 0, tclamp(p0.y, c.y0, c.y1), tclamp(p3.y, c.y0, c.y1));
-    return;
+    return 0;
   }
 
-  P2 spline[8 * 3 + 1];
   spline[0] = p0; spline[1] = p1; spline[2] = p2; spline[3] = p3;
   int pieces = 1;
 
@@ -720,16 +784,75 @@ B2D_HD void build_cubic(P2 p0, P2 p1, P2 p2, P2 p3, const ClipBox& c, double tol
       if (pieces == 0) { spline[1] = p1; spline[2] = p2; spline[3] = p3; pieces = 1; }
     }
   }
+  return pieces;
+}
+
+template<typename Out>
+B2D_HD void build_cubic(P2 p0, P2 p1, P2 p2, P2 p3, const ClipBox& c, double tol_sq, Out& out) {
+  P2 spline[8 * 3 + 1];
+  uint32_t any;
+  const int pieces = prepare_cubic(p0, p1, p2, p3, c, out, spline, any);
 
   MonoCurve<4> mc;
   mc.tol_sq = tol_sq;
-  uint32_t any = f0 | f1 | f2 | f3;
   for (int i = 0; i < pieces; i++) {
     const P2* piece = spline + i * 3;
     uint32_t sign_bit = piece[0].y > piece[3].y;
     if (any) flatten_unsafe<4>(mc, piece, sign_bit, c, out);
     else flatten_safe<4>(mc, piece, sign_bit, out);
   }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// Subdivision-tree nodes (device edge builder).  A monotone piece is expanded breadth first into at most kNodeCap nodes,
+// which are then walked independently (safe_walk / unsafe_walk).  The children of a node are exactly what the
+// reference's push() leaves as "current curve" (first half) and "stack top" (second half).
+// -----------------------------------------------------------------------------------------------------------------
+enum : int { kNodeCap = 32 };
+enum : uint32_t { kNodePendingMask = 0xFFu, kNodeSign = 0x100u, kNodeUnsafe = 0x200u, kNodeLtr = 0x400u };
+
+// Root node of monotone piece `piece` (N points): what flatten_safe / flatten_unsafe set up before they start walking.
+// Returns false when the piece needs no walk (clipped away, or emitted by the vertical-line case).
+template<int N, typename Out>
+B2D_HD bool piece_root(MonoCurve<N>& mc, const P2* piece, bool unsafe, const ClipBox& c, Out& out, uint32_t& meta) {
+  const uint32_t sign_bit = piece[0].y > piece[N - 1].y;
+  meta = sign_bit ? kNodeSign : 0u;
+  if (unsafe) {
+    bool ltr = true;
+    if (!unsafe_prepare<N>(mc, piece, sign_bit, c, out, ltr)) return false;
+    meta |= kNodeUnsafe | (ltr ? kNodeLtr : 0u);
+  }
+  else {
+    mc.begin(piece, sign_bit);
+    mc.bound(mc.first().x < mc.last().x);
+  }
+  return true;
+}
+
+// One breadth-first step on the node in mc.p: false = leaf (flat, or the reference's stack would be full), true =
+// `first` / `second` receive the halves (pending + 1 / pending).
+template<int N>
+B2D_HD bool node_split(const MonoCurve<N>& mc, uint32_t pending, P2* first, P2* second) {
+  typename MonoCurve<N>::Step st;
+  if (mc.is_flat(st) || pending == uint32_t(kFlattenRecursionLimit)) return false;
+  mc.split(st);
+  if (N == 3) {
+    first[0] = mc.p[0]; first[1] = st.a; first[2] = st.mid;
+    second[0] = st.mid; second[1] = st.b; second[2] = mc.p[2];
+  }
+  else {
+    first[0] = mc.p[0]; first[1] = st.a; first[2] = st.d; first[3] = st.mid;
+    second[0] = st.mid; second[1] = st.e; second[2] = st.c; second[3] = mc.p[N - 1];
+  }
+  return true;
+}
+
+template<int N, typename Out>
+B2D_HD void node_walk(MonoCurve<N>& mc, const P2* node, uint32_t meta, const ClipBox& c, Out& out) {
+  mc.begin_at(node, meta & kNodePendingMask);
+  const uint32_t sign_bit = (meta & kNodeSign) ? 1u : 0u;
+  if (meta & kNodeUnsafe) unsafe_walk<N>(mc, (meta & kNodeLtr) != 0u, sign_bit, c, out);
+  else safe_walk<N>(mc, sign_bit, out);
 }
 
 // -----------------------------------------------------------------------------------------------------------------

@@ -1,8 +1,9 @@
 // kernels.cu - the sm_100a kernels of libb2dgpu and their launchers.
 //
 //   K1  k_build_edges<count|write>   one thread per path segment: transform -> clip -> monotone split -> flatten
-//                                    (FP64, no FMA) -> 24.8 integer edges.  Two passes (count, exclusive scan, write)
-//                                    give every command a contiguous, deterministic edge range.
+//                                    (FP64, no FMA) -> 24.8 integer edges; curves are flattened by the whole warp (one
+//                                    node of the subdivision tree per lane).  Two passes (count, exclusive scan, write)
+//                                    give every command a contiguous edge range.
 //   K1b k_scan_*                     exclusive prefix sum of the per-segment edge counts.
 //   K1c k_analytic_bbox / k_finalize_commands   per-command pixel bounding boxes used for tile culling.
 //   K1d k_bin_*                      per-band ordered command lists + per (band, command) column extents (tile culling).
@@ -36,11 +37,34 @@ namespace b2d {
 // =================================================================================================================
 
 struct CountOut {
+  enum : bool { kOrdered = false };
   uint32_t n;
   __device__ __forceinline__ void edge(int, int, int, int) { n++; }
 };
 
+// Write pass: the edges of ONE segment go to consecutive slots starting at `dst`.  What the reference emits once per
+// curve or per piece (borders, the vertical-line case) takes its slot from a counter the warp shares; the lines of the
+// node walks are written in CURVE ORDER (lane_dst: the lane's own run of slots, from a counting walk + warp scan), so
+// that consecutive edges stay neighbours on the canvas - the tile compositor classifies edges 32 at a time and is
+// measurably slower (14.5 vs 13.9 ms per config-1 step) when a curve's edges are shuffled.
 struct WriteOut {
+  enum : bool { kOrdered = true };
+  b2dgpu_edge* dst;
+  uint32_t* cursor;                  // shared memory (a local variable cannot be the target of an atomic)
+  b2dgpu_edge* lane_dst;
+  uint32_t n;
+  int min_x, min_y, max_x, max_y;
+  __device__ __forceinline__ void edge(int x0, int y0, int x1, int y1) {
+    b2dgpu_edge e; e.x0 = x0; e.y0 = y0; e.x1 = x1; e.y1 = y1;
+    if (lane_dst) lane_dst[n++] = e;
+    else dst[atomicAdd(cursor, 1u)] = e;
+    min_x = min(min_x, min(x0, x1)); max_x = max(max_x, max(x0, x1));
+    min_y = min(min_y, min(y0, y1)); max_y = max(max_y, max(y0, y1));
+  }
+};
+
+// A line segment is written by its own lane: private slot counter.
+struct WriteOutLane {
   b2dgpu_edge* dst;
   uint32_t n;
   int min_x, min_y, max_x, max_y;
@@ -52,8 +76,22 @@ struct WriteOut {
   }
 };
 
-template<typename Out>
-__device__ __forceinline__ void build_segment(const BuildParams& P, uint32_t seg_index, Out& out) {
+// Per-warp scratch of the edge builder.
+struct K1Warp {
+  P2 spline[8 * 3 + 1];              // monotone pieces of the curve being flattened
+  P2 node[2][kNodeCap][4];           // breadth-first frontier of its subdivision tree (double buffered)
+  uint32_t meta[2][kNodeCap];
+  uint32_t cursor;                   // write pass: edges of the current segment written so far
+};
+
+struct SegmentInput {
+  P2 p[4];
+  ClipBox cb;
+  double tol_sq;
+  uint32_t kind;
+};
+
+__device__ __forceinline__ SegmentInput load_segment(const BuildParams& P, uint32_t seg_index) {
   const b2dgpu_segment seg = P.segments[seg_index];
   const b2dgpu_command& cmd = P.commands[seg.command];
   const b2dgpu_geometry_state& gs = P.states[cmd.state_index];
@@ -62,60 +100,203 @@ __device__ __forceinline__ void build_segment(const BuildParams& P, uint32_t seg
   xf.m00 = gs.m[0]; xf.m01 = gs.m[1]; xf.m10 = gs.m[2]; xf.m11 = gs.m[3]; xf.m20 = gs.m[4]; xf.m21 = gs.m[5];
   xf.affine = gs.transform_type > 2u;
 
-  ClipBox cb;
-  cb.x0 = gs.clip[0]; cb.y0 = gs.clip[1]; cb.x1 = gs.clip[2]; cb.y1 = gs.clip[3];
-  cb.ix0 = trunc_i(cb.x0); cb.ix1 = trunc_i(cb.x1);
+  SegmentInput in;
+  in.cb.x0 = gs.clip[0]; in.cb.y0 = gs.clip[1]; in.cb.x1 = gs.clip[2]; in.cb.y1 = gs.clip[3];
+  in.cb.ix0 = trunc_i(in.cb.x0); in.cb.ix1 = trunc_i(in.cb.x1);
+  in.tol_sq = gs.tolerance_sq;
 
   const double2* v = reinterpret_cast<const double2*>(P.vertices);
-  const uint32_t kind = seg.p1_kind & 3u;
+  in.kind = seg.p1_kind & 3u;
   const uint32_t i1 = seg.p1_kind >> 2;
-
-  double2 a = v[seg.p0];
-  double2 b = v[i1];
-  P2 p0 = xform(xf, mk(a.x, a.y));
-  P2 p1 = xform(xf, mk(b.x, b.y));
-
-  if (kind == B2DGPU_SEG_LINE) {
-    build_line(p0, p1, cb, out);
+  const double2 a = v[seg.p0], b = v[i1];
+  in.p[0] = xform(xf, mk(a.x, a.y));
+  in.p[1] = xform(xf, mk(b.x, b.y));
+  in.p[2] = in.p[1]; in.p[3] = in.p[1];
+  if (in.kind == B2DGPU_SEG_CUBIC) {
+    const double2 c = v[i1 + 1], d = v[i1 + 2];
+    in.p[2] = xform(xf, mk(c.x, c.y));
+    in.p[3] = xform(xf, mk(d.x, d.y));
   }
-  else if (kind == B2DGPU_SEG_CUBIC) {
-    double2 c = v[i1 + 1], d = v[i1 + 2];
-    build_cubic(p0, p1, xform(xf, mk(c.x, c.y)), xform(xf, mk(d.x, d.y)), cb, gs.tolerance_sq, out);
-  }
-  else {
+  else if (in.kind != B2DGPU_SEG_LINE) {
     // Quad, or conic: the reference flattens a conic through its quad machinery using vertex[+2] as the end point
     // (EdgeSourcePath::next_conic_to, edgebuilder_p.h:267-272; FlattenMonoConic :666-768).
-    double2 c = v[i1 + (kind == B2DGPU_SEG_CONIC ? 2u : 1u)];
-    build_quad(p0, p1, xform(xf, mk(c.x, c.y)), cb, gs.tolerance_sq, out);
+    const double2 c = v[i1 + (in.kind == B2DGPU_SEG_CONIC ? 2u : 1u)];
+    in.p[2] = xform(xf, mk(c.x, c.y));
   }
+  return in;
 }
 
-__global__ void __launch_bounds__(128) k_count_edges(BuildParams P) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.segment_count) return;
-  CountOut out; out.n = 0;
-  build_segment(P, i, out);
-  P.seg_counts[i] = out.n;
+__device__ __forceinline__ void set_lane_run(CountOut&, uint32_t) {}
+__device__ __forceinline__ void set_lane_run(WriteOut& out, uint32_t offset) { out.lane_dst = out.dst + *out.cursor + offset; out.n = 0; }
+
+// A warp flattens ONE curve (N = 3 quad / conic, 4 cubic).  Lane 0 does what the reference does once per curve (reject,
+// monotone split); the lanes then take the pieces, expand them breadth first into at most kNodeCap nodes of the
+// subdivision tree (node_split: the very halves the reference's depth-first walk would visit) and walk one node each
+// (node_walk).  A canvas-sized curve of bl_bench / the tester flattens into ~80 lines: one thread walking it alone was
+// what kept this kernel at 1.3 active lanes per instruction in round 1.
+template<int N, typename Out>
+__device__ __forceinline__ void flatten_curve_warp(const SegmentInput& in, K1Warp& W, int lane, Out& out) {
+  int pieces = 0;
+  uint32_t any = 0;
+  if (lane == 0) {
+    pieces = N == 3 ? prepare_quad(in.p[0], in.p[1], in.p[2], in.cb, out, W.spline, any)
+                    : prepare_cubic(in.p[0], in.p[1], in.p[2], in.p[3], in.cb, out, W.spline, any);
+  }
+  pieces = __shfl_sync(0xFFFFFFFFu, pieces, 0);
+  any = __shfl_sync(0xFFFFFFFFu, any, 0);
+  if (!pieces) return;
+  __syncwarp();
+
+  MonoCurve<N> mc;
+  mc.tol_sq = in.tol_sq;
+
+  // roots: lane k sets up piece k
+  bool have = false;
+  uint32_t meta = 0;
+  if (lane < pieces) have = piece_root<N>(mc, W.spline + lane * (N - 1), any != 0u, in.cb, out, meta);
+  uint32_t mask = __ballot_sync(0xFFFFFFFFu, have);
+  uint32_t count = __popc(mask);
+  if (!count) return;
+  int cur = 0;
+  if (have) {
+    const uint32_t pos = __popc(mask & ((1u << lane) - 1u));
+    #pragma unroll
+    for (int k = 0; k < N; k++) W.node[0][pos][k] = mc.p[k];
+    W.meta[0][pos] = meta;
+  }
+  __syncwarp();
+
+  // breadth-first expansion while the frontier can still double
+  while (count * 2u <= uint32_t(kNodeCap)) {
+    P2 first[4], second[4];
+    bool split = false;
+    if (uint32_t(lane) < count) {
+      meta = W.meta[cur][lane];
+      mc.begin_at(W.node[cur][lane], 0);
+      split = node_split<N>(mc, meta & kNodePendingMask, first, second);
+    }
+    const uint32_t smask = __ballot_sync(0xFFFFFFFFu, split);
+    if (!smask) break;
+    if (uint32_t(lane) < count) {
+      const uint32_t pos = uint32_t(lane) + __popc(smask & ((1u << lane) - 1u));
+      if (split) {
+        #pragma unroll
+        for (int k = 0; k < N; k++) { W.node[cur ^ 1][pos][k] = first[k]; W.node[cur ^ 1][pos + 1][k] = second[k]; }
+        W.meta[cur ^ 1][pos] = meta + 1u;
+        W.meta[cur ^ 1][pos + 1] = meta;
+      }
+      else {
+        #pragma unroll
+        for (int k = 0; k < N; k++) W.node[cur ^ 1][pos][k] = mc.p[k];
+        W.meta[cur ^ 1][pos] = meta;
+      }
+    }
+    count += __popc(smask);
+    cur ^= 1;
+    __syncwarp();
+  }
+
+  if (Out::kOrdered) {
+    CountOut cnt; cnt.n = 0;
+    if (uint32_t(lane) < count) node_walk<N>(mc, W.node[cur][lane], W.meta[cur][lane], in.cb, cnt);
+    uint32_t inc = cnt.n;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncwarp();
+    set_lane_run(out, inc - cnt.n);                  // after what prepare / the roots emitted through the shared counter
+  }
+  if (uint32_t(lane) < count) node_walk<N>(mc, W.node[cur][lane], W.meta[cur][lane], in.cb, out);
+  __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) k_write_edges(BuildParams P) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.segment_count) return;
-  uint32_t begin = P.seg_offsets[i];
-  uint32_t end = P.seg_offsets[i + 1];
-  if (begin == end) return;
-  if (end > P.edge_capacity - P.edge_base) {           // capacity is checked on the host too; never write past it
-    atomicOr(P.error_flag, 1u);
-    return;
+// K1: one thread per path segment, a warp per batch of 32 consecutive segments.  Lines are built by their own lane;
+// the curves of the batch are then flattened one after the other by the whole warp.
+//   WRITE == false: seg_counts[i] = edges of segment i.
+//   WRITE == true : the edges are written at seg_offsets[i] .. seg_offsets[i + 1]; the command's bounding box grows.
+template<bool WRITE>
+__global__ void __launch_bounds__(128) k_build_edges(BuildParams P) {
+  __shared__ K1Warp s_warp[4];
+  const int lane = threadIdx.x & 31;
+  K1Warp& W = s_warp[threadIdx.x >> 5];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < P.segment_count;
+
+  uint32_t kind = B2DGPU_SEG_LINE;
+  uint32_t begin = 0, end = 0;
+  bool writable = false;
+  if (valid) {
+    kind = P.segments[i].p1_kind & 3u;
+    if (WRITE) {
+      begin = P.seg_offsets[i]; end = P.seg_offsets[i + 1];
+      writable = begin != end;
+      if (writable && end > P.edge_capacity - P.edge_base) {       // capacity is checked on the host too; never write past it
+        atomicOr(P.error_flag, 1u);
+        writable = false;
+      }
+    }
   }
-  WriteOut out;
-  out.dst = P.edges + P.edge_base + begin;
-  out.n = 0;
-  out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
-  build_segment(P, i, out);
-  int4* bb = P.cmd_bbox_fixed + P.segments[i].command;
-  atomicMin(&bb->x, out.min_x); atomicMin(&bb->y, out.min_y);
-  atomicMax(&bb->z, out.max_x); atomicMax(&bb->w, out.max_y);
+  const bool active = valid && (!WRITE || writable);
+
+  // ---- lines: one per lane ----
+  if (active && kind == B2DGPU_SEG_LINE) {
+    const SegmentInput in = load_segment(P, i);
+    if (!WRITE) {
+      CountOut out; out.n = 0;
+      build_line(in.p[0], in.p[1], in.cb, out);
+      P.seg_counts[i] = out.n;
+    }
+    else {
+      WriteOutLane out;
+      out.dst = P.edges + P.edge_base + begin; out.n = 0;
+      out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
+      build_line(in.p[0], in.p[1], in.cb, out);
+      int4* bb = P.cmd_bbox_fixed + P.segments[i].command;
+      atomicMin(&bb->x, out.min_x); atomicMin(&bb->y, out.min_y);
+      atomicMax(&bb->z, out.max_x); atomicMax(&bb->w, out.max_y);
+    }
+  }
+  else if (valid && !WRITE && kind == B2DGPU_SEG_LINE) P.seg_counts[i] = 0;
+
+  // ---- curves: the warp takes them one at a time ----
+  uint32_t todo = __ballot_sync(0xFFFFFFFFu, active && kind != B2DGPU_SEG_LINE);
+  if (!WRITE) {
+    // segments that are skipped still need a count
+    if (valid && !active) P.seg_counts[i] = 0;
+  }
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const uint32_t seg = blockIdx.x * blockDim.x + (threadIdx.x & ~31u) + uint32_t(src);
+    const SegmentInput in = load_segment(P, seg);                  // every lane reads the same addresses: broadcast loads
+    if (!WRITE) {
+      CountOut out; out.n = 0;
+      if (in.kind == B2DGPU_SEG_CUBIC) flatten_curve_warp<4>(in, W, lane, out);
+      else flatten_curve_warp<3>(in, W, lane, out);
+      const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, out.n);
+      if (lane == 0) P.seg_counts[seg] = total;
+    }
+    else {
+      if (lane == 0) W.cursor = 0;
+      __syncwarp();
+      WriteOut out;
+      out.dst = P.edges + P.edge_base + __shfl_sync(0xFFFFFFFFu, begin, src); out.cursor = &W.cursor;
+      out.lane_dst = nullptr; out.n = 0;
+      out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
+      if (in.kind == B2DGPU_SEG_CUBIC) flatten_curve_warp<4>(in, W, lane, out);
+      else flatten_curve_warp<3>(in, W, lane, out);
+      const int mnx = __reduce_min_sync(0xFFFFFFFFu, out.min_x), mny = __reduce_min_sync(0xFFFFFFFFu, out.min_y);
+      const int mxx = __reduce_max_sync(0xFFFFFFFFu, out.max_x), mxy = __reduce_max_sync(0xFFFFFFFFu, out.max_y);
+      if (lane == 0 && mnx <= mxx) {
+        int4* bb = P.cmd_bbox_fixed + P.segments[seg].command;
+        atomicMin(&bb->x, mnx); atomicMin(&bb->y, mny);
+        atomicMax(&bb->z, mxx); atomicMax(&bb->w, mxy);
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // =================================================================================================================
@@ -1076,13 +1257,13 @@ static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; 
 
 int launch_count_edges(const BuildParams& P, cudaStream_t s) {
   if (!P.segment_count) return 0;
-  k_count_edges<<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
+  k_build_edges<false><<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
   return 1;
 }
 
 int launch_write_edges(const BuildParams& P, cudaStream_t s) {
   if (!P.segment_count) return 0;
-  k_write_edges<<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
+  k_build_edges<true><<<div_up(P.segment_count, 128), 128, 0, s>>>(P);
   return 1;
 }
 

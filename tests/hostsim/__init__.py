@@ -19,6 +19,8 @@ def lib():
         _lib.hostsim_render.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_uint32, C.c_void_p]
         _lib.hostsim_build_edges.restype = C.c_uint32
         _lib.hostsim_build_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib.hostsim_flatten_equivalence.restype = C.c_uint32
+        _lib.hostsim_flatten_equivalence.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32]
     return _lib
 
 
@@ -67,3 +69,9 @@ def draw(scene, W, H, fmt=1, seed=1):
     out = img.to_numpy().copy()
     ctx.close()
     return out
+
+
+def flatten_equivalence(kind, count, seed, mode):
+    """Curves (kind 3 quads / 4 cubics) whose edges differ between the sequential flattening (the reference's walk) and
+    the node expansion the device edge builder uses; see hostsim.cpp hostsim_flatten_equivalence."""
+    return int(lib().hostsim_flatten_equivalence(kind, count, seed, mode))

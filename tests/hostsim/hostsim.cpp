@@ -14,6 +14,8 @@
 
 #include <limits.h>
 #include <string.h>
+#include <algorithm>
+#include <utility>
 #include <vector>
 
 using namespace b2d;
@@ -225,6 +227,110 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
     }
   }
   return written;
+}
+
+} // extern "C"
+
+// Equivalence check for the device edge builder's node expansion (dev_flatten.cuh piece_root / node_split / node_walk):
+// `count` random quads (kind 3) or cubics (kind 4) with a random clip box are flattened (a) by the sequential routine
+// build_quad / build_cubic - the reference's walk - and (b) piece by piece through the breadth-first expansion into at
+// most kNodeCap nodes followed by independent walks, exactly as k_build_edges does.  Lines must agree as multisets;
+// vertical lines (borders are un-merged in (b)) must agree as signed coverage along y per x.  Returns the number of
+// curves that differ.
+template<int N>
+static void expanded_build(const P2* pts, const ClipBox& cb, double tol_sq, VecOut& out) {
+  P2 spline[25];
+  uint32_t any = 0;
+  const int pieces = N == 3 ? prepare_quad(pts[0], pts[1], pts[2], cb, out, spline, any)
+                            : prepare_cubic(pts[0], pts[1], pts[2], pts[3], cb, out, spline, any);
+  struct Node { P2 p[4]; uint32_t meta; };
+  std::vector<Node> cur, nxt;
+  MonoCurve<N> mc;
+  mc.tol_sq = tol_sq;
+  for (int i = 0; i < pieces; i++) {
+    uint32_t meta = 0;
+    if (!piece_root<N>(mc, spline + i * (N - 1), any != 0, cb, out, meta)) continue;
+    Node n; for (int k = 0; k < N; k++) n.p[k] = mc.p[k]; n.meta = meta;
+    cur.push_back(n);
+  }
+  while (!cur.empty() && cur.size() * 2 <= size_t(kNodeCap)) {
+    bool split_any = false;
+    nxt.clear();
+    for (const Node& n : cur) {
+      mc.begin_at(n.p, 0);
+      Node a = n, b = n;
+      if (node_split<N>(mc, n.meta & kNodePendingMask, a.p, b.p)) { a.meta = n.meta + 1u; nxt.push_back(a); nxt.push_back(b); split_any = true; }
+      else nxt.push_back(n);
+    }
+    cur.swap(nxt);
+    if (!split_any) break;
+  }
+  for (const Node& n : cur) node_walk<N>(mc, n.p, n.meta, cb, out);
+}
+
+static void canonical(const std::vector<b2dgpu_edge>& in, std::vector<b2dgpu_edge>& lines, std::vector<b2dgpu_edge>& vert) {
+  lines.clear(); vert.clear();
+  std::vector<std::pair<std::pair<int, int>, int>> ev;        // ((x, y), +-1)
+  for (const b2dgpu_edge& e : in) {
+    if (e.x0 != e.x1) { lines.push_back(e); continue; }
+    const int sgn = e.y0 < e.y1 ? 1 : -1;
+    ev.push_back({ { e.x0, e.y0 < e.y1 ? e.y0 : e.y1 }, sgn });
+    ev.push_back({ { e.x0, e.y0 < e.y1 ? e.y1 : e.y0 }, -sgn });
+  }
+  auto less = [](const b2dgpu_edge& a, const b2dgpu_edge& b) { return memcmp(&a, &b, sizeof(a)) < 0; };
+  std::sort(lines.begin(), lines.end(), less);
+  std::sort(ev.begin(), ev.end());
+  // running winding along y per x -> maximal runs of constant non-zero winding
+  size_t i = 0;
+  while (i < ev.size()) {
+    const int x = ev[i].first.first;
+    int w = 0, run_start = 0;
+    while (i < ev.size() && ev[i].first.first == x) {
+      const int y = ev[i].first.second;
+      int d = 0;
+      while (i < ev.size() && ev[i].first.first == x && ev[i].first.second == y) d += ev[i++].second;
+      if (d == 0) continue;
+      if (w != 0) { b2dgpu_edge e; e.x0 = x; e.x1 = w; e.y0 = run_start; e.y1 = y; vert.push_back(e); }
+      w += d; run_start = y;
+    }
+  }
+}
+
+extern "C" {
+
+__attribute__((visibility("default")))
+uint32_t hostsim_flatten_equivalence(uint32_t kind, uint32_t count, uint64_t seed, uint32_t mode) {
+  uint64_t st = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return double(st >> 11) / 9007199254740992.0; };
+  uint32_t bad = 0;
+  std::vector<b2dgpu_edge> va, vb, la, lb, ca, cb2;
+  for (uint32_t it = 0; it < count; it++) {
+    // clip box in 24.8 units, like final_clip_box_fixed_d of a W x H canvas
+    const double W = double(int(8 + rnd() * 4000)) * 256.0, H = double(int(8 + rnd() * 2500)) * 256.0;
+    ClipBox cb; cb.x0 = 0.0; cb.y0 = 0.0; cb.x1 = W; cb.y1 = H; cb.ix0 = trunc_i(cb.x0); cb.ix1 = trunc_i(cb.x1);
+    // mode 0: points a little outside the box (tester paths); 1: far outside; 2: all inside; 3: tiny curves (glyphs)
+    const double m = mode == 0 ? 0.05 : mode == 1 ? 3.0 : 0.0;
+    P2 pts[4];
+    if (mode == 3) {
+      const double ox = rnd() * W, oy = rnd() * H, sz = 256.0 * (1.0 + rnd() * 40.0);
+      for (int k = 0; k < 4; k++) pts[k] = mk(ox + rnd() * sz, oy + rnd() * sz);
+    }
+    else for (int k = 0; k < 4; k++) pts[k] = mk((rnd() * (1.0 + 2.0 * m) - m) * W, (rnd() * (1.0 + 2.0 * m) - m) * H);
+    if (it % 7 == 3) pts[1] = pts[0];                              // degenerate control points
+    if (it % 11 == 5) pts[2].x = pts[1].x;
+    if (it % 13 == 6) { pts[0].x = 0.0; pts[kind - 1].x = W; }     // end points exactly on the clip edges
+    const double tol = 0.2 * 256.0;
+    va.clear(); vb.clear();
+    VecOut oa{ &va }, ob{ &vb };
+    if (kind == 3) { build_quad(pts[0], pts[1], pts[2], cb, tol * tol, oa); expanded_build<3>(pts, cb, tol * tol, ob); }
+    else { build_cubic(pts[0], pts[1], pts[2], pts[3], cb, tol * tol, oa); expanded_build<4>(pts, cb, tol * tol, ob); }
+    canonical(va, la, ca); canonical(vb, lb, cb2);
+    const bool same = la.size() == lb.size() && ca.size() == cb2.size() &&
+                      (la.empty() || memcmp(la.data(), lb.data(), la.size() * sizeof(b2dgpu_edge)) == 0) &&
+                      (ca.empty() || memcmp(ca.data(), cb2.data(), ca.size() * sizeof(b2dgpu_edge)) == 0);
+    if (!same) bad++;
+  }
+  return bad;
 }
 
 } // extern "C"

@@ -52,3 +52,15 @@ def test_mixed_unaligned_canvas(ref, fmt):
 @pytest.mark.parametrize("fmt", [1, 3])
 def test_fill_mask(ref, style, fmt):
     compare(ref, S.masked_fills(80, 300, 200, S.SRC_OVER, style), 300, 200, fmt, 4)
+
+
+@pytest.mark.parametrize("kind", [3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_node_expansion_equals_sequential_flattening(kind, mode):
+    """k_build_edges flattens a curve with a warp: the monotone pieces are expanded breadth first into <= 32 nodes of the
+    reference's subdivision tree and every node is walked on its own (dev_flatten.cuh node_split / node_walk).  The
+    same device functions, run on the CPU, must emit the edges of the sequential walk (edgebuilder_p.h:2029-2445): equal
+    multisets of lines, equal signed coverage of the (un-merged) vertical border lines.  mode: 0 control points slightly
+    outside the clip box, 1 far outside, 2 all inside, 3 glyph-sized curves."""
+    from tests import hostsim
+    assert hostsim.flatten_equivalence(kind, 60000, 99 + mode, mode) == 0
