@@ -465,7 +465,10 @@ __global__ void __launch_bounds__(256) k_bin_count(BinParams B) {
   if (bb.x < bb.z && bb.y < bb.w) {
     const int band0 = (bb.y - B.y_begin) / B.tile_h, band1 = (bb.w - 1 - B.y_begin) / B.tile_h;
     nb = uint32_t(band1 - band0 + 1);
-    for (int b = band0; b <= band1; b++) atomicAdd(B.band_count + b, 1u);
+    // difference array: +1 where the command's bands start, -1 after they end; its prefix sum is the number of commands
+    // per band (two atomics per command whatever it spans)
+    atomicAdd(B.band_count + band0, 1u);
+    atomicAdd(B.band_count + band1 + 1, 0xFFFFFFFFu);
   }
   B.cm_count[c] = nb;
 }
@@ -476,14 +479,15 @@ __global__ void k_bin_check(BinParams B) {
   B.state[1] = total <= B.capacity ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) k_bin_fill(BinParams B) {
+__global__ void __launch_bounds__(1024) k_bin_fill(BinParams B) {
   if (!B.state[1]) return;
-  __shared__ uint32_t s_w[8];
+  __shared__ uint32_t s_w[32];
   const int b = blockIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int by0 = B.y_begin + b * B.tile_h, by1 = by0 + B.tile_h;
   uint32_t run = B.band_off[b];
-  for (uint32_t base = 0; base < B.command_count; base += 256) {
+  if (B.band_off[b + 1] == run) return;                  // nothing covers this band
+  for (uint32_t base = 0; base < B.command_count; base += 1024) {
     const uint32_t c = base + threadIdx.x;
     bool hit = false;
     int4 bb = make_int4(0, 0, 0, 0);
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(BinParams B) {
     __syncthreads();
     uint32_t wbase = 0, total = 0;
     #pragma unroll
-    for (uint32_t w = 0; w < 8; w++) { const uint32_t n = s_w[w]; if (w < warp) wbase += n; total += n; }
+    for (uint32_t w = 0; w < 32; w++) { const uint32_t n = s_w[w]; if (w < warp) wbase += n; total += n; }
     if (hit) {
       const uint32_t pos = run + wbase + __popc(ballot & ((1u << lane) - 1u));
       B.cell_cmd[pos] = c;
@@ -1363,19 +1367,23 @@ int launch_stream_solid(const SolidStreamParams& P, int sm_count, cudaStream_t s
 }
 
 size_t bin_scratch_items(uint32_t command_count, int tiles_y) {
-  return scan_scratch_items(command_count) + scan_scratch_items(uint32_t(tiles_y)) + 16;
+  return scan_scratch_items(command_count) + scan_scratch_items(uint32_t(tiles_y) + 1u) + 16;
 }
 
 int launch_binning(const BinParams& B, cudaStream_t s) {
   if (!B.command_count || B.tiles_y <= 0) return 0;
   int launches = 0;
-  cudaMemsetAsync(B.band_count, 0, sizeof(uint32_t) * (size_t(B.tiles_y) + 1), s);
+  // band_count doubles as the difference array: tiles_y + 2 entries (k_bin_count writes index band1 + 1 <= tiles_y)
+  cudaMemsetAsync(B.band_count, 0, sizeof(uint32_t) * (size_t(B.tiles_y) + 2), s);
   k_bin_count<<<div_up(B.command_count, 256), 256, 0, s>>>(B);
   launches += 1;
   launches += launch_exclusive_scan(B.cm_count, B.cm_base, B.command_count, B.scan_scratch, nullptr, s);
-  launches += launch_exclusive_scan(B.band_count, B.band_off, uint32_t(B.tiles_y), B.scan_scratch + scan_scratch_items(B.command_count), nullptr, s);
+  // exclusive scan E of the differences: commands per band b = E[b + 1]; band_off = exclusive scan of those
+  uint32_t* scratch2 = B.scan_scratch + scan_scratch_items(B.command_count);
+  launches += launch_exclusive_scan(B.band_count, B.band_prefix, uint32_t(B.tiles_y) + 1u, scratch2, nullptr, s);
+  launches += launch_exclusive_scan(B.band_prefix + 1, B.band_off, uint32_t(B.tiles_y), scratch2, nullptr, s);
   k_bin_check<<<1, 1, 0, s>>>(B);
-  k_bin_fill<<<B.tiles_y, 256, 0, s>>>(B);
+  k_bin_fill<<<B.tiles_y, 1024, 0, s>>>(B);
   k_bin_extents<<<div_up(B.command_count * 32, 256), 256, 0, s>>>(B);
   return launches + 3;
 }

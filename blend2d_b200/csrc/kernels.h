@@ -68,7 +68,8 @@ struct BinParams {
   int y_begin, tile_h, tiles_y;
   uint32_t* cm_count;                     // per command: bands its pixel box covers           (command_count + 1)
   uint32_t* cm_base;                      // exclusive scan of cm_count                        (command_count + 1)
-  uint32_t* band_count;                   // per band: commands whose pixel box covers it      (tiles_y + 1)
+  uint32_t* band_count;                   // difference array of the commands per band         (tiles_y + 2)
+  uint32_t* band_prefix;                  // its exclusive scan: commands of band b = [b + 1]  (tiles_y + 2)
   uint32_t* band_off;                     // exclusive scan of band_count                      (tiles_y + 1)
   uint32_t* cm_index;                     // [cm_base[c] + band - first band of c] -> cell     (capacity)
   uint32_t* cell_cmd;                     // band-major cells                                  (capacity)

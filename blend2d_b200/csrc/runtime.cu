@@ -957,7 +957,8 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     const size_t o_state = take(16);
     const size_t o_cm_count = take(sizeof(uint32_t) * (size_t(in.command_count) + 1));
     const size_t o_cm_base = take(sizeof(uint32_t) * (size_t(in.command_count) + 1));
-    const size_t o_band_count = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 1));
+    const size_t o_band_count = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 2));
+    const size_t o_band_prefix = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 2));
     const size_t o_band_off = take(sizeof(uint32_t) * (size_t(T.tiles_y) + 1));
     const size_t o_scratch = take(sizeof(uint32_t) * bin_scratch_items(in.command_count, T.tiles_y));
     const size_t o_cm_index = take(sizeof(uint32_t) * size_t(cap));
@@ -976,6 +977,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     Bn.state = reinterpret_cast<uint32_t*>(bp + o_state);
     Bn.cm_count = reinterpret_cast<uint32_t*>(bp + o_cm_count); Bn.cm_base = reinterpret_cast<uint32_t*>(bp + o_cm_base);
     Bn.band_count = reinterpret_cast<uint32_t*>(bp + o_band_count); Bn.band_off = reinterpret_cast<uint32_t*>(bp + o_band_off);
+    Bn.band_prefix = reinterpret_cast<uint32_t*>(bp + o_band_prefix);
     Bn.scan_scratch = reinterpret_cast<uint32_t*>(bp + o_scratch);
     Bn.cm_index = reinterpret_cast<uint32_t*>(bp + o_cm_index); Bn.cell_cmd = reinterpret_cast<uint32_t*>(bp + o_cell_cmd);
     Bn.cell_ext = reinterpret_cast<uint2*>(bp + o_cell_ext);

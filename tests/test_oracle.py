@@ -215,3 +215,95 @@ def test_gpu_operators_against_oracle(gpu, op):
     ctx.end()
     got = img.to_numpy().copy(); ctx.close()
     assert np.array_equal(got, expected_jit_only(op, backdrop, shapes, w, h))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Plus pinned to the reference itself: CompOp_Plus_Op instantiated from the reference's own headers
+# (oracle/ref_internals.cpp: pipeline/reference/compopgeneric_p.h:65-81 through CompOp_Base / FillDispatch,
+# fixedpiperuntime.cpp:58-69).  The reference's runtime never dispatches it (fixedpiperuntime.cpp:254), its templates do.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def refint(ref):
+    from oracle import ref_internals as RI
+    if not RI.available():
+        pytest.skip("oracle/_ref/libref_internals.so not built (make -f oracle/Makefile.ref where /root/reference exists)")
+    return RI
+
+
+@pytest.mark.parametrize("op", [O.SRC_OVER, O.SRC_COPY, O.PLUS])
+def test_oracle_operators_pinned_to_reference_templates(refint, op):
+    rng = np.random.default_rng(50 + op)
+    n = 20000
+    d, s = premul(rng, n), premul(rng, n)
+    m = rng.integers(0, 256, n).astype(np.uint32)
+    m[:2048] = 255; m[2048:4096] = 1
+    keep = m != 0                                   # m == 0 never reaches an operator (the fillers skip such pixels)
+    want = refint.comp_op_pixels(op, d, s, m)
+    got = np.array([O.lib().orc_composite_prgb32(op, int(a), int(b), int(c)) for a, b, c in zip(d, s, m)], np.uint32)
+    assert np.array_equal(got[keep], want[keep])
+
+
+def plus_scene(backdrop, rects, shapes):
+    def scene(api, ctx, rng):
+        ctx.set_comp_op(O.PLUS)
+        for (x, y, w, h), color, alpha in rects:
+            ctx.set_fill_style(color); ctx.set_global_alpha(alpha)
+            ctx.fill_rect_i(x, y, w, h)
+        for pts, color, alpha in shapes:
+            ctx.set_fill_style(color); ctx.set_global_alpha(alpha)
+            ctx.fill_polygon(pts.reshape(-1).tolist())
+    return scene
+
+
+def expected_plus_from_reference(ref, refint, backdrop, rects, shapes, w, h):
+    """Plus through the reference: boxes through its FillBoxA pipeline instantiated with CompOp_Plus_Op; anti-aliased
+    shapes through its operator template applied with the masks ITS rasterizer produces (a SrcCopy of opaque white on
+    black leaves exactly the mask in every channel)."""
+    out = backdrop.copy()
+    for (x, y, bw, bh), color, alpha in rects:
+        refint.fill_box_a_solid(O.PLUS, out, (x, y, x + bw, y + bh), premultiply_rgba32(color), alpha8(alpha))
+    for pts, color, alpha in shapes:
+        img = ref.Image(w, h, 1)
+        ctx = ref.Context(img)
+        ctx.set_comp_op(O.SRC_COPY); ctx.set_fill_style(0xFFFFFFFF); ctx.set_global_alpha(alpha)
+        ctx.fill_polygon(pts.reshape(-1).tolist())
+        ctx.end(); ctx.close()
+        mask = img.to_numpy() & 0xFF
+        res = refint.comp_op_pixels(O.PLUS, out, premultiply_rgba32(color), mask)
+        out = np.where(mask != 0, res, out)
+    return out
+
+
+def make_plus_case(seed, w, h):
+    rng = np.random.default_rng(seed)
+    backdrop, shapes = make_shapes(seed, w, h, 14)
+    rects = [((int(rng.integers(0, w - 20)), int(rng.integers(0, h - 20)), int(rng.integers(1, 120)), int(rng.integers(1, 90))),
+              int(rng.integers(0, 2 ** 32)), float(rng.choice([1.0, 0.5, 0.25]))) for _ in range(10)]
+    rects = [((x, y, min(bw, w - x), min(bh, h - y)), c, a) for (x, y, bw, bh), c, a in rects]
+    return backdrop, rects, shapes
+
+
+def test_hostsim_plus_against_reference_templates(ref, refint):
+    import blend2d_b200 as G
+    from tests import hostsim
+    w, h = 150, 100
+    backdrop, rects, shapes = make_plus_case(910, w, h)
+    img = G.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = G.Context(img, record_only=True)
+    plus_scene(backdrop, rects, shapes)(G, ctx, None)
+    hostsim.render(ctx, img)
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_plus_from_reference(ref, refint, backdrop, rects, shapes, w, h))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [911, 912])
+def test_gpu_plus_against_reference_templates(ref, refint, gpu, seed):
+    w, h = 640, 400
+    backdrop, rects, shapes = make_plus_case(seed, w, h)
+    img = gpu.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = gpu.Context(img)
+    plus_scene(backdrop, rects, shapes)(gpu, ctx, None)
+    ctx.end()
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_plus_from_reference(ref, refint, backdrop, rects, shapes, w, h))
