@@ -517,7 +517,7 @@ def other_config_legs(gb, args):
         f"config2: {args.config2_fills} FillRectRot/FillRoundU, 64x64 PRGB32 sprite REPEAT, nearest+bilinear, SrcCopy/Plus/Multiply/Screen on {W4K}x{H4K} PRGB32",
         sc, args.config2_fills, W4K, H4K, steps, warmup, tol=0, parity_scene=psc,
         parity_note="the reference's portable pipeline has no Plus/Multiply/Screen: parity on the same geometry and patterns with those operators "
-                    "remapped to SrcOver/SrcCopy; the three operators are checked against the C restatement in tests/ (Plus pinned to the reference's CompOp_Plus_Op)"))
+                    "remapped to SrcOver/SrcCopy; Plus is checked in tests/ against the reference's own CompOp_Plus_Op template (oracle/ref_internals.cpp), Multiply / Screen against the C restatement (unpinned)"))
     # config 3: 100 000 glyphs
     sc, keep = BS.make_config3_scene(args.config3_strings, W4K, H4K)
     out["config3_glyphs"] = summarize_leg(gb.leg(
@@ -744,6 +744,7 @@ def measure_band_sharded(gb, args):
     # The exchange: every stripe goes straight to its rows of rank 0's final image (no staging, no concatenation), and
     # the render of stripe j + 1 overlaps the transfer of stripe j (sharding.StripeGather).
     gather = SH.StripeGather(side, k, rank, world, torch.device("cuda", local_rank))
+    side_stream = torch.cuda.Stream(priority=-1)
     t_render, t_gather, t_overlap = e0.elapsed_time(e1), None, None
     if world > 1:
         gather.run(local)                                                       # warm-up: NCCL channel setup
@@ -762,11 +763,13 @@ def measure_band_sharded(gb, args):
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         o0.record(stream)
         gather.begin()
+        render_all()                                                        # ONE geometry pass, the stripes composited in order
         for j, t_ in enumerate(tgts):
-            one = (C.c_void_p * 1)(t_.value)
-            N.check(lib.b2dgpu_batch_render_multi(rt._h, one, 1, batch._h), "batch_render_multi")
-            gather.stripe_ready(j, local[j], stream)
-        gather.finish(stream)
+            # the side stream waits for stripe j only (b2dgpu_target_wait), its transfer runs while j + 1 .. are composited
+            N.check(lib.b2dgpu_target_wait(t_, side_stream.cuda_stream), "target_wait")
+            gather.stripe_ready(j, local[j], side_stream)
+        gather.finish(side_stream)
+        stream.wait_stream(side_stream)
         o1.record(stream)
         torch.cuda.synchronize()
         t_overlap = o0.elapsed_time(o1)
@@ -785,7 +788,7 @@ def measure_band_sharded(gb, args):
                "n_gpus": world, "render_ms_max_over_ranks": vals[0], "value": px[0] / (vals[0] * 1e-3) / 1e6, "unit": "Mpix/s", "scaling": "strong",
                "gather_ms": vals[1] if world > 1 else None, "render_plus_gather_overlapped_ms": vals[2] if world > 1 else None,
                "gathered_bytes": side * side * 4 if world > 1 else 0,
-               "collective": "per-stripe ncclSend/ncclRecv straight into rank 0's image rows, overlapped with the render of the next stripe" if world > 1 else "none (single GPU anchor)"}
+               "collective": "per-stripe ncclSend/ncclRecv straight into rank 0's image rows on a side stream that waits per stripe (b2dgpu_target_wait): one geometry pass, transfer of stripe j under the compositing of j + 1 .." if world > 1 else "none (single GPU anchor)"}
     batch.close()
     for t_ in tgts:
         N.check(lib.b2dgpu_target_destroy(t_), "target_destroy")

@@ -109,6 +109,7 @@ _SIGS = {
     "b2dgpu_batch_render_multi": (_R, [_P, C.POINTER(_P), C.c_uint32, _P]),
     "b2dgpu_batch_render": (_R, [_P, _P, _P]),
     "b2dgpu_sync": (_R, [_P]),
+    "b2dgpu_target_wait": (_R, [_P, _P]),
     "b2dgpu_get_stats": (_R, [_P, C.POINTER(Stats), C.c_int]),
     "b2dgpu_set_profiling": (_R, [_P, C.c_int]),
     "b2dgpu_debug_build_edges": (_R, [_P, C.POINTER(BatchView), C.POINTER(Edge), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

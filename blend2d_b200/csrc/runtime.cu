@@ -131,6 +131,8 @@ struct b2dgpu_target {
   uint8_t* d_pixels;
   size_t stride;
   int padded_w, padded_h;
+  cudaEvent_t rendered;                     // recorded after the last compositing kernel that wrote this target
+  bool rendered_valid;
 };
 
 // Offsets of the sections inside a device block.
@@ -460,6 +462,9 @@ extern "C" b2dgpu_result b2dgpu_target_create_slab(b2dgpu_runtime* rt, int32_t w
   if (e != cudaSuccess) { delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMalloc(canvas)"); }
   e = cudaMemsetAsync(t->d_pixels, 0, t->stride * t->padded_h, rt->stream);
   if (e != cudaSuccess) { cudaFree(t->d_pixels); delete t; return cuda_fail(e, "b2dgpu_target_create: cudaMemset"); }
+  t->rendered = nullptr; t->rendered_valid = false;
+  e = cudaEventCreateWithFlags(&t->rendered, cudaEventDisableTiming);
+  if (e != cudaSuccess) { cudaFree(t->d_pixels); delete t; return cuda_fail(e, "b2dgpu_target_create: cudaEventCreate"); }
   { std::lock_guard<std::mutex> g(g_registry_mutex); g_targets.push_back(t); }
   *out = t;
   return B2DGPU_SUCCESS;
@@ -475,6 +480,7 @@ extern "C" b2dgpu_result b2dgpu_target_destroy(b2dgpu_target* t) {
   cudaSetDevice(t->rt->device);
   cudaStreamSynchronize(t->rt->stream);
   cudaFree(t->d_pixels);
+  if (t->rendered) cudaEventDestroy(t->rendered);
   delete t;
   return B2DGPU_SUCCESS;
 }
@@ -483,6 +489,14 @@ extern "C" b2dgpu_result b2dgpu_target_clear(b2dgpu_target* t) {
   if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_clear: null");
   cudaSetDevice(t->rt->device);
   CU_TRY(cudaMemsetAsync(t->d_pixels, 0, t->stride * t->padded_h, t->rt->stream));
+  return B2DGPU_SUCCESS;
+}
+
+extern "C" b2dgpu_result b2dgpu_target_wait(b2dgpu_target* t, void* stream) {
+  if (!t) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_target_wait: invalid argument");
+  if (!t->rendered_valid) return B2DGPU_SUCCESS;           // nothing was rendered into it yet
+  cudaSetDevice(t->rt->device);
+  CU_TRY(cudaStreamWaitEvent((cudaStream_t)stream, t->rendered, 0));
   return B2DGPU_SUCCESS;
 }
 
@@ -1025,6 +1039,8 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     }
   }
   if (!streamed) launches += launch_tile_render(T, t->bpp, tile_h, s);
+  CU_TRY(cudaEventRecord(t->rendered, s));              // b2dgpu_target_wait(): stream-ordered consumers of this target
+  t->rendered_valid = true;
   }
   if (rt->profiling) {
     CU_TRY(cudaEventRecord(ev[2], s));

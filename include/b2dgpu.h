@@ -267,6 +267,10 @@ B2DGPU_API b2dgpu_result b2dgpu_host_register(b2dgpu_runtime* rt, void* pixels, 
 B2DGPU_API b2dgpu_result b2dgpu_host_unregister(b2dgpu_runtime* rt, void* pixels);
 /* Device view of the canvas (for torch / NCCL plumbing): base pointer of row y0, stride in bytes, padded extents. */
 B2DGPU_API b2dgpu_result b2dgpu_target_device_view(b2dgpu_target* t, void** dev_ptr, intptr_t* stride, int32_t* padded_w, int32_t* padded_h);
+/* Makes `stream` (a cudaStream_t) wait for the last render into `t` - and for nothing queued behind it: with
+ * b2dgpu_batch_render_multi() a consumer (the NCCL send of a stripe) can start on stripe j while stripes
+ * j + 1 .. are still being composited.  Returns immediately; no host synchronisation. */
+B2DGPU_API b2dgpu_result b2dgpu_target_wait(b2dgpu_target* t, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Seam A - render batch.

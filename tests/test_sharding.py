@@ -97,6 +97,8 @@ def worker(rank, world, port, out_dir):
 
 def test_world2_gloo_band_gather_and_frame_sharding(tmp_path):
     world = 2
+    from tests import hostsim
+    hostsim.lib()                 # build the simulator once here: the two workers must not run `make` on it concurrently
     mp.spawn(worker, args=(world, free_port(), str(tmp_path)), nprocs=world, join=True)
     canvas = np.load(tmp_path / "canvas.npy").view(np.uint32)
     assert np.array_equal(canvas, full_render(7))
