@@ -134,7 +134,109 @@ B2D_HD uint32_t comp_screen(uint32_t d, uint32_t s, uint32_t m) {
   return out;
 }
 
-enum CompOpId : uint32_t { kOpSrcOver = 0, kOpSrcCopy = 1, kOpPlus = 12, kOpMultiply = 15, kOpScreen = 16 };
+// ---------------------------------------------------------------------------------------------------------------
+// The other operators the JIT specifies for a PRGB32 destination (jit/compoppart.cpp v_mask_proc_rgba32_vec, the
+// `has_mask` variants :3731-5350; at m == 255 they reduce to the unmasked ones).  Restated channel by channel with the
+// JIT's 16-bit lane semantics: products and sums wrap at 16 bits (pmullw / paddw), v_div255_u16 is
+// ((x + 128) * 257) >> 16, the result is packed with unsigned saturation of the SIGNED 16-bit lane (packuswb).
+// The reference build here has no JIT, so these are unpinned like Multiply and Screen.
+// ---------------------------------------------------------------------------------------------------------------
+enum CompOpId : uint32_t {
+  kOpSrcOver = 0, kOpSrcCopy = 1, kOpSrcIn = 2, kOpSrcOut = 3, kOpSrcAtop = 4, kOpDstOver = 5, kOpDstCopy = 6, kOpDstIn = 7,
+  kOpDstOut = 8, kOpDstAtop = 9, kOpXor = 10, kOpClear = 11, kOpPlus = 12, kOpMinus = 13, kOpModulate = 14, kOpMultiply = 15,
+  kOpScreen = 16, kOpDarken = 18, kOpLighten = 19, kOpLinearBurn = 22, kOpDifference = 27, kOpExclusion = 28
+};
+
+B2D_HD uint32_t w16(uint32_t v) { return v & 0xFFFFu; }
+B2D_HD uint32_t subs_u16(uint32_t a, uint32_t b) { return a > b ? a - b : 0u; }
+B2D_HD uint32_t packus_i16(uint32_t v) { int32_t x = int32_t(int16_t(uint16_t(v))); return uint32_t(x < 0 ? 0 : x > 255 ? 255 : x); }
+B2D_HD uint32_t minmax_u8x2(uint32_t a, uint32_t b, bool take_min) {            // pminub / pmaxub on the two bytes of a lane
+  uint32_t al = a & 0xFFu, ah = (a >> 8) & 0xFFu, bl_ = b & 0xFFu, bh = (b >> 8) & 0xFFu;
+  uint32_t lo = take_min ? (al < bl_ ? al : bl_) : (al > bl_ ? al : bl_);
+  uint32_t hi = take_min ? (ah < bh ? ah : bh) : (ah > bh ? ah : bh);
+  return lo | (hi << 8);
+}
+
+B2D_HD uint32_t comp_jit_ext(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
+  const uint32_t da = d >> 24, sa = s >> 24;
+  const uint32_t n = 255u - m;                                                  // CompOpPart_negateMask
+  const uint32_t sma = jit_div255_u16(w16(sa * m));                             // alpha of S.m
+  uint32_t out = 0;
+  #pragma unroll
+  for (int sh = 0; sh < 32; sh += 8) {
+    const bool is_alpha = sh == 24;
+    const uint32_t dc = (d >> sh) & 0xFFu, sc = (s >> sh) & 0xFFu;
+    const uint32_t sm = jit_div255_u16(w16(sc * m));                            // S.m
+    uint32_t v;
+    switch (op) {
+      case kOpSrcIn: {        // Dca' = Sca.m.Da + Dca.(1 - m)                                          :3751-3774
+        uint32_t x = w16(jit_div255_u16(w16(da * sc)) * m);
+        v = jit_div255_u16(w16(w16(dc * n) + x));
+        break;
+      }
+      case kOpSrcOut: {       // Dca' = Sca.(1 - Da).m + Dca.(1 - m)                                    :3801-3826
+        uint32_t x = w16(jit_div255_u16(w16((255u - da) * sc)) * m);
+        v = jit_div255_u16(w16(w16(dc * n) + x));
+        break;
+      }
+      case kOpSrcAtop:        // Dca' = Sca.Da.m + Dca.(1 - Sa.m)                                       :3859-3879
+        v = jit_div255_u16(w16(w16(dc * (255u - sma)) + w16(da * sm)));
+        break;
+      case kOpDstOver:        // Dca' = Dca + Sca.m.(1 - Da); the sum is a 32-bit add of packed pixels   :3919-3937
+        v = packus_i16(jit_div255_u16(w16((255u - da) * sm)));
+        break;
+      case kOpDstIn:          // Dca' = Dca.(1 - m.(1 - Sa))                                            :3969-3983
+        v = jit_div255_u16(w16(dc * (255u - jit_div255_u16(w16((255u - sa) * m)))));
+        break;
+      case kOpDstOut:         // Dca' = Dca.(1 - Sa.m)                                                  :4012-4026
+        v = jit_div255_u16(w16(dc * (255u - sma)));
+        break;
+      case kOpDstAtop: {      // Dca' = Dca.(1 - m.(1 - Sa)) + Sca.m.(1 - Da)                           :4061-4085
+        uint32_t u = 255u - jit_div255_u16(w16((255u - sa) * m));
+        v = jit_div255_u16(w16(w16(dc * u) + w16((255u - da) * sm)));
+        break;
+      }
+      case kOpXor:            // Dca' = Dca.(1 - Sa.m) + Sca.m.(1 - Da)                                 :4119-4140
+        v = jit_div255_u16(w16(w16(dc * (255u - sma)) + w16(sm * (255u - da))));
+        break;
+      case kOpMinus: {        // Dca' = (Clamp(Dca - Sca) + Sca.(1 - Da)).m + Dca.(1 - m); Da' = Da + Sa.m.(1 - Da)  :4229-4256
+        uint32_t t = is_alpha ? 0u : subs_u16(dc, sc);
+        t = w16(t + jit_div255_u16(w16(sc * (255u - da))));
+        v = jit_div255_u16(w16(w16(t * m) + w16(dc * (is_alpha ? 255u : n))));
+        break;
+      }
+      case kOpModulate:       // Dca' = Dca.(Sca.m + 1 - m)                                             :4303-4313
+        v = jit_div255_u16(w16(dc * w16(sm + 255u - m)));
+        break;
+      case kOpDarken:
+      case kOpLighten: {      // Dca' = minmax(Dca + Sca.(1 - Da), Sca + Dca.(1 - Sa)) on S.m           :4654-4678
+        uint32_t x = jit_div255_u16(w16((255u - da) * sm));
+        uint32_t y = jit_div255_u16(w16((255u - sma) * dc));
+        v = minmax_u8x2(w16(dc + x), w16(sm + y), op == kOpDarken);
+        break;
+      }
+      case kOpLinearBurn:     // Dca' = Dca + Sca - Sa.Da on S.m                                        :4861-4870
+        v = subs_u16(w16(dc + sm), jit_div255_u16(w16(sma * da)));
+        break;
+      case kOpDifference: {   // Dca' = Dca + Sca.m - 2.min(Sca.Da, Dca.Sa).m; alpha subtracts it once    :5287-5314
+        uint32_t a = w16(sma * dc), b = w16(da * sm);
+        uint32_t y = jit_div255_u16(a < b ? a : b);
+        v = w16(w16(dc + sm) - y);
+        if (!is_alpha) v = w16(v - y);
+        break;
+      }
+      default: {              // kOpExclusion: Dca' = Dca + Sca - 2.Sca.Dca on S.m; alpha subtracts once  :5326-5346
+        uint32_t x = jit_div255_u16(w16(dc * sm));
+        v = w16(w16(dc + sm) - x);
+        if (!is_alpha) v = w16(v - x);
+        break;
+      }
+    }
+    out |= packus_i16(v) << sh;
+  }
+  if (op == kOpDstOver) out += d;                                               // v_add_i32 on the packed pixels
+  return out;
+}
 
 B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) {
   switch (comp_op) {
@@ -142,7 +244,8 @@ B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) 
     case kOpSrcCopy:  return comp_src_copy(d, s, m);
     case kOpPlus:     return comp_plus(d, s, m);
     case kOpMultiply: return comp_multiply(d, s, m);
-    default:          return comp_screen(d, s, m);
+    case kOpScreen:   return comp_screen(d, s, m);
+    default:          return comp_jit_ext(comp_op, d, s, m);
   }
 }
 
@@ -151,7 +254,8 @@ B2D_HD_COLD uint32_t composite_cold(uint32_t comp_op, uint32_t d, uint32_t s, ui
   switch (comp_op) {
     case kOpPlus:     return comp_plus(d, s, m);
     case kOpMultiply: return comp_multiply(d, s, m);
-    default:          return comp_screen(d, s, m);
+    case kOpScreen:   return comp_screen(d, s, m);
+    default:          return comp_jit_ext(comp_op, d, s, m);
   }
 }
 

@@ -146,7 +146,9 @@ inline uint32_t format_from_rgba32(uint32_t rgba32) {                          /
 // override the reference applies (transparent / opaque black / opaque white).
 // ---------------------------------------------------------------------------------------------------------------
 enum SolidId : uint32_t { kSolidNone = 0, kSolidTransparent = 1, kSolidOpaqueBlack = 2, kSolidOpaqueWhite = 3, kSolidNop = 4 };
-enum : uint32_t { kOpSrcOver = 0, kOpSrcCopy = 1, kOpDstOver = 5, kOpDstCopy = 6, kOpClear = 11, kOpPlus = 12, kOpModulate = 14, kOpMultiply = 15, kOpScreen = 16 };
+enum : uint32_t { kOpSrcOver = 0, kOpSrcCopy = 1, kOpSrcIn = 2, kOpSrcOut = 3, kOpSrcAtop = 4, kOpDstOver = 5, kOpDstCopy = 6, kOpDstIn = 7,
+                  kOpDstOut = 8, kOpDstAtop = 9, kOpXor = 10, kOpClear = 11, kOpPlus = 12, kOpMinus = 13, kOpModulate = 14, kOpMultiply = 15,
+                  kOpScreen = 16, kOpDarken = 18, kOpLighten = 19, kOpLinearBurn = 22, kOpDifference = 27, kOpExclusion = 28 };
 
 struct Simplified { uint32_t op, dst, src, solid; bool implemented; };
 
@@ -224,6 +226,13 @@ Simplified simplify(uint32_t op, uint32_t d, uint32_t s) {
     case kOpPlus: return s_plus(d, s);
     case kOpMultiply: return s_multiply(d, s);
     case kOpScreen: return s_screen(d, s);
+    // The other operators of the GPU runtime (dev_pixel.cuh comp_jit_ext): this mirror only knows the case the
+    // reference leaves untouched, PRGB32 x PRGB32 (core/compopsimplifyimpl_p.h: every [Op PRGBxPRGB] entry is the operator
+    // itself); sources without alpha are rewritten there (SrcAtop -> SrcIn, Xor -> SrcOut, ...) - applications get
+    // that through the real frontend (shim/).
+    case kOpSrcIn: case kOpSrcOut: case kOpSrcAtop: case kOpDstOver: case kOpDstIn: case kOpDstOut: case kOpDstAtop: case kOpXor:
+    case kOpMinus: case kOpModulate: case kOpDarken: case kOpLighten: case kOpLinearBurn: case kOpDifference: case kOpExclusion:
+      return d == P && s == P ? mk_op(op, d, s) : mk_unimpl(op, d, s);
     default: return mk_unimpl(op, d, s);
   }
 }
@@ -936,7 +945,6 @@ Resolved resolve(b2d_context* c, bool is_clear) {
   Simplified s = simplify(op, c->dst_format, src_format);
   if (s.solid == kSolidNop) return r;
   if (!s.implemented) { r.err = B2DGPU_ERROR_NOT_IMPLEMENTED; return r; }
-  if (!(s.op == kOpSrcOver || s.op == kOpSrcCopy || s.op == kOpPlus || s.op == kOpMultiply || s.op == kOpScreen)) { r.err = B2DGPU_ERROR_NOT_IMPLEMENTED; return r; }
 
   r.nop = false;
   r.alpha = is_clear ? 255u : c->fill_alpha_i;

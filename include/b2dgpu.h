@@ -75,8 +75,14 @@ enum {
 
 /* BLCompOp (blend2d/core/context.h:244-300) - the subset the GPU runtime implements. */
 enum {
-  B2DGPU_COMP_OP_SRC_OVER = 0, B2DGPU_COMP_OP_SRC_COPY = 1, B2DGPU_COMP_OP_PLUS = 12,
-  B2DGPU_COMP_OP_MULTIPLY = 15, B2DGPU_COMP_OP_SCREEN = 16
+  B2DGPU_COMP_OP_SRC_OVER = 0, B2DGPU_COMP_OP_SRC_COPY = 1, B2DGPU_COMP_OP_SRC_IN = 2, B2DGPU_COMP_OP_SRC_OUT = 3,
+  B2DGPU_COMP_OP_SRC_ATOP = 4, B2DGPU_COMP_OP_DST_OVER = 5, B2DGPU_COMP_OP_DST_COPY = 6, B2DGPU_COMP_OP_DST_IN = 7,
+  B2DGPU_COMP_OP_DST_OUT = 8, B2DGPU_COMP_OP_DST_ATOP = 9, B2DGPU_COMP_OP_XOR = 10, B2DGPU_COMP_OP_CLEAR = 11,
+  B2DGPU_COMP_OP_PLUS = 12, B2DGPU_COMP_OP_MINUS = 13, B2DGPU_COMP_OP_MODULATE = 14, B2DGPU_COMP_OP_MULTIPLY = 15,
+  B2DGPU_COMP_OP_SCREEN = 16, B2DGPU_COMP_OP_OVERLAY = 17, B2DGPU_COMP_OP_DARKEN = 18, B2DGPU_COMP_OP_LIGHTEN = 19,
+  B2DGPU_COMP_OP_COLOR_DODGE = 20, B2DGPU_COMP_OP_COLOR_BURN = 21, B2DGPU_COMP_OP_LINEAR_BURN = 22,
+  B2DGPU_COMP_OP_LINEAR_LIGHT = 23, B2DGPU_COMP_OP_PIN_LIGHT = 24, B2DGPU_COMP_OP_HARD_LIGHT = 25,
+  B2DGPU_COMP_OP_SOFT_LIGHT = 26, B2DGPU_COMP_OP_DIFFERENCE = 27, B2DGPU_COMP_OP_EXCLUSION = 28
 };
 
 /* FillType (pipedefs_p.h:64-76). */

@@ -96,6 +96,118 @@ static uint32_t orc_screen(uint32_t d, uint32_t s, uint32_t m) {
   return out;
 }
 
+/* The remaining operators of the JIT for a PRGB32 destination, masked variants (`has_mask`), restated as the SEQUENCE of
+ * vector instructions the JIT emits (compoppart.cpp v_mask_proc_rgba32_vec), on four 16-bit lanes b, g, r, a.
+ * UNPINNED: the reference build here has no JIT (asmjit is not vendored) and its portable pipeline has none of them.
+ *   sv / dv = source / destination channels, vm = mask in every lane, xv / yv = scratch registers like in the JIT. */
+typedef struct { uint32_t l[4]; } v4;
+static v4 v_load(uint32_t p) { v4 r; for (int i = 0; i < 4; i++) r.l[i] = (p >> (8 * i)) & 0xFFu; return r; }
+static v4 v_set1(uint32_t x) { v4 r; for (int i = 0; i < 4; i++) r.l[i] = x & 0xFFFFu; return r; }
+static v4 v_mul(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = jit_mul16(a.l[i], b.l[i]); return a; }
+static v4 v_add(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = jit_add16(a.l[i], b.l[i]); return a; }
+static v4 v_sub(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = (a.l[i] - b.l[i]) & 0xFFFFu; return a; }
+static v4 v_subs(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] > b.l[i] ? a.l[i] - b.l[i] : 0u; return a; }   /* psubusw */
+static v4 v_d255(v4 a) { for (int i = 0; i < 4; i++) a.l[i] = jit_div255(a.l[i]); return a; }
+static v4 v_inv255(v4 a) { for (int i = 0; i < 4; i++) a.l[i] = (a.l[i] ^ 0x00FFu) & 0xFFFFu; return a; }                 /* pxor 0x00FF */
+static v4 v_alpha(v4 a) { return v_set1(a.l[3]); }                                                                        /* v_expand_alpha_16 */
+static v4 v_zero_alpha(v4 a) { a.l[3] = 0; return a; }                                                                    /* vZeroAlphaW */
+static v4 v_minu16(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] < b.l[i] ? a.l[i] : b.l[i]; return a; }
+static v4 v_minmax_u8(v4 a, v4 b, int take_min) {
+  for (int i = 0; i < 4; i++) {
+    uint32_t r = 0;
+    for (int k = 0; k < 16; k += 8) {
+      uint32_t x = (a.l[i] >> k) & 0xFFu, y = (b.l[i] >> k) & 0xFFu;
+      r |= (take_min ? (x < y ? x : y) : (x > y ? x : y)) << k;
+    }
+    a.l[i] = r;
+  }
+  return a;
+}
+static uint32_t v_packus(v4 a) { uint32_t p = 0; for (int i = 0; i < 4; i++) p |= jit_packus(a.l[i]) << (8 * i); return p; }
+
+enum { ORC_SRC_IN = 2, ORC_SRC_OUT = 3, ORC_SRC_ATOP = 4, ORC_DST_OVER = 5, ORC_DST_IN = 7, ORC_DST_OUT = 8, ORC_DST_ATOP = 9, ORC_XOR = 10,
+       ORC_MINUS = 13, ORC_MODULATE = 14, ORC_DARKEN = 18, ORC_LIGHTEN = 19, ORC_LINEAR_BURN = 22, ORC_DIFFERENCE = 27, ORC_EXCLUSION = 28 };
+
+static uint32_t orc_jit_ext(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
+  v4 sv = v_load(s), dv = v_load(d), vm = v_set1(m), vn = v_inv255(vm), xv, yv, uv;
+  switch (op) {
+    case ORC_SRC_IN:                                                                 /* compoppart.cpp:3751-3774 */
+      xv = v_alpha(dv); xv = v_mul(xv, sv); xv = v_d255(xv); xv = v_mul(xv, vm);
+      dv = v_mul(dv, vn); dv = v_add(dv, xv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_SRC_OUT:                                                                /* :3801-3826 */
+      xv = v_alpha(dv); xv = v_inv255(xv); xv = v_mul(xv, sv); xv = v_d255(xv); xv = v_mul(xv, vm);
+      dv = v_mul(dv, vn); dv = v_add(dv, xv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_SRC_ATOP:                                                               /* :3859-3879 */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_alpha(sv); xv = v_inv255(xv); yv = v_alpha(dv);
+      dv = v_mul(dv, xv); yv = v_mul(yv, sv); dv = v_add(dv, yv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_DST_OVER:                                                               /* :3919-3937: d.ui * S.m, packed, + d.pc */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_inv255(v_alpha(dv)); xv = v_mul(xv, sv); xv = v_d255(xv);
+      return v_packus(xv) + d;
+    case ORC_DST_IN:                                                                 /* :3969-3983: s.ui = 255 - Sa */
+      uv = v_inv255(v_alpha(sv)); uv = v_mul(uv, vm); uv = v_d255(uv); uv = v_inv255(uv);
+      dv = v_mul(dv, uv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_DST_OUT:                                                                /* :4012-4026: s.ua = Sa */
+      uv = v_alpha(sv); uv = v_mul(uv, vm); uv = v_d255(uv); uv = v_inv255(uv);
+      dv = v_mul(dv, uv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_DST_ATOP:                                                               /* :4061-4085 */
+      uv = v_inv255(v_alpha(sv));
+      xv = v_alpha(dv);
+      sv = v_mul(sv, vm); uv = v_mul(uv, vm); sv = v_d255(sv); uv = v_d255(uv);
+      xv = v_inv255(xv); uv = v_inv255(uv);
+      xv = v_mul(xv, sv); dv = v_mul(dv, uv); dv = v_add(dv, xv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_XOR:                                                                    /* :4119-4140 */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_inv255(v_alpha(sv)); yv = v_inv255(v_alpha(dv));
+      dv = v_mul(dv, xv); sv = v_mul(sv, yv); dv = v_add(dv, sv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_MINUS:                                                                  /* :4229-4256 (use_da) */
+      xv = v_alpha(dv); yv = dv; xv = v_inv255(xv);
+      dv = v_subs(dv, sv); sv = v_mul(sv, xv); dv = v_zero_alpha(dv); sv = v_d255(sv);
+      dv = v_add(dv, sv); dv = v_mul(dv, vm);
+      vm = v_zero_alpha(vm); vm = v_inv255(vm); yv = v_mul(yv, vm);
+      dv = v_add(dv, yv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_MODULATE:                                                               /* :4303-4313 */
+      sv = v_mul(sv, vm); sv = v_d255(sv); sv = v_add(sv, v_set1(0x00FF)); sv = v_sub(sv, vm);
+      dv = v_mul(dv, sv); dv = v_d255(dv);
+      return v_packus(dv);
+    case ORC_DARKEN:
+    case ORC_LIGHTEN:                                                                /* :4650-4678 (has_mask => use_sa) */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_inv255(v_alpha(dv)); yv = v_inv255(v_alpha(sv));
+      xv = v_mul(xv, sv); yv = v_mul(yv, dv); xv = v_d255(xv); yv = v_d255(yv);
+      dv = v_add(dv, xv); sv = v_add(sv, yv);
+      dv = v_minmax_u8(dv, sv, op == ORC_DARKEN);
+      return v_packus(dv);
+    case ORC_LINEAR_BURN:                                                            /* :4853-4870 */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_alpha(sv); yv = v_alpha(dv); xv = v_mul(xv, yv); xv = v_d255(xv);
+      dv = v_add(dv, sv); dv = v_subs(dv, xv);
+      return v_packus(dv);
+    case ORC_DIFFERENCE:                                                             /* :5287-5314 */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      yv = v_alpha(sv); xv = v_alpha(dv);
+      yv = v_mul(yv, dv); xv = v_mul(xv, sv); dv = v_add(dv, sv); yv = v_minu16(yv, xv);
+      yv = v_d255(yv); dv = v_sub(dv, yv); yv = v_zero_alpha(yv); dv = v_sub(dv, yv);
+      return v_packus(dv);
+    case ORC_EXCLUSION:                                                              /* :5326-5346 */
+      sv = v_mul(sv, vm); sv = v_d255(sv);
+      xv = v_mul(dv, sv); dv = v_add(dv, sv); xv = v_d255(xv);
+      dv = v_sub(dv, xv); xv = v_zero_alpha(xv); dv = v_sub(dv, xv);
+      return v_packus(dv);
+    default:
+      return d;
+  }
+}
+
 /* A8 pixels (P8_Alpha / U8_Alpha, pixelgeneric_p.h:85-200): one 16-bit lane, packed adds wrap at 8 bits. */
 static uint32_t a8_div255(uint32_t u) { u = (u + 0x80u) & 0xFFFFu; return ((u + ((u >> 8) & 0xFFu)) >> 8) & 0xFFu; }
 static uint32_t orc_a8_src_copy(uint32_t d, uint32_t s, uint32_t m) { return a8_div255(d * (m ^ 0xFFu) + s * m); }
@@ -113,7 +225,8 @@ ORC_API uint32_t orc_composite_prgb32(uint32_t op, uint32_t d, uint32_t s, uint3
     case ORC_SRC_COPY: return orc_src_copy(d, s, m);
     case ORC_PLUS: return orc_plus(d, s, m);
     case ORC_MULTIPLY: return orc_multiply(d, s, m);
-    default: return orc_screen(d, s, m);
+    case ORC_SCREEN: return orc_screen(d, s, m);
+    default: return orc_jit_ext(op, d, s, m);
   }
 }
 

@@ -307,3 +307,64 @@ def test_gpu_plus_against_reference_templates(ref, refint, gpu, seed):
     ctx.end()
     got = img.to_numpy().copy(); ctx.close()
     assert np.array_equal(got, expected_plus_from_reference(ref, refint, backdrop, rects, shapes, w, h))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the rest of the Porter-Duff set and the division-free separable operators (dev_pixel.cuh comp_jit_ext).
+# UNPINNED like Multiply / Screen: the checker is oracle/b2d_oracle.c orc_jit_ext, which replays the JIT's instruction
+# sequences (pipeline/jit/compoppart.cpp:3731-5350); masks come from the pinned rasterizer restatement.
+# ---------------------------------------------------------------------------------------------------------------------
+EXT_OPS = [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 18, 19, 22, 27, 28]
+
+
+def translucent_shapes(seed, w, h, n):
+    backdrop, shapes = make_shapes(seed, w, h, n)
+    # alpha < 255 keeps the style PRGB32: an opaque colour is an XRGB32 source, which the frontend rewrites into another
+    # operator (core/compopsimplifyimpl_p.h) - the mirror used here only implements PRGB32 x PRGB32 for these operators
+    return backdrop, [(pts, color & 0xFEFFFFFF, alpha) for pts, color, alpha in shapes]
+
+
+@pytest.mark.parametrize("op", EXT_OPS)
+def test_hostsim_extended_operators_against_oracle(op):
+    import blend2d_b200 as G
+    from tests import hostsim
+    w, h = 150, 100
+    backdrop, shapes = translucent_shapes(500 + op, w, h, 12)
+    img = G.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = G.Context(img, record_only=True)
+    jit_only_scene(op, backdrop, shapes)(G, ctx, None)
+    hostsim.render(ctx, img)
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_jit_only(op, backdrop, shapes, w, h))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("op", EXT_OPS)
+def test_gpu_extended_operators_against_oracle(gpu, op):
+    w, h = 300, 200
+    backdrop, shapes = translucent_shapes(600 + op, w, h, 30)
+    img = gpu.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = gpu.Context(img)
+    jit_only_scene(op, backdrop, shapes)(gpu, ctx, None)
+    ctx.end()
+    got = img.to_numpy().copy(); ctx.close()
+    assert np.array_equal(got, expected_jit_only(op, backdrop, shapes, w, h))
+
+
+def test_extended_operator_identities():
+    one = lambda op, d, s, m: int(O.lib().orc_composite_prgb32(op, d, s, m))
+    d, s = 0x80402010, 0xC0603020
+    assert one(2, 0x00000000, s, 255) == 0                     # SrcIn: nothing where the backdrop is transparent
+    assert one(2, 0xFF102030, s, 255) == s                     # SrcIn: the source where it is opaque
+    assert one(3, 0xFF102030, s, 255) == 0                     # SrcOut: nothing where the backdrop is opaque
+    assert one(5, 0xFF102030, s, 255) == 0xFF102030            # DstOver: an opaque backdrop hides the source
+    assert one(5, 0x00000000, s, 255) == s
+    assert one(7, d, 0xFF000000, 255) == d                     # DstIn with an opaque source keeps the backdrop
+    assert one(8, d, 0xFF000000, 255) == 0                     # DstOut with an opaque source clears it
+    assert one(10, 0, s, 255) == s and one(10, d, 0, 255) == d # Xor with nothing
+    assert one(14, d, 0xFFFFFFFF, 255) == d                    # Modulate by white
+    assert one(18, 0xFF808080, 0xFF404040, 255) == 0xFF404040  # Darken / Lighten of opaque greys
+    assert one(19, 0xFF808080, 0xFF404040, 255) == 0xFF808080
+    assert one(27, 0xFF808080, 0xFF808080, 255) == 0xFF000000  # Difference of equal opaque colours
+    for op in EXT_OPS:
+        assert one(op, d, s, 0) == d

@@ -195,8 +195,11 @@ def test_pipe_runtime_lookup_semantics(gpu):
     ok = sig(1, 1, 0, 3, 0)                                   # PRGB32 <- PRGB32, SrcOver, analytic fill, solid fetch
     assert N.lib.b2dgpu_runtime_get(rt._h, ok, C.byref(dd), None) == 0 and dd.fill_func
     assert N.lib.b2dgpu_runtime_test(rt._h, ok, C.byref(dd), None) == 0
-    src_in = sig(1, 1, 2, 3, 0)                               # BL_COMP_OP_SRC_IN: a next-row operator
-    assert N.lib.b2dgpu_runtime_get(rt._h, src_in, C.byref(dd), None) == 0x10007      # BL_ERROR_NOT_IMPLEMENTED
-    assert N.lib.b2dgpu_runtime_test(rt._h, src_in, C.byref(dd), None) == 0x10017     # BL_ERROR_NO_ENTRY
+    assert N.lib.b2dgpu_runtime_get(rt._h, sig(1, 1, 2, 3, 0), C.byref(dd), None) == 0 # BL_COMP_OP_SRC_IN on PRGB32: implemented
+    overlay = sig(1, 1, 17, 3, 0)                             # BL_COMP_OP_OVERLAY: outside the runtime's table
+    src_in_a8 = sig(3, 1, 2, 3, 0)                            # SrcIn on an A8 destination: the JIT has separate code, we have none
+    for missing in (overlay, src_in_a8):
+        assert N.lib.b2dgpu_runtime_get(rt._h, missing, C.byref(dd), None) == 0x10007      # BL_ERROR_NOT_IMPLEMENTED
+        assert N.lib.b2dgpu_runtime_test(rt._h, missing, C.byref(dd), None) == 0x10017     # BL_ERROR_NO_ENTRY
     assert N.lib.b2dgpu_runtime_get(rt._h, ok | 0x80000000, C.byref(dd), None) != 0    # pending flag: not a pipeline
     rt.close()

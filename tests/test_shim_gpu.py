@@ -150,3 +150,38 @@ def test_existing_pixels_and_incremental_flush(B):
 def test_many_small_batches(B):
     cpu, gpu = both(B, S.mixed(200, 256, 256), 256, 256, seed=3, command_queue_limit=16)
     assert_same(cpu, gpu, 1)
+
+
+@pytest.mark.parametrize("op", [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 18, 19, 22, 27, 28])
+def test_extended_operators_through_blend2d(B, op):
+    """SURVEY 8f-2 through the real frontend: bl_context_set_comp_op(op) on a GPU context.  The reference's portable
+    pipeline has none of these operators (its CPU context answers BL_ERROR_NOT_IMPLEMENTED), so the expected image is
+    built from the masks the CPU context rasterizes (SrcCopy of opaque white) and the C restatement of the JIT's
+    operator (oracle/b2d_oracle.c orc_jit_ext; unpinned)."""
+    from oracle import c_oracle as O
+    from tests.test_oracle import premul, premultiply_rgba32
+    w, h = 320, 200
+    rng = np.random.default_rng(40 + op)
+    backdrop = premul(rng, (h, w))
+    shapes = [(rng.uniform(0, 1, (6, 2)) * [w, h], int(rng.integers(0, 2 ** 32)) & 0xFEFFFFFF, float(rng.choice([1.0, 0.6]))) for _ in range(16)]
+
+    img = B.Image(w, h, 1); img.from_numpy(backdrop)
+    ctx = B.Context(img)
+    ctx.set_comp_op(op)
+    for pts, color, alpha in shapes:
+        ctx.set_fill_style(color); ctx.set_global_alpha(alpha)
+        ctx.fill_polygon(pts.reshape(-1).tolist())
+    ctx.end()
+    assert ctx.accumulated_error_flags() == 0
+    got = img.to_numpy().copy(); ctx.close()
+
+    want = backdrop.copy()
+    for pts, color, alpha in shapes:
+        mi = B.Image(w, h, 1)
+        mc = B.cpu_context(mi)
+        mc.set_comp_op(S.SRC_COPY); mc.set_fill_style(0xFFFFFFFF); mc.set_global_alpha(alpha)
+        mc.fill_polygon(pts.reshape(-1).tolist())
+        mc.end(); mc.close()
+        mask = (mi.to_numpy() & 0xFF).astype(np.uint8)
+        want = O.composite_prgb32(op, want, premultiply_rgba32(color), mask)
+    assert np.array_equal(got, want)
