@@ -76,6 +76,8 @@ struct WriteOutLane {
   }
 };
 
+enum : int { kBigCurve = 48 };        // control polygon wider / taller than this many pixels: flattened by the whole warp
+
 // Per-warp scratch of the edge builder.
 struct K1Warp {
   P2 spline[8 * 3 + 1];              // monotone pieces of the curve being flattened
@@ -217,7 +219,7 @@ __device__ __forceinline__ void flatten_curve_warp(const SegmentInput& in, K1War
 //   WRITE == false: seg_counts[i] = edges of segment i.
 //   WRITE == true : the edges are written at seg_offsets[i] .. seg_offsets[i + 1]; the command's bounding box grows.
 template<bool WRITE>
-__global__ void __launch_bounds__(128) k_build_edges(BuildParams P) {
+__global__ void __launch_bounds__(128, 5) k_build_edges(BuildParams P) {
   __shared__ K1Warp s_warp[4];
   const int lane = threadIdx.x & 31;
   K1Warp& W = s_warp[threadIdx.x >> 5];
@@ -240,28 +242,46 @@ __global__ void __launch_bounds__(128) k_build_edges(BuildParams P) {
   }
   const bool active = valid && (!WRITE || writable);
 
-  // ---- lines: one per lane ----
-  if (active && kind == B2DGPU_SEG_LINE) {
+  // ---- lines and small curves: one per lane (a glyph-sized curve flattens into a handful of lines; sharing it over
+  //      a warp would cost more than it saves) ----
+  bool big = false;
+  if (active) {
     const SegmentInput in = load_segment(P, i);
-    if (!WRITE) {
-      CountOut out; out.n = 0;
-      build_line(in.p[0], in.p[1], in.cb, out);
-      P.seg_counts[i] = out.n;
+    if (kind != B2DGPU_SEG_LINE) {
+      // size of the control polygon against kBigCurve pixels (24.8 units): NaNs compare false -> handled here
+      const double lim = double(kBigCurve) * 256.0;
+      #pragma unroll
+      for (int k = 1; k < 4; k++) {
+        const double dx = in.p[k].x - in.p[0].x, dy = in.p[k].y - in.p[0].y;
+        big = big || dx > lim || dx < -lim || dy > lim || dy < -lim;
+      }
     }
-    else {
-      WriteOutLane out;
-      out.dst = P.edges + P.edge_base + begin; out.n = 0;
-      out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
-      build_line(in.p[0], in.p[1], in.cb, out);
-      int4* bb = P.cmd_bbox_fixed + P.segments[i].command;
-      atomicMin(&bb->x, out.min_x); atomicMin(&bb->y, out.min_y);
-      atomicMax(&bb->z, out.max_x); atomicMax(&bb->w, out.max_y);
+    if (!big) {
+      if (!WRITE) {
+        CountOut out; out.n = 0;
+        if (kind == B2DGPU_SEG_LINE) build_line(in.p[0], in.p[1], in.cb, out);
+        else if (kind == B2DGPU_SEG_CUBIC) build_cubic(in.p[0], in.p[1], in.p[2], in.p[3], in.cb, in.tol_sq, out);
+        else build_quad(in.p[0], in.p[1], in.p[2], in.cb, in.tol_sq, out);
+        P.seg_counts[i] = out.n;
+      }
+      else {
+        WriteOutLane out;
+        out.dst = P.edges + P.edge_base + begin; out.n = 0;
+        out.min_x = out.min_y = INT_MAX; out.max_x = out.max_y = INT_MIN;
+        if (kind == B2DGPU_SEG_LINE) build_line(in.p[0], in.p[1], in.cb, out);
+        else if (kind == B2DGPU_SEG_CUBIC) build_cubic(in.p[0], in.p[1], in.p[2], in.p[3], in.cb, in.tol_sq, out);
+        else build_quad(in.p[0], in.p[1], in.p[2], in.cb, in.tol_sq, out);
+        if (out.n) {
+          int4* bb = P.cmd_bbox_fixed + P.segments[i].command;
+          atomicMin(&bb->x, out.min_x); atomicMin(&bb->y, out.min_y);
+          atomicMax(&bb->z, out.max_x); atomicMax(&bb->w, out.max_y);
+        }
+      }
     }
   }
-  else if (valid && !WRITE && kind == B2DGPU_SEG_LINE) P.seg_counts[i] = 0;
 
-  // ---- curves: the warp takes them one at a time ----
-  uint32_t todo = __ballot_sync(0xFFFFFFFFu, active && kind != B2DGPU_SEG_LINE);
+  // ---- big curves: the warp takes them one at a time ----
+  uint32_t todo = __ballot_sync(0xFFFFFFFFu, big);
   if (!WRITE) {
     // segments that are skipped still need a count
     if (valid && !active) P.seg_counts[i] = 0;

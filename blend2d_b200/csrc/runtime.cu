@@ -963,7 +963,11 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   // Per-band command lists with x-extents (k_bin_*).  Their size is only known on the device: the buffer holds
   // `bin_capacity` cells (the dense bound tiles_y * commands when that is small); a render that needed more renders
   // without lists (every tile scans every command - slow but correct) and the buffer is grown for the next one.
-  {
+  // A batch of boxes only on a small canvas (bl_bench rectangles on 512 x 600) is culled exactly by the pixel boxes;
+  // when all tiles x commands tests are few the lists cost more than they save.
+  const bool bin = in.has_analytic || in.segment_count ||
+                   size_t(in.command_count) * size_t(T.tiles_x) * size_t(T.tiles_y) > (size_t(128) << 20);
+  if (bin) {
     const size_t dense = size_t(in.command_count) * size_t(T.tiles_y);
     if (rt->h_bin_state[1] == 0u && rt->h_bin_state[0] > rt->bin_capacity)
       rt->bin_capacity = rt->h_bin_state[0] + rt->h_bin_state[0] / 4u;                    // reported by an earlier render
