@@ -66,7 +66,12 @@ class BatchView(C.Structure):
                 ("vertices", f64p), ("vertex_count", C.c_uint32), ("_pad2", C.c_uint32),
                 ("segments", C.POINTER(Segment)), ("segment_count", C.c_uint32), ("_pad3", C.c_uint32),
                 ("geometry_states", C.POINTER(GeometryState)), ("geometry_state_count", C.c_uint32), ("_pad4", C.c_uint32),
-                ("pixel_origin_x", C.c_int32), ("pixel_origin_y", C.c_int32)]
+                ("pixel_origin_x", C.c_int32), ("pixel_origin_y", C.c_int32),
+                # glyph instancing (include/b2dgpu.h b2dgpu_glyph_instance); unused by the Python veneer
+                ("glyph_cache", C.c_void_p), ("glyph_cache_words", C.c_uint32), ("_pad5", C.c_uint32),
+                ("glyph_cache_id", C.c_uint64),
+                ("glyph_instances", C.c_void_p), ("glyph_instance_count", C.c_uint32), ("_pad6", C.c_uint32),
+                ("generated_vertex_count", C.c_uint32), ("generated_segment_count", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -26,11 +26,39 @@
 #include "dev_flatten.cuh"
 #include "dev_fetch.cuh"
 #include "dev_tile.cuh"
+#include "dev_glyph.cuh"
 
 #include <cuda_runtime.h>
 #include <limits.h>
 
 namespace b2d {
+
+// =================================================================================================================
+// K0 - glyph instancing: TrueType outline + instance matrix -> vertices + path segments
+// =================================================================================================================
+struct GlyphVertexPut {
+  double2* dst;
+  __device__ __forceinline__ void operator()(uint32_t index, double x, double y) { dst[index] = make_double2(x, y); }
+};
+
+__global__ void __launch_bounds__(128) k_glyph_instances(GlyphParams P) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.instance_count) return;
+  const b2dgpu_glyph_instance inst = P.instances[i];
+  const GlyphBlobView g = glyph_blob_view(P.cache + inst.blob_offset);
+  GlyphVertexPut put{ reinterpret_cast<double2*>(P.vertices) + inst.vertex_base };
+  const uint32_t n = glyph_emit(g, inst.m, put);
+  if (n != g.vertices) atomicOr(P.error_flag, 2u);                 // the host checked every entry: cannot happen
+  const uint32_t* sw = g.segment_words();
+  b2dgpu_segment* seg = P.segments + inst.segment_base;
+  for (uint32_t k = 0; k < g.segments; k++) {
+    b2dgpu_segment o;
+    o.p0 = inst.vertex_base + sw[2 * k];
+    o.p1_kind = ((inst.vertex_base + (sw[2 * k + 1] >> 2)) << 2) | (sw[2 * k + 1] & 3u);
+    o.command = inst.command;
+    seg[k] = o;
+  }
+}
 
 // =================================================================================================================
 // K1 - edge builder
@@ -1278,6 +1306,12 @@ __global__ void __launch_bounds__(256) k_stream_solid(SolidStreamParams P, int c
 // Launchers (host)
 // =================================================================================================================
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int launch_glyph_instances(const GlyphParams& P, cudaStream_t s) {
+  if (!P.instance_count) return 0;
+  k_glyph_instances<<<div_up(P.instance_count, 128), 128, 0, s>>>(P);
+  return 1;
+}
 
 int launch_count_edges(const BuildParams& P, cudaStream_t s) {
   if (!P.segment_count) return 0;

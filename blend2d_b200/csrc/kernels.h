@@ -57,6 +57,18 @@ struct TileParams {
   unsigned long long* pixel_counter;
 };
 
+// K0: glyph instancing (dev_glyph.cuh).  One thread per instance writes the glyph's vertices and path segments into the
+// batch's arrays, behind the uploaded ones.
+struct GlyphParams {
+  const uint32_t* cache;                  // device mirror of the caller's glyph cache
+  const b2dgpu_glyph_instance* instances;
+  uint32_t instance_count;
+  double* vertices;                       // the batch's vertex array (x, y pairs)
+  b2dgpu_segment* segments;               // the batch's segment array
+  uint32_t* error_flag;
+};
+int launch_glyph_instances(const GlyphParams& P, cudaStream_t s);
+
 // Binning (K1d): per-band ordered command lists with x-extents, the GPU form of the reference's per-band edge lists
 // (raster/edgestorage_p.h:38-178) and of its band-by-band command walk (raster/workerproc.cpp:166-255).
 struct BinParams {

@@ -4,6 +4,7 @@
 // block -> one H2D copy -> pointer patching), and the kernel sequence  K1 count -> scan -> K1 write -> finalize ->
 // K2+K3 tile render.  No pixel is ever computed on the host: if CUDA is unavailable every entry point fails.
 #include "kernels.h"
+#include "dev_glyph.cuh"
 #include "dev_common.cuh"
 
 #include <cuda_runtime.h>
@@ -110,6 +111,10 @@ struct b2dgpu_runtime {
   int slot_next;
   cudaEvent_t prep_ready;
   DevBuffer oneshot_edges;
+  DevBuffer glyph_cache;                    // device mirror of the caller's glyph cache (b2dgpu_batch_view::glyph_cache)
+  uint32_t glyph_cache_words;               // words already uploaded
+  uint64_t glyph_cache_id;
+  cudaEvent_t glyph_cache_ready;            // recorded behind the last upload into the mirror
   DevBuffer bins;                           // per-band command lists (k_bin_*), rebuilt by every render
   uint32_t bin_capacity;                    // cells the lists can hold; grown when a render reports that it needed more
   uint32_t* h_bin_state;                    // pinned: [0] cells the last render needed, [1] whether its lists were built
@@ -137,9 +142,13 @@ struct b2dgpu_target {
 
 // Offsets of the sections inside a device block.
 struct BlockLayout {
-  size_t commands, fetch_data, vertices, segments, states, supplied_edges, blobs;
+  size_t commands, fetch_data, vertices, segments, states, supplied_edges, blobs, instances;
   size_t seg_counts, seg_offsets, scan_scratch, bbox_fixed, bbox_px, cmd_edges;
-  size_t upload_bytes;                      // sections [0, upload_bytes) are filled on the host and copied
+  // Host-filled data: [0, upload1_bytes) of the block - everything up to and including the uploaded vertices - and the
+  // uploaded segments; the vertices / segments the glyph instances generate follow their uploaded ones on the device
+  // only.  The pinned staging buffer holds part 1 at offset 0 and the segments at `staging_segments`.
+  size_t upload1_bytes, seg_upload_bytes, staging_segments;
+  size_t upload_bytes;                      // bytes copied host -> device per upload (statistics, staging size)
   size_t total_bytes;
 };
 
@@ -152,7 +161,8 @@ struct b2dgpu_batch {
   DevBuffer block;
   DevBuffer edges;
   BlockLayout lay;
-  uint32_t command_count, fetch_count, supplied_edges, vertex_count, segment_count, state_count;
+  uint32_t command_count, fetch_count, supplied_edges, vertex_count, segment_count, state_count;   // segment_count: uploaded + generated
+  uint32_t instance_count;
   int origin_x, origin_y;
   bool has_analytic;
   uint32_t built_edges;                     // known after the first render
@@ -301,6 +311,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
   rt->bin_capacity = 0; rt->h_bin_state = nullptr;
+  rt->glyph_cache_words = 0; rt->glyph_cache_id = 0; rt->glyph_cache_ready = nullptr;
   rt->profiling = false;
   rt->count_pixels = true;
   rt->sm_count = 148;
@@ -331,6 +342,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&rt->glyph_cache_ready, cudaEventDisableTiming);
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -380,6 +392,8 @@ extern "C" b2dgpu_result b2dgpu_runtime_destroy(b2dgpu_runtime* rt) {
   rt->oneshot_block[1].release();
   rt->oneshot_edges.release();
   rt->bins.release();
+  rt->glyph_cache.release();
+  if (rt->glyph_cache_ready) cudaEventDestroy(rt->glyph_cache_ready);
   if (rt->h_bin_state) cudaFreeHost(rt->h_bin_state);
   if (rt->own_stream) cudaStreamDestroy(rt->stream);
   rt->magic = 0;
@@ -612,6 +626,46 @@ static SolidFill detect_solid_fill(const b2dgpu_batch_view* v) {
 
 struct FetchUse { uint32_t fetch_type; uint32_t src_format; bool used; };
 
+// Callers built against the first layout of b2dgpu_batch_view pass a shorter struct: the missing tail reads as zero.
+static bool normalize_view(const b2dgpu_batch_view* v, b2dgpu_batch_view* out) {
+  if (!v || v->struct_size < B2DGPU_BATCH_VIEW_SIZE_V1) return false;
+  memset(out, 0, sizeof(*out));
+  memcpy(out, v, v->struct_size < sizeof(*out) ? v->struct_size : sizeof(*out));
+  out->struct_size = uint32_t(sizeof(*out));
+  return true;
+}
+
+static b2dgpu_result validate_glyph_instances(const b2dgpu_batch_view* v) {
+  if (!v->glyph_instance_count) {
+    if (v->generated_vertex_count || v->generated_segment_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: generated counts without glyph instances");
+    return B2DGPU_SUCCESS;
+  }
+  if (!v->glyph_instances || !v->glyph_cache || !v->glyph_cache_words) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph instances without a cache");
+  // Instances must tile the generated ranges in order, so that every generated vertex / segment is written exactly once.
+  uint64_t vtx = v->vertex_count, seg = v->segment_count;
+  for (uint32_t i = 0; i < v->glyph_instance_count; i++) {
+    const b2dgpu_glyph_instance& gi = v->glyph_instances[i];
+    if (uint64_t(gi.blob_offset) + 3u > v->glyph_cache_words) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph instance outside the cache");
+    const b2d::GlyphBlobView g = b2d::glyph_blob_view(v->glyph_cache + gi.blob_offset);
+    if (uint64_t(gi.blob_offset) + g.total_words() > v->glyph_cache_words) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: truncated glyph cache entry");
+    if (gi.vertex_base != vtx || gi.segment_base != seg) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph instances do not tile the generated ranges");
+    if (gi.command >= v->command_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph instance names no command");
+    const b2dgpu_command& c = v->commands[gi.command];
+    if (c.type != B2DGPU_CMD_FILL_GEOMETRY || seg < c.data_offset || seg + g.segments > uint64_t(c.data_offset) + c.data_count)
+      return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph instance outside the segment range of its command");
+    for (uint32_t k = 0; k < g.segments; k++) {
+      const uint32_t p0 = g.segment_words()[2 * k], p1 = g.segment_words()[2 * k + 1] >> 2, kind = g.segment_words()[2 * k + 1] & 3u;
+      const uint32_t extra = kind == B2DGPU_SEG_LINE ? 0u : kind == B2DGPU_SEG_QUAD ? 1u : 2u;
+      if (p0 >= g.vertices || uint64_t(p1) + extra >= g.vertices) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: glyph cache segment refers outside its glyph");
+    }
+    vtx += g.vertices; seg += g.segments;
+  }
+  if (vtx != uint64_t(v->vertex_count) + v->generated_vertex_count || seg != uint64_t(v->segment_count) + v->generated_segment_count)
+    return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: generated counts do not match the glyph instances");
+  if (vtx > 0x3FFFFFF0u || seg > 0xFFFFFFF0u) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: too many generated vertices");
+  return B2DGPU_SUCCESS;
+}
+
 static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
   if (!v || v->struct_size < sizeof(b2dgpu_batch_view)) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: bad struct_size");
   if (v->command_count && !v->commands) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: commands is null");
@@ -634,7 +688,7 @@ static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
     if (c.type == B2DGPU_CMD_FILL_ANALYTIC && (uint64_t(c.data_offset) + c.data_count > v->edge_count))
       return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: edge range out of bounds");
     if (c.type == B2DGPU_CMD_FILL_GEOMETRY) {
-      if (uint64_t(c.data_offset) + c.data_count > v->segment_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment range out of bounds");
+      if (uint64_t(c.data_offset) + c.data_count > uint64_t(v->segment_count) + v->generated_segment_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment range out of bounds");
       if (c.state_index >= v->geometry_state_count) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: state_index out of range");
     }
     if ((c.type == B2DGPU_CMD_FILL_BOX_A || c.type == B2DGPU_CMD_FILL_BOX_U) && !(c.box[0] < c.box[2] && c.box[1] < c.box[3]))
@@ -652,24 +706,28 @@ static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
     if (c.type != B2DGPU_CMD_FILL_GEOMETRY || i < c.data_offset || uint64_t(i) >= uint64_t(c.data_offset) + c.data_count)
       return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: segment does not belong to the geometry command it names");
   }
-  return B2DGPU_SUCCESS;
+  return validate_glyph_instances(v);
 }
 
 static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, BlockLayout& L) {
   size_t off = 0;
   auto add = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
+  const size_t total_segments = size_t(v->segment_count) + v->generated_segment_count;
   L.commands = add(sizeof(b2dgpu_command) * v->command_count);
   L.fetch_data = add(sizeof(b2dgpu_fetch_data) * v->fetch_count);
-  L.vertices = add(sizeof(double) * 2 * v->vertex_count);
-  L.segments = add(sizeof(b2dgpu_segment) * v->segment_count);
   L.states = add(sizeof(b2dgpu_geometry_state) * v->geometry_state_count);
   L.supplied_edges = add(sizeof(b2dgpu_edge) * v->edge_count);
   L.blobs = add(blob_bytes);
-  L.upload_bytes = align_up(off, 256);
-  off = L.upload_bytes;
-  L.seg_counts = add(sizeof(uint32_t) * (size_t(v->segment_count) + 1));
-  L.seg_offsets = add(sizeof(uint32_t) * (size_t(v->segment_count) + 1));
-  L.scan_scratch = add(sizeof(uint32_t) * scan_scratch_items(v->segment_count));
+  L.instances = add(sizeof(b2dgpu_glyph_instance) * v->glyph_instance_count);
+  L.vertices = add(sizeof(double) * 2 * (size_t(v->vertex_count) + v->generated_vertex_count));
+  L.upload1_bytes = L.vertices + sizeof(double) * 2 * v->vertex_count;
+  L.segments = add(sizeof(b2dgpu_segment) * total_segments);
+  L.seg_upload_bytes = sizeof(b2dgpu_segment) * v->segment_count;
+  L.staging_segments = align_up(L.upload1_bytes, 256);
+  L.upload_bytes = align_up(L.staging_segments + L.seg_upload_bytes, 256);
+  L.seg_counts = add(sizeof(uint32_t) * (total_segments + 1));
+  L.seg_offsets = add(sizeof(uint32_t) * (total_segments + 1));
+  L.scan_scratch = add(sizeof(uint32_t) * scan_scratch_items(uint32_t(total_segments)));
   L.bbox_fixed = add(sizeof(int4) * v->command_count);
   L.bbox_px = add(sizeof(int4) * v->command_count);
   L.cmd_edges = add(sizeof(uint2) * v->command_count);
@@ -680,7 +738,8 @@ static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, BlockLayo
 static b2dgpu_result serialize_batch(const b2dgpu_batch_view* v, std::vector<BlobRef>& blobs, const BlockLayout& L, uint8_t* host_block, const uint8_t* dev_base) {
   memcpy(host_block + L.commands, v->commands, sizeof(b2dgpu_command) * v->command_count);
   if (v->vertex_count) memcpy(host_block + L.vertices, v->vertices, sizeof(double) * 2 * v->vertex_count);
-  if (v->segment_count) memcpy(host_block + L.segments, v->segments, sizeof(b2dgpu_segment) * v->segment_count);
+  if (v->segment_count) memcpy(host_block + L.staging_segments, v->segments, sizeof(b2dgpu_segment) * v->segment_count);
+  if (v->glyph_instance_count) memcpy(host_block + L.instances, v->glyph_instances, sizeof(b2dgpu_glyph_instance) * v->glyph_instance_count);
   if (v->geometry_state_count) memcpy(host_block + L.states, v->geometry_states, sizeof(b2dgpu_geometry_state) * v->geometry_state_count);
   if (v->edge_count) memcpy(host_block + L.supplied_edges, v->edges, sizeof(b2dgpu_edge) * v->edge_count);
   for (const BlobRef& b : blobs) memcpy(host_block + L.blobs + b.offset, b.host, b.bytes);
@@ -786,6 +845,32 @@ static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb
   return B2DGPU_SUCCESS;
 }
 
+// Brings the device mirror of the caller's glyph cache up to date (append-only: only the new tail travels).
+static b2dgpu_result sync_glyph_cache(b2dgpu_runtime* rt, const b2dgpu_batch_view* v, cudaStream_t stream) {
+  if (!v->glyph_instance_count) return B2DGPU_SUCCESS;
+  if (v->glyph_cache_id != rt->glyph_cache_id || v->glyph_cache_words < rt->glyph_cache_words) {
+    rt->glyph_cache_id = v->glyph_cache_id;
+    rt->glyph_cache_words = 0;
+  }
+  const size_t need = size_t(v->glyph_cache_words) * 4;
+  if (need > rt->glyph_cache.cap) {
+    // the old mirror may still be read by kernels in flight on either stream
+    CU_TRY(cudaStreamSynchronize(rt->stream));
+    CU_TRY(cudaStreamSynchronize(rt->prep_stream));
+    CU_TRY(rt->glyph_cache.ensure(need * 2));
+    rt->glyph_cache_words = 0;
+  }
+  if (v->glyph_cache_words > rt->glyph_cache_words) {
+    const size_t from = size_t(rt->glyph_cache_words) * 4;
+    CU_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(rt->glyph_cache.ptr) + from, reinterpret_cast<const uint8_t*>(v->glyph_cache) + from,
+                           need - from, cudaMemcpyHostToDevice, stream));
+    CU_TRY(cudaEventRecord(rt->glyph_cache_ready, stream));
+    rt->stats.h2d_bytes += need - from;
+    rt->glyph_cache_words = v->glyph_cache_words;
+  }
+  return B2DGPU_SUCCESS;
+}
+
 // Fills the pinned block and copies it to `dev_block`.
 static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v, PreparedBatch& pb, uint8_t* dev_block, cudaStream_t stream) {
   PinnedBuffer& st = rt->staging[rt->staging_next];
@@ -804,11 +889,13 @@ static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v
     else fd[i].pattern.src.pixel_data = dev;
   }
 
-  CU_TRY(cudaMemcpyAsync(dev_block, host_block, pb.lay.upload_bytes, cudaMemcpyHostToDevice, stream));
+  CU_TRY(cudaMemcpyAsync(dev_block, host_block, pb.lay.upload1_bytes, cudaMemcpyHostToDevice, stream));
+  if (pb.lay.seg_upload_bytes)
+    CU_TRY(cudaMemcpyAsync(dev_block + pb.lay.segments, host_block + pb.lay.staging_segments, pb.lay.seg_upload_bytes, cudaMemcpyHostToDevice, stream));
   CU_TRY(cudaEventRecord(st.free_event, stream));
   st.in_flight = true;
-  rt->stats.h2d_bytes += pb.lay.upload_bytes;
-  return B2DGPU_SUCCESS;
+  rt->stats.h2d_bytes += pb.lay.upload1_bytes + pb.lay.seg_upload_bytes;
+  return sync_glyph_cache(rt, v, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -819,7 +906,8 @@ struct RenderInput {
   uint8_t* block;
   const BlockLayout* lay;
   DevBuffer* edges;
-  uint32_t command_count, supplied_edges, segment_count;
+  uint32_t command_count, supplied_edges, segment_count;      // segment_count: uploaded + generated
+  uint32_t instance_count;
   int origin_x, origin_y;
   bool has_analytic;
   bool built_known;
@@ -856,6 +944,18 @@ static b2dgpu_result prep_block(b2dgpu_runtime* rt, RenderInput& in, cudaStream_
   uint8_t* blk = in.block;
   BuildParams B = make_build_params(rt, in);
   launches += launch_init_bbox(B.cmd_bbox_fixed, in.command_count, s);
+  if (in.instance_count) {
+    // K0: the glyph instances write their vertices and segments behind the uploaded ones
+    GlyphParams G;
+    G.cache = static_cast<const uint32_t*>(rt->glyph_cache.ptr);
+    G.instances = reinterpret_cast<const b2dgpu_glyph_instance*>(blk + L.instances);
+    G.instance_count = in.instance_count;
+    G.vertices = reinterpret_cast<double*>(blk + L.vertices);
+    G.segments = reinterpret_cast<b2dgpu_segment*>(blk + L.segments);
+    G.error_flag = rt->d_scalars + 1;
+    CU_TRY(cudaStreamWaitEvent(s, rt->glyph_cache_ready, 0));
+    launches += launch_glyph_instances(G, s);
+  }
   if (in.segment_count) {
     launches += launch_count_edges(B, s);
     launches += launch_exclusive_scan(B.seg_counts, const_cast<uint32_t*>(B.seg_offsets), in.segment_count,
@@ -1070,9 +1170,13 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
 
 static b2dgpu_result submit_impl(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view);
 
-extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view) {
+extern "C" b2dgpu_result b2dgpu_submit(b2dgpu_runtime* rt, b2dgpu_target* target, const b2dgpu_batch_view* view_in) {
   if (!rt || rt->magic != kRuntimeMagic || !target || target->rt != rt) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: invalid argument");
-  if (!view || view->command_count == 0) return view ? B2DGPU_SUCCESS : fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: view is null");
+  if (!view_in) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_submit: view is null");
+  b2dgpu_batch_view full;
+  if (!normalize_view(view_in, &full)) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: bad struct_size");
+  const b2dgpu_batch_view* view = &full;
+  if (view->command_count == 0) return B2DGPU_SUCCESS;
   b2dgpu_result r = submit_impl(rt, target, view);
   if (r) return r;
   // Capture (b2dgpu_capture_begin): keep a device-resident copy of the batch so it can be replayed with its inputs in HBM.
@@ -1111,7 +1215,8 @@ static b2dgpu_result submit_impl(b2dgpu_runtime* rt, b2dgpu_target* target, cons
 
   RenderInput in;
   in.block = blk; in.lay = &pb.lay; in.edges = &rt->oneshot_edges;
-  in.command_count = view->command_count; in.supplied_edges = view->edge_count; in.segment_count = view->segment_count;
+  in.command_count = view->command_count; in.supplied_edges = view->edge_count;
+  in.segment_count = view->segment_count + view->generated_segment_count; in.instance_count = view->glyph_instance_count;
   in.origin_x = view->pixel_origin_x; in.origin_y = view->pixel_origin_y;
   in.has_analytic = pb.has_analytic;
   in.built_known = false; in.built_edges = 0; in.edges_staged = false; in.prepped = false;
@@ -1132,9 +1237,12 @@ static b2dgpu_result submit_impl(b2dgpu_runtime* rt, b2dgpu_target* target, cons
   return B2DGPU_SUCCESS;
 }
 
-extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_batch_view* view, b2dgpu_batch** out) {
-  if (!rt || rt->magic != kRuntimeMagic || !view || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_upload: invalid argument");
+extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_batch_view* view_in, b2dgpu_batch** out) {
+  if (!rt || rt->magic != kRuntimeMagic || !view_in || !out) return fail(B2DGPU_ERROR_INVALID_VALUE, "b2dgpu_batch_upload: invalid argument");
   *out = nullptr;
+  b2dgpu_batch_view full;
+  if (!normalize_view(view_in, &full)) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: bad struct_size");
+  const b2dgpu_batch_view* view = &full;
   std::lock_guard<std::mutex> lock(rt->mutex);
   cudaSetDevice(rt->device);
 
@@ -1147,7 +1255,8 @@ extern "C" b2dgpu_result b2dgpu_batch_upload(b2dgpu_runtime* rt, const b2dgpu_ba
   b->rt = rt;
   b->lay = pb.lay;
   b->command_count = view->command_count; b->fetch_count = view->fetch_count; b->supplied_edges = view->edge_count;
-  b->vertex_count = view->vertex_count; b->segment_count = view->segment_count; b->state_count = view->geometry_state_count;
+  b->vertex_count = view->vertex_count; b->segment_count = view->segment_count + view->generated_segment_count; b->state_count = view->geometry_state_count;
+  b->instance_count = view->glyph_instance_count;
   b->origin_x = view->pixel_origin_x; b->origin_y = view->pixel_origin_y;
   b->has_analytic = pb.has_analytic;
   b->built_known = false; b->built_edges = 0;
@@ -1184,6 +1293,7 @@ extern "C" b2dgpu_result b2dgpu_batch_render_multi(b2dgpu_runtime* rt, b2dgpu_ta
   RenderInput in;
   in.block = static_cast<uint8_t*>(b->block.ptr); in.lay = &b->lay; in.edges = &b->edges;
   in.command_count = b->command_count; in.supplied_edges = b->supplied_edges; in.segment_count = b->segment_count;
+  in.instance_count = b->instance_count;
   in.origin_x = b->origin_x; in.origin_y = b->origin_y;
   in.has_analytic = b->has_analytic;
   in.built_known = b->built_known; in.built_edges = b->built_edges; in.edges_staged = b->edges_staged; in.prepped = false;
@@ -1336,6 +1446,17 @@ extern "C" b2dgpu_result b2dgpu_debug_build_edges(b2dgpu_runtime* rt, const b2dg
   cudaError_t e = cudaSuccess;
   uint32_t built = 0;
   std::vector<uint32_t> offs(size_t(b->segment_count) + 1, 0);
+  if (b->instance_count) {
+    GlyphParams G;
+    G.cache = static_cast<const uint32_t*>(rt->glyph_cache.ptr);
+    G.instances = reinterpret_cast<const b2dgpu_glyph_instance*>(blk + L.instances);
+    G.instance_count = b->instance_count;
+    G.vertices = reinterpret_cast<double*>(blk + L.vertices);
+    G.segments = reinterpret_cast<b2dgpu_segment*>(blk + L.segments);
+    G.error_flag = rt->d_scalars + 1;
+    cudaStreamWaitEvent(s, rt->glyph_cache_ready, 0);
+    launch_glyph_instances(G, s);
+  }
   if (b->segment_count) {
     launch_init_bbox(B.cmd_bbox_fixed, b->command_count, s);
     launch_count_edges(B, s);

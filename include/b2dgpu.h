@@ -333,6 +333,19 @@ typedef struct b2dgpu_geometry_state {        /* 96 bytes */
   uint32_t reserved;
 } b2dgpu_geometry_state;
 
+/* Glyph instancing.  The caller keeps an append-only cache of TrueType outlines (format:
+ * blend2d_b200/csrc/dev_glyph.cuh; the runtime mirrors it on the device and uploads only what was appended since the last
+ * submit) and describes every glyph of a text fill by ONE of these records instead of its decoded outline.  The device
+ * replays the reference's decoder (opentype/otglyf.cpp:376-448) for the instance matrix and writes the vertices and path
+ * segments the glyph contributes at `vertex_base` / `segment_base` of the batch's arrays, behind the uploaded ones. */
+typedef struct b2dgpu_glyph_instance {
+  double m[6];                 /* glyph matrix: font matrix x placement x final (fixed-point) transform, core/font.cpp:659-744 */
+  uint32_t blob_offset;        /* word offset of the glyph inside the cache                                        */
+  uint32_t vertex_base;        /* >= vertex_count: first vertex index this instance writes                          */
+  uint32_t segment_base;       /* >= segment_count: first segment index this instance writes                        */
+  uint32_t command;            /* the FILL_GEOMETRY command the segments belong to                                  */
+} b2dgpu_glyph_instance;
+
 typedef struct b2dgpu_batch_view {
   uint32_t struct_size;
   uint32_t command_count;
@@ -343,7 +356,14 @@ typedef struct b2dgpu_batch_view {
   const b2dgpu_segment* segments;        uint32_t segment_count; uint32_t _pad3;
   const b2dgpu_geometry_state* geometry_states; uint32_t geometry_state_count; uint32_t _pad4;
   int32_t pixel_origin_x, pixel_origin_y;                                          /* ContextData::pixel_origin */
+  /* --- glyph instancing; absent (struct_size ends before it) or zero when unused --- */
+  const uint32_t* glyph_cache;           uint32_t glyph_cache_words; uint32_t _pad5;
+  uint64_t glyph_cache_id;               /* changes when the cache is not an extension of the previous submit's */
+  const b2dgpu_glyph_instance* glyph_instances; uint32_t glyph_instance_count; uint32_t _pad6;
+  uint32_t generated_vertex_count;       /* vertices / segments the instances write: commands may refer to segment */
+  uint32_t generated_segment_count;      /* indices up to segment_count + generated_segment_count                 */
 } b2dgpu_batch_view;
+#define B2DGPU_BATCH_VIEW_SIZE_V1 ((uint32_t)offsetof(b2dgpu_batch_view, glyph_cache))
 
 /* Copies/serialises the batch (the caller may free it on return, cf. rastercontext.cpp:1060-1063), uploads it and
  * launches the edge builder + tile compositor asynchronously on the runtime stream. */

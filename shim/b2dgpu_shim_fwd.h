@@ -11,13 +11,22 @@
 #ifndef B2DGPU_SHIM_FWD_H_INCLUDED
 #define B2DGPU_SHIM_FWD_H_INCLUDED
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
 
+#include <unordered_map>
+
 #include <b2dgpu.h>
+#include <dev_glyph.cuh>                         // glyph cache format + the decoder replay shared with the CUDA kernel
 #include <blend2d/raster/renderjobproc_p.h>      // JobProc::process_job (CPU edge building, B2DGPU_SHIM_CPU_EDGES=1)
+#include <blend2d/core/font_p.h>
+#include <blend2d/core/fontface_p.h>
+#include <blend2d/opentype/otface_p.h>
+#include <blend2d/opentype/otglyf_p.h>
+#include <blend2d/support/scopedbuffer_p.h>
 
 namespace bl::RasterEngine {
 namespace GpuShim {

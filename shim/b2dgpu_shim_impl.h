@@ -51,7 +51,17 @@ struct State {
 
   BLPath tmp_path[5];               // stroker scratch: a, b, c, input copy, glyph outlines
 
-  void clear_geometry() noexcept { vtx.clear(); segs.clear(); states.clear(); direct.clear(); }
+  // Glyph cache: TrueType outlines in the format of dev_glyph.cuh, append-only, mirrored on the device by
+  // the runtime; a text fill is described by one b2dgpu_glyph_instance per glyph instead of its decoded outline.
+  struct GlyphEntry { uint32_t blob_offset, vertices, segments; uint8_t kind; };   // kind: 0 cached, 1 no outline, 2 decode on the host
+  std::unordered_map<uint64_t, GlyphEntry> glyph_map;
+  std::vector<uint32_t> glyph_cache;
+  std::vector<b2dgpu_glyph_instance> instances;     // vertex_base / segment_base relative to the generated ranges until submit
+  uint32_t gen_vertices = 0, gen_segments = 0;
+  bool use_glyph_cache = true;
+  uint64_t glyphs_instanced = 0, glyph_runs_on_host = 0;    // B2DGPU_SHIM_STATS=1 prints them when the context goes away
+
+  void clear_geometry() noexcept { vtx.clear(); segs.clear(); states.clear(); direct.clear(); instances.clear(); gen_vertices = 0; gen_segments = 0; }
 };
 
 struct Runtime : public Pipeline::PipeRuntime {
@@ -89,6 +99,10 @@ static void BL_CDECL runtime_destroy(Pipeline::PipeRuntime* self) noexcept {
   Runtime* rt = static_cast<Runtime*>(self);
   State* st = rt->state;
   if (st) {
+    if (const char* e = getenv("B2DGPU_SHIM_STATS"))
+      if (e[0] == '1')
+        fprintf(stderr, "b2dgpu shim: %llu glyphs instanced from a cache of %zu glyphs (%zu KiB), %llu glyph runs decoded on the host\n",
+                (unsigned long long)st->glyphs_instanced, st->glyph_map.size(), st->glyph_cache.size() / 256, (unsigned long long)st->glyph_runs_on_host);
     if (st->rt) b2dgpu_sync(st->rt);
     if (st->registered_pixels) b2dgpu_host_unregister(st->rt, st->registered_pixels);
     if (st->target) b2dgpu_target_destroy(st->target);
@@ -138,6 +152,8 @@ static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::Pip
   st->cpu_edges = e && e[0] == '1';
   e = getenv("B2DGPU_SHIM_PIN");
   st->pin_images = !(e && e[0] == '0');
+  e = getenv("B2DGPU_SHIM_GLYPH_CACHE");
+  st->use_glyph_cache = !(e && e[0] == '0');
 
   rt->_runtime_type = Pipeline::PipeRuntimeType(kPipeRuntimeTypeGpu);
   rt->_runtime_flags = Pipeline::PipeRuntimeFlags::kIsolated;
@@ -384,9 +400,229 @@ static BLResult BL_CDECL stroke_glyph_run_segment_sink(BLPathCore* path, const v
   return result;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Glyph cache
+// ---------------------------------------------------------------------------------------------------------------
+struct GlyphPathPut {
+  const BLPoint* want;          // the reference decoder's vertices
+  size_t size;
+  bool ok;
+  void operator()(uint32_t index, double x, double y) noexcept {
+    if (index >= size || memcmp(&want[index].x, &x, 8) != 0 || memcmp(&want[index].y, &y, 8) != 0) ok = false;
+  }
+};
+
+// Builds the cache entry of one glyph: parses its `glyf` record (TrueType "Simple Glyph Description": flags with
+// repeats, byte / word coordinate deltas), takes the path STRUCTURE from the reference's own decoder and keeps the entry
+// only if replaying the deltas (b2d::glyph_emit) reproduces the reference's vertices bit for bit under the identity AND
+// under a general matrix.  Anything else - compound glyphs, empty contours, malformed data - is decoded on the host.
+static State::GlyphEntry build_glyph_entry(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id) noexcept {
+  State::GlyphEntry host = { 0, 0, 0, 2 };
+  const OpenType::OTFaceImpl* ot = static_cast<const OpenType::OTFaceImpl*>(face_impl);
+  if (glyph_id >= ot->face_info.glyph_count) return host;
+  const OpenType::RawTable glyf = ot->glyf.glyf_table, loca = ot->glyf.loca_table;
+  size_t offset, end_off;
+  if (ot->loca_offset_size() == 2) {
+    const size_t index = size_t(glyph_id) * 2u;
+    if (index + 4u > loca.size) return host;
+    offset = size_t(MemOps::readU16uBE(loca.data + index)) * 2u;
+    end_off = size_t(MemOps::readU16uBE(loca.data + index + 2)) * 2u;
+  }
+  else {
+    const size_t index = size_t(glyph_id) * 4u;
+    if (index + 8u > loca.size) return host;
+    offset = MemOps::readU32uBE(loca.data + index);
+    end_off = MemOps::readU32uBE(loca.data + index + 4);
+  }
+  if (offset == end_off && end_off <= glyf.size) return State::GlyphEntry{ 0, 0, 0, 1 };      // no outline (space)
+  if (offset >= end_off || end_off > glyf.size || end_off - offset < 12u) return host;
+
+  const uint8_t* p = glyf.data + offset;
+  const uint8_t* end = glyf.data + end_off;
+  const int contours = int(int16_t(MemOps::readU16uBE(p)));
+  if (contours <= 0 || contours > 4096) return host;                                            // compound (-1) or nothing
+  p += 10;
+  if (size_t(end - p) < size_t(contours) * 2u + 2u) return host;
+  std::vector<uint32_t> ends(size_t(contours), 0u);
+  for (int c = 0; c < contours; c++) ends[size_t(c)] = MemOps::readU16uBE(p + c * 2);
+  p += size_t(contours) * 2u;
+  const size_t instructions = MemOps::readU16uBE(p);
+  p += 2;
+  if (size_t(end - p) < instructions) return host;
+  p += instructions;
+  const size_t n = size_t(ends.back()) + 1u;
+  if (n < 2 || n > 0xFFFFu) return host;
+
+  std::vector<uint8_t> flags(n);
+  for (size_t i = 0; i < n; ) {
+    if (p == end) return host;
+    const uint8_t f = *p++;
+    flags[i++] = f;
+    if (f & 0x08u) {                                                                            // kRepeatFlag
+      if (p == end) return host;
+      size_t r = *p++;
+      if (r > n - i) return host;
+      while (r--) flags[i++] = f;
+    }
+  }
+  std::vector<int> dx(n, 0), dy(n, 0);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t f = flags[i];
+    if (f & 0x02u) { if (p == end) return host; int v = *p++; dx[i] = (f & 0x10u) ? v : -v; }
+    else if (!(f & 0x10u)) { if (end - p < 2) return host; dx[i] = int(int16_t(MemOps::readU16uBE(p))); p += 2; }
+  }
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t f = flags[i];
+    if (f & 0x04u) { if (p == end) return host; int v = *p++; dy[i] = (f & 0x20u) ? v : -v; }
+    else if (!(f & 0x20u)) { if (end - p < 2) return host; dy[i] = int(int16_t(MemOps::readU16uBE(p))); p += 2; }
+  }
+
+  // The path structure: what the reference's decoder (the variant this process dispatches to) emits.
+  BLPath path;
+  size_t contour_count = 0;
+  ScopedBufferTmp<BL_FONT_GET_GLYPH_OUTLINE_BUFFER_SIZE> tmp_buffer;
+  const BLMatrix2D identity(1.0, 0.0, 0.0, 1.0, 0.0, 0.0);
+  if (face_impl->funcs.get_glyph_outlines(face_impl, glyph_id, &identity, &path, &contour_count, &tmp_buffer) != BL_SUCCESS) return host;
+  const size_t nv = path.size();
+  if (!nv || nv > 0xFFFFu) return host;
+
+  // segments relative to the glyph, exactly as append_path() would record them for the decoded path
+  State scratch;
+  append_path(&scratch, path.view(), true);
+  const size_t ns = scratch.segs.size();
+
+  std::vector<uint32_t> blob;
+  blob.push_back(uint32_t(n) | (uint32_t(contours) << 16));
+  blob.push_back(uint32_t(nv));
+  blob.push_back(uint32_t(ns));
+  for (int c = 0; c < contours; c += 2)
+    blob.push_back(ends[size_t(c)] | (c + 1 < contours ? ends[size_t(c) + 1] << 16 : 0u));
+  for (size_t i = 0; i < n; i++) blob.push_back(uint32_t(uint16_t(int16_t(dx[i]))) | (uint32_t(uint16_t(int16_t(dy[i]))) << 16));
+  for (size_t i = 0; i < n; i += 32) {
+    uint32_t w = 0;
+    for (size_t k = 0; k < 32 && i + k < n; k++) w |= uint32_t(flags[i + k] & 1u) << k;
+    blob.push_back(w);
+  }
+  for (const b2dgpu_segment& sg : scratch.segs) { blob.push_back(sg.p0); blob.push_back(sg.p1_kind); }
+
+  // Trust, but verify: the replay must reproduce the reference bit for bit.
+  const b2d::GlyphBlobView view = b2d::glyph_blob_view(blob.data());
+  if (view.total_words() != blob.size()) return host;
+  {
+    const double m[6] = { 1.0, 0.0, 0.0, 1.0, 0.0, 0.0 };
+    GlyphPathPut put = { path.vertex_data(), nv, true };
+    if (b2d::glyph_emit(view, m, put) != nv || !put.ok) return host;
+  }
+  {
+    const BLMatrix2D general(0.37109375, -0.113, 0.2291, 0.90625, 5.53, -3.2517);
+    BLPath path2;
+    if (face_impl->funcs.get_glyph_outlines(face_impl, glyph_id, &general, &path2, &contour_count, &tmp_buffer) != BL_SUCCESS || path2.size() != nv) return host;
+    const double m[6] = { general.m00, general.m01, general.m10, general.m11, general.m20, general.m21 };
+    GlyphPathPut put = { path2.vertex_data(), nv, true };
+    if (b2d::glyph_emit(view, m, put) != nv || !put.ok) return host;
+  }
+
+  State::GlyphEntry e = { uint32_t(st->glyph_cache.size()), uint32_t(nv), uint32_t(ns), 0 };
+  st->glyph_cache.insert(st->glyph_cache.end(), blob.begin(), blob.end());
+  return e;
+}
+
+// A filled glyph run as glyph instances: the per-glyph matrices of bl_font_get_glyph_run_outlines (core/font.cpp:659-744)
+// - font matrix x user transform, translated by the glyph's placement / advance - without decoding an outline.  Returns
+// false (and records nothing) when some glyph of the run has to be decoded on the host; the caller then takes the
+// reference's path for the whole run, so that a command's segments stay contiguous.
+static bool instance_glyph_run(State* st, const BLFontCore* font, const BLGlyphRun* glyph_run, const BLMatrix2D& user_transform) noexcept {
+  BLFontPrivateImpl* font_impl = FontInternal::get_impl(font);
+  BLFontFacePrivateImpl* face_impl = FontFaceInternal::get_impl(&font_impl->face);
+  if (face_impl->face_info.outline_type != BL_FONT_OUTLINE_TYPE_TRUETYPE) return false;
+  if (!glyph_run->size) return true;
+
+  const size_t first_instance = st->instances.size();
+  const uint32_t gen_v0 = st->gen_vertices, gen_s0 = st->gen_segments;
+  bool ok = true;
+
+  auto emit = [&](BLGlyphId glyph_id, const BLMatrix2D& m) noexcept {
+    const uint64_t key = (uint64_t(face_impl->unique_id) << 32) | glyph_id;
+    auto it = st->glyph_map.find(key);
+    if (it == st->glyph_map.end()) it = st->glyph_map.emplace(key, build_glyph_entry(st, face_impl, glyph_id)).first;
+    const State::GlyphEntry& e = it->second;
+    if (e.kind == 1) return;
+    if (e.kind != 0) { ok = false; return; }
+    b2dgpu_glyph_instance gi;
+    gi.m[0] = m.m00; gi.m[1] = m.m01; gi.m[2] = m.m10; gi.m[3] = m.m11; gi.m[4] = m.m20; gi.m[5] = m.m21;
+    gi.blob_offset = e.blob_offset;
+    gi.vertex_base = st->gen_vertices;
+    gi.segment_base = st->gen_segments;
+    gi.command = 0;                                // patched in consume_batch()
+    st->instances.push_back(gi);
+    st->gen_vertices += e.vertices;
+    st->gen_segments += e.segments;
+  };
+
+  BLMatrix2D final_transform;
+  const BLFontMatrix& fMat = font_impl->matrix;
+  bl_font_matrix_multiply(&final_transform, &fMat, &user_transform);
+
+  const uint32_t placement_type = glyph_run->placement_type;
+  BLGlyphRunIterator it(*glyph_run);
+  if (it.has_placement() && placement_type != BL_GLYPH_PLACEMENT_TYPE_NONE) {
+    BLMatrix2D offset_transform(1.0, 0.0, 0.0, 1.0, final_transform.m20, final_transform.m21);
+    switch (placement_type) {
+      case BL_GLYPH_PLACEMENT_TYPE_ADVANCE_OFFSET:
+      case BL_GLYPH_PLACEMENT_TYPE_DESIGN_UNITS:
+        offset_transform.m00 = final_transform.m00; offset_transform.m01 = final_transform.m01;
+        offset_transform.m10 = final_transform.m10; offset_transform.m11 = final_transform.m11;
+        break;
+      case BL_GLYPH_PLACEMENT_TYPE_USER_UNITS:
+        offset_transform.m00 = user_transform.m00; offset_transform.m01 = user_transform.m01;
+        offset_transform.m10 = user_transform.m10; offset_transform.m11 = user_transform.m11;
+        break;
+    }
+    if (placement_type == BL_GLYPH_PLACEMENT_TYPE_ADVANCE_OFFSET) {
+      double ox = final_transform.m20, oy = final_transform.m21;
+      while (!it.at_end() && ok) {
+        const BLGlyphPlacement& pos = it.placement<BLGlyphPlacement>();
+        double px = pos.placement.x, py = pos.placement.y;
+        final_transform.m20 = px * offset_transform.m00 + py * offset_transform.m10 + ox;
+        final_transform.m21 = px * offset_transform.m01 + py * offset_transform.m11 + oy;
+        emit(it.glyph_id(), final_transform);
+        it.advance();
+        px = pos.advance.x; py = pos.advance.y;
+        ox += px * offset_transform.m00 + py * offset_transform.m10;
+        oy += px * offset_transform.m01 + py * offset_transform.m11;
+      }
+    }
+    else {
+      while (!it.at_end() && ok) {
+        const BLPoint& placement = it.placement<BLPoint>();
+        final_transform.m20 = placement.x * offset_transform.m00 + placement.y * offset_transform.m10 + offset_transform.m20;
+        final_transform.m21 = placement.x * offset_transform.m01 + placement.y * offset_transform.m11 + offset_transform.m21;
+        emit(it.glyph_id(), final_transform);
+        it.advance();
+      }
+    }
+  }
+  else {
+    while (!it.at_end() && ok) {
+      emit(it.glyph_id(), final_transform);
+      it.advance();
+    }
+  }
+
+  if (!ok) {
+    st->instances.resize(first_instance);
+    st->gen_vertices = gen_v0; st->gen_segments = gen_s0;
+    st->glyph_runs_on_host++;
+  }
+  else st->glyphs_instanced += st->instances.size() - first_instance;
+  return ok;
+}
+
 struct JobGeometry {
   bool valid;
+  bool generated;               // the segments come from glyph instances: seg_begin is relative to the generated range
   uint32_t seg_begin, seg_count, state_index;
+  uint32_t inst_begin, inst_count;
 };
 
 static BL_INLINE const BLGlyphRun* job_glyph_run(WorkData* work_data, RenderJob_TextOp* job, BLResult& result) noexcept {
@@ -406,7 +642,7 @@ static BL_INLINE const BLGlyphRun* job_glyph_run(WorkData* work_data, RenderJob_
 }
 
 static JobGeometry process_job(State* st, WorkData* work_data, RenderJob* base_job) noexcept {
-  JobGeometry out = { false, uint32_t(st->segs.size()), 0, 0 };
+  JobGeometry out = { false, false, uint32_t(st->segs.size()), 0, 0, 0, 0 };
   const size_t vtx_begin = st->vtx.size();
   BLResult result = BL_SUCCESS;
   BLMatrix2D state_transform;
@@ -466,12 +702,27 @@ static JobGeometry process_job(State* st, WorkData* work_data, RenderJob* base_j
       const BLGlyphRun* glyph_run = job_glyph_run(work_data, job, result);
       if (result == BL_SUCCESS) {
         BLMatrix2D transform(accessor.final_transform_fixed(job->origin_fixed()));
+        state_transform.reset();
+        state_transform_type = BL_TRANSFORM_TYPE_IDENTITY;
+        const size_t inst_begin = st->instances.size();
+        const uint32_t gen_begin = st->gen_segments;
+        if (st->use_glyph_cache && instance_glyph_run(st, &job->_font, glyph_run, transform)) {
+          // every glyph of the run is in the device cache: no outline is decoded here
+          job->destroy();
+          out.generated = true;
+          out.seg_begin = gen_begin;
+          out.seg_count = st->gen_segments - gen_begin;
+          out.inst_begin = uint32_t(inst_begin);
+          out.inst_count = uint32_t(st->instances.size() - inst_begin);
+          if (!out.seg_count) return out;
+          out.state_index = add_state(st, state_transform, state_transform_type, fill_state->final_clip_box_fixed_d, fill_state->toleranceFixedD);
+          out.valid = true;
+          return out;
+        }
         BLPath* path = &st->tmp_path[4];
         path->clear();
         SegmentSink sink = { st, st->tmp_path, nullptr, nullptr };
         result = bl_font_get_glyph_run_outlines(&job->_font, glyph_run, &transform, path, fill_glyph_run_segment_sink, &sink);
-        state_transform.reset();
-        state_transform_type = BL_TRANSFORM_TYPE_IDENTITY;
       }
       job->destroy();
       break;
@@ -580,7 +831,7 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
 
   // ---- pass 1: jobs ----
   struct PendingJob { RenderJob* job; uint32_t command; };
-  std::vector<JobGeometry> job_geometry(command_count, JobGeometry{ false, 0, 0, 0 });
+  std::vector<JobGeometry> job_geometry(command_count, JobGeometry{ false, false, 0, 0, 0, 0, 0 });
   {
     uint32_t base = 0;
     for (const RenderCommandQueue* q = batch->command_list().first(); q; q = q->next()) {
@@ -655,6 +906,12 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
             const JobGeometry& g = job_geometry[ci];
             c.type = B2DGPU_CMD_FILL_GEOMETRY;
             c.data_offset = g.seg_begin; c.data_count = g.seg_count; c.state_index = g.state_index;
+            if (g.generated) {
+              // glyph instances: their segments live behind the uploaded ones (all jobs have run: the count is final)
+              c.data_offset += uint32_t(st->segs.size());
+              for (uint32_t k = 0; k < g.inst_count; k++) st->instances[g.inst_begin + k].command = out_count;
+              break;
+            }
           }
           else continue;                                            // everything clipped out / failed job
           if (c.type == B2DGPU_CMD_FILL_GEOMETRY)
@@ -706,6 +963,15 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
     v.vertices = st->vtx.data();            v.vertex_count = uint32_t(st->vtx.size() / 2);
     v.segments = st->segs.data();           v.segment_count = uint32_t(st->segs.size());
     v.geometry_states = st->states.data();  v.geometry_state_count = uint32_t(st->states.size());
+    if (!st->instances.empty()) {
+      // the generated ranges start where the uploaded arrays end
+      const uint32_t v0 = v.vertex_count, s0 = v.segment_count;
+      for (b2dgpu_glyph_instance& gi : st->instances) { gi.vertex_base += v0; gi.segment_base += s0; }
+      v.glyph_cache = st->glyph_cache.data(); v.glyph_cache_words = uint32_t(st->glyph_cache.size());
+      v.glyph_cache_id = uint64_t(uintptr_t(st));
+      v.glyph_instances = st->instances.data(); v.glyph_instance_count = uint32_t(st->instances.size());
+      v.generated_vertex_count = st->gen_vertices; v.generated_segment_count = st->gen_segments;
+    }
     v.pixel_origin_x = work_data->ctx_data.pixel_origin.x;
     v.pixel_origin_y = work_data->ctx_data.pixel_origin.y;
     // Copies everything it needs before returning (rastercontext.cpp:1060-1063 frees the batch right after).

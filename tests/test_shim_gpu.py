@@ -185,3 +185,19 @@ def test_extended_operators_through_blend2d(B, op):
         mask = (mi.to_numpy() & 0xFF).astype(np.uint8)
         want = O.composite_prgb32(op, want, premultiply_rgba32(color), mask)
     assert np.array_equal(got, want)
+
+
+def test_glyph_cache_equals_host_decoding(B, monkeypatch, capfd):
+    """filled text goes to the device as glyph instances (cached TrueType deltas + one matrix per glyph,
+    decoded by k_glyph_instances); B2DGPU_SHIM_GLYPH_CACHE=0 takes the reference's decoder on the host instead.  Both
+    must equal the CPU context, and the cache must really be in use."""
+    scene = S.text_runs(200, 640, 360, size=27.0, chars=6, style="radial")
+    monkeypatch.setenv("B2DGPU_SHIM_STATS", "1")
+    cpu, gpu = both(B, scene, 640, 360)
+    err = capfd.readouterr().err
+    assert_same(cpu, gpu)
+    assert "glyphs instanced" in err and " 0 glyphs instanced" not in err, err
+    monkeypatch.setenv("B2DGPU_SHIM_GLYPH_CACHE", "0")
+    cpu2, gpu2 = both(B, scene, 640, 360)
+    assert_same(cpu2, gpu2)
+    assert np.array_equal(gpu, gpu2)
