@@ -71,7 +71,9 @@ class BatchView(C.Structure):
                 ("glyph_cache", C.c_void_p), ("glyph_cache_words", C.c_uint32), ("_pad5", C.c_uint32),
                 ("glyph_cache_id", C.c_uint64),
                 ("glyph_instances", C.c_void_p), ("glyph_instance_count", C.c_uint32), ("_pad6", C.c_uint32),
-                ("generated_vertex_count", C.c_uint32), ("generated_segment_count", C.c_uint32)]
+                ("generated_vertex_count", C.c_uint32), ("generated_segment_count", C.c_uint32),
+                ("lut_requests", C.c_void_p), ("lut_request_count", C.c_uint32), ("_pad7", C.c_uint32),
+                ("lut_stops", C.c_void_p), ("lut_stop_count", C.c_uint32), ("_pad8", C.c_uint32)]
 
 
 class Stats(C.Structure):

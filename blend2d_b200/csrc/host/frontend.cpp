@@ -829,6 +829,7 @@ struct Style {
   uint32_t fetch_type;          // non-solid
   int32_t fetch_index;          // index in the current batch (-1 = not yet materialised in this batch)
   b2dgpu_fetch_data fd;
+  const struct b2d_gradient* device_lut;   // non-null: fd.gradient.lut.data is NULL, the runtime interpolates the table from these stops
 };
 
 } // namespace
@@ -869,6 +870,9 @@ struct b2d_context {
   std::vector<double> vtx;
   std::vector<b2dgpu_segment> segs;
   std::vector<b2dgpu_geometry_state> states;
+  std::vector<b2dgpu_lut_request> lut_requests;      // gradient tables the device builds (b2dgpu_lut_request)
+  std::vector<b2dgpu_gradient_stop> lut_stops;
+  bool device_luts;                                   // GPU contexts: gradient tables are interpolated on the device
   bool state_valid;             // states.back() matches the current transform
   // Style objects whose memory (LUTs, pixels) the queued FetchData still points to - released after the flush,
   // like RenderFetchData's reference to its style (renderfetchdata_p.h:43, 181-184).
@@ -921,7 +925,7 @@ b2dgpu_result flush_batch(b2d_context* c) {
   memset(&v, 0, sizeof(v));
   b2d_context_peek_batch(c, &v);
   b2dgpu_result r = b2dgpu_submit(c->rt, c->target, &v);
-  c->cmds.clear(); c->fetch.clear(); c->vtx.clear(); c->segs.clear(); c->states.clear();
+  c->cmds.clear(); c->fetch.clear(); c->vtx.clear(); c->segs.clear(); c->states.clear(); c->lut_requests.clear(); c->lut_stops.clear();
   c->state_valid = false;
   c->style.fetch_index = -1;
   c->dirty = true;
@@ -962,7 +966,16 @@ Resolved resolve(b2d_context* c, bool is_clear) {
   else {
     r.solid = false;
     r.sig |= st.fetch_type << 16;
-    if (st.fetch_index < 0) { st.fetch_index = int32_t(c->fetch.size()); c->fetch.push_back(st.fd); }
+    if (st.fetch_index < 0) {
+      st.fetch_index = int32_t(c->fetch.size()); c->fetch.push_back(st.fd);
+      if (st.device_lut) {
+        b2dgpu_lut_request q;
+        q.fetch_index = uint32_t(st.fetch_index); q.stop_offset = uint32_t(c->lut_stops.size());
+        q.stop_count = uint32_t(st.device_lut->stops.size()); q.lut_size = st.fd.gradient.lut.size;
+        for (const Stop& sp : st.device_lut->stops) c->lut_stops.push_back(b2dgpu_gradient_stop{ sp.offset, sp.rgba });
+        c->lut_requests.push_back(q);
+      }
+    }
     r.fetch_index = st.fetch_index;
   }
   return r;
@@ -1088,7 +1101,7 @@ b2dgpu_result fill_box_d(b2d_context* c, const Resolved& r, double bx0, double b
 b2dgpu_result set_non_solid_style(b2d_context* c, uint32_t fetch_type, uint32_t format, const b2dgpu_fetch_data& fd) {
   Style& st = c->style;
   if (fetch_type == kPending) { st.kind = 2; return B2DGPU_SUCCESS; }
-  st.kind = 1; st.format = format; st.fetch_type = fetch_type; st.fetch_index = -1; st.fd = fd;
+  st.kind = 1; st.format = format; st.fetch_type = fetch_type; st.fetch_index = -1; st.fd = fd; st.device_lut = nullptr;
   return B2DGPU_SUCCESS;
 }
 
@@ -1104,6 +1117,9 @@ extern "C" b2dgpu_result b2d_context_create(b2d_image* target, const b2d_context
   c->own_rt = false;
   c->target = nullptr;
   c->record_only = info && (info->flags & B2D_CONTEXT_CREATE_FLAG_RECORD_ONLY);
+  // A recorded batch may be rendered by the test-only host simulator, which needs real tables; a GPU context lets the
+  // device interpolate them (B2D_HOST_DEVICE_LUTS=0 keeps the host tables, for A/B tests).
+  { const char* e = getenv("B2D_HOST_DEVICE_LUTS"); c->device_luts = !c->record_only && !(e && e[0] == '0'); }
   b2dgpu_result r = B2DGPU_SUCCESS;
   if (c->record_only) c->rt = nullptr;
   else if (!c->rt) {
@@ -1200,12 +1216,14 @@ extern "C" b2dgpu_result b2d_context_peek_batch(b2d_context* c, b2dgpu_batch_vie
   v->segments = c->segs.data(); v->segment_count = uint32_t(c->segs.size());
   v->geometry_states = c->states.data(); v->geometry_state_count = uint32_t(c->states.size());
   v->pixel_origin_x = c->origin_x; v->pixel_origin_y = c->origin_y;
+  v->lut_requests = c->lut_requests.data(); v->lut_request_count = uint32_t(c->lut_requests.size());
+  v->lut_stops = c->lut_stops.data(); v->lut_stop_count = uint32_t(c->lut_stops.size());
   return B2DGPU_SUCCESS;
 }
 
 extern "C" b2dgpu_result b2d_context_discard_batch(b2d_context* c) {
   if (!c) return B2DGPU_ERROR_INVALID_VALUE;
-  c->cmds.clear(); c->fetch.clear(); c->vtx.clear(); c->segs.clear(); c->states.clear();
+  c->cmds.clear(); c->fetch.clear(); c->vtx.clear(); c->segs.clear(); c->states.clear(); c->lut_requests.clear(); c->lut_stops.clear();
   c->state_valid = false; c->style.fetch_index = -1;
   release_kept(c, true);
   return B2DGPU_SUCCESS;
@@ -1286,6 +1304,9 @@ extern "C" b2dgpu_result b2d_context_set_fill_style_gradient(b2d_context* c, con
     if (!g->lut64) { g->lut64.reset(new uint64_t[lut_size]); make_lut64(g->lut64.get(), lut_size, g->stops.data(), g->stops.size()); }
     fd.gradient.lut.data = g->lut64.get();
   }
+  else if (c->device_luts && !g->lut32) {
+    fd.gradient.lut.data = nullptr;               // k_build_luts interpolates it from the stops (b2dgpu_lut_request)
+  }
   else {
     if (!g->lut32) { g->lut32.reset(new uint32_t[lut_size]); make_lut32(g->lut32.get(), lut_size, g->stops.data(), g->stops.size()); }
     fd.gradient.lut.data = g->lut32.get();
@@ -1298,7 +1319,9 @@ extern "C" b2dgpu_result b2d_context_set_fill_style_gradient(b2d_context* c, con
   else ft = init_conic_gradient(fd.gradient, g->values, quality, m);
   g->refs++;
   c->kept_gradients.push_back(g);
-  return set_non_solid_style(c, ft, g->format, fd);
+  b2dgpu_result sr = set_non_solid_style(c, ft, g->format, fd);
+  if (sr == B2DGPU_SUCCESS && c->style.kind == 1 && !dither && !fd.gradient.lut.data) c->style.device_lut = g;
+  return sr;
 }
 
 extern "C" b2dgpu_result b2d_context_set_fill_style_pattern(b2d_context* c, const b2d_pattern* p) {

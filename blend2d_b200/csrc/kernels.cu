@@ -61,6 +61,77 @@ __global__ void __launch_bounds__(128) k_glyph_instances(GlyphParams P) {
 }
 
 // =================================================================================================================
+// K0b - gradient table interpolation
+//
+// interpolate_prgb32 as the reference executes it on AVX2 hosts (pixelops/interpolation_avx2.cpp:18-205; called by
+// GradientInternal::ensure_lut32, core/gradient.cpp:289-330): the stops are walked in order, a span of i + 1 table
+// entries between two stops is a linear ramp of 8-bit channels in 9.23 fixed point with the per-channel step
+// trunc((c1 - c0) * (2^23 / i)) computed in double, each entry is premultiplied afterwards, and a later span overwrites
+// the entry it shares with the previous one.  The ramp is a closed form in the entry index (u32 wrap-around adds), so
+// the lanes of a warp take the entries of a span in parallel; the spans stay sequential.
+// =================================================================================================================
+__device__ __forceinline__ uint32_t lut_premul_top8(uint64_t c) {
+  const uint32_t a = uint32_t(c >> 56), r = uint32_t((c >> 40) & 0xFFu), g = uint32_t((c >> 24) & 0xFFu), b = uint32_t((c >> 8) & 0xFFu);
+  return (a << 24) | (udiv255(r * a) << 16) | (udiv255(g * a) << 8) | udiv255(b * a);
+}
+
+__global__ void __launch_bounds__(128) k_build_luts(LutParams P) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (w >= P.request_count) return;
+  const b2dgpu_lut_request rq = P.requests[w];
+  const b2dgpu_gradient_stop* stops = P.stops + rq.stop_offset;
+  uint32_t* d = P.tables + P.table_offsets[w];
+  const uint32_t size = rq.lut_size, n = rq.stop_count;
+
+  uint64_t c0 = stops[0].rgba64, c1 = c0;
+  uint32_t u0 = 0;
+  uint32_t si = (stops[0].offset == 0.0 && n > 1) ? 1u : 0u;
+  const uint32_t d_size = size - 1u;
+  const double f_width = double(int32_t(d_size << 8));
+  uint32_t pos = 0;                                       // `dp - d` of the reference after the last span
+
+  do {
+    c1 = stops[si].rgba64;
+    const uint32_t u1 = uint32_t(__double2int_rn(stops[si].offset * f_width));
+    pos = u0 >> 8;
+    const uint32_t i = (u1 >> 8) - (u0 >> 8);
+    u0 = u1;
+    if (i <= 1u) {
+      if (lane == 0) {
+        d[pos] = lut_premul_top8(c0);
+        if (i == 1u) d[pos + 1u] = lut_premul_top8(c1);
+      }
+      pos += i == 0u ? 1u : 2u;
+    }
+    else {
+      const uint32_t cnt = i + 1u;
+      const double scale = double(1 << 23) / double(int(i));
+      uint32_t cx[4]; uint32_t dx[4];
+      #pragma unroll
+      for (int ch = 0; ch < 4; ch++) {
+        const int sh = 8 + ch * 16;                       // top byte of each 16-bit channel: b, g, r, a
+        const int32_t a0 = int32_t((c0 >> sh) & 0xFFu), a1 = int32_t((c1 >> sh) & 0xFFu);
+        dx[ch] = uint32_t(__double2int_rz(double(a1 - a0) * scale));          // cvttpd2dq
+        cx[ch] = (uint32_t(a0) << 23) + (1u << 22);
+      }
+      for (uint32_t k = lane; k < cnt; k += 32) {
+        const uint32_t b = (cx[0] + k * dx[0]) >> 23, g = (cx[1] + k * dx[1]) >> 23, r = (cx[2] + k * dx[2]) >> 23, a = (cx[3] + k * dx[3]) >> 23;
+        d[pos + k] = (a << 24) | (udiv255(r * a) << 16) | (udiv255(g * a) << 8) | udiv255(b * a);
+      }
+      pos += cnt;
+    }
+    c0 = c1;
+    __syncwarp();                                         // the next span may overwrite this span's last entry
+  } while (++si < n);
+
+  const uint32_t last = lut_premul_top8(c0);
+  for (uint32_t k = pos + lane; k < size; k += 32) d[k] = last;
+  __syncwarp();
+  if (lane == 0) d[0] = lut_premul_top8(stops[0].rgba64);
+}
+
+// =================================================================================================================
 // K1 - edge builder
 // =================================================================================================================
 
@@ -1306,6 +1377,12 @@ __global__ void __launch_bounds__(256) k_stream_solid(SolidStreamParams P, int c
 // Launchers (host)
 // =================================================================================================================
 static inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+int launch_build_luts(const LutParams& P, cudaStream_t s) {
+  if (!P.request_count) return 0;
+  k_build_luts<<<div_up(P.request_count * 32, 128), 128, 0, s>>>(P);
+  return 1;
+}
 
 int launch_glyph_instances(const GlyphParams& P, cudaStream_t s) {
   if (!P.instance_count) return 0;

@@ -69,6 +69,16 @@ struct GlyphParams {
 };
 int launch_glyph_instances(const GlyphParams& P, cudaStream_t s);
 
+// Gradient tables built on the device: one warp per request.
+struct LutParams {
+  const b2dgpu_lut_request* requests;
+  uint32_t request_count;
+  const b2dgpu_gradient_stop* stops;
+  const uint32_t* table_offsets;          // per request: word offset of its table inside `tables`
+  uint32_t* tables;
+};
+int launch_build_luts(const LutParams& P, cudaStream_t s);
+
 // Binning (K1d): per-band ordered command lists with x-extents, the GPU form of the reference's per-band edge lists
 // (raster/edgestorage_p.h:38-178) and of its band-by-band command walk (raster/workerproc.cpp:166-255).
 struct BinParams {

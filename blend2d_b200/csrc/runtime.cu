@@ -143,6 +143,8 @@ struct b2dgpu_target {
 // Offsets of the sections inside a device block.
 struct BlockLayout {
   size_t commands, fetch_data, vertices, segments, states, supplied_edges, blobs, instances;
+  size_t lut_requests, lut_stops, lut_offsets;      // uploaded: the requests, their stops, word offset of every table
+  size_t gen_luts;                                  // device only: the tables k_build_luts writes
   size_t seg_counts, seg_offsets, scan_scratch, bbox_fixed, bbox_px, cmd_edges;
   // Host-filled data: [0, upload1_bytes) of the block - everything up to and including the uploaded vertices - and the
   // uploaded segments; the vertices / segments the glyph instances generate follow their uploaded ones on the device
@@ -709,7 +711,7 @@ static b2dgpu_result validate_batch(const b2dgpu_batch_view* v) {
   return validate_glyph_instances(v);
 }
 
-static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, BlockLayout& L) {
+static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, size_t gen_lut_bytes, BlockLayout& L) {
   size_t off = 0;
   auto add = [&](size_t bytes) { off = align_up(off, 256); size_t o = off; off += bytes; return o; };
   const size_t total_segments = size_t(v->segment_count) + v->generated_segment_count;
@@ -719,12 +721,16 @@ static void plan_layout(const b2dgpu_batch_view* v, size_t blob_bytes, BlockLayo
   L.supplied_edges = add(sizeof(b2dgpu_edge) * v->edge_count);
   L.blobs = add(blob_bytes);
   L.instances = add(sizeof(b2dgpu_glyph_instance) * v->glyph_instance_count);
+  L.lut_requests = add(sizeof(b2dgpu_lut_request) * v->lut_request_count);
+  L.lut_stops = add(sizeof(b2dgpu_gradient_stop) * v->lut_stop_count);
+  L.lut_offsets = add(sizeof(uint32_t) * v->lut_request_count);
   L.vertices = add(sizeof(double) * 2 * (size_t(v->vertex_count) + v->generated_vertex_count));
   L.upload1_bytes = L.vertices + sizeof(double) * 2 * v->vertex_count;
   L.segments = add(sizeof(b2dgpu_segment) * total_segments);
   L.seg_upload_bytes = sizeof(b2dgpu_segment) * v->segment_count;
   L.staging_segments = align_up(L.upload1_bytes, 256);
   L.upload_bytes = align_up(L.staging_segments + L.seg_upload_bytes, 256);
+  L.gen_luts = add(gen_lut_bytes);
   L.seg_counts = add(sizeof(uint32_t) * (total_segments + 1));
   L.seg_offsets = add(sizeof(uint32_t) * (total_segments + 1));
   L.scan_scratch = add(sizeof(uint32_t) * scan_scratch_items(uint32_t(total_segments)));
@@ -751,7 +757,7 @@ static b2dgpu_result serialize_batch(const b2dgpu_batch_view* v, std::vector<Blo
 
 // Collects the host memory referenced by fetch data (gradient LUTs, pattern pixels), de-duplicated by address.
 static b2dgpu_result collect_blobs(const b2dgpu_batch_view* v, std::vector<FetchUse>& uses, std::vector<BlobRef>& blobs,
-                                   std::vector<size_t>& fetch_blob, size_t& blob_bytes) {
+                                   std::vector<size_t>& fetch_blob, size_t& blob_bytes, const std::vector<int32_t>& fetch_lut_request) {
   uses.assign(v->fetch_count, FetchUse{0, 0, false});
   for (uint32_t i = 0; i < v->command_count; i++) {
     const b2dgpu_command& c = v->commands[i];
@@ -789,6 +795,7 @@ static b2dgpu_result collect_blobs(const b2dgpu_batch_view* v, std::vector<Fetch
                     uses[i].fetch_type == B2DGPU_FETCH_GRADIENT_CONIC_DITHER;
       host = fd.gradient.lut.data;
       bytes = size_t(fd.gradient.lut.size) * (dither ? 8 : 4);
+      if (!host && bytes && !dither && fetch_lut_request[i] >= 0) continue;      // built on the device (k_build_luts)
       if (!host || !bytes) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: gradient without a LUT");
     }
     else {
@@ -810,6 +817,9 @@ static b2dgpu_result collect_blobs(const b2dgpu_batch_view* v, std::vector<Fetch
 
 struct PreparedBatch {
   BlockLayout lay;
+  std::vector<uint32_t> lut_table_offsets;          // per request, in words, inside the gen_luts section
+  size_t gen_lut_bytes;
+  std::vector<int32_t> fetch_lut_request;           // per fetch_data entry: its request or -1
   std::vector<BlobRef> blobs;
   std::vector<FetchUse> uses;
   std::vector<size_t> fetch_blob;
@@ -822,10 +832,32 @@ struct PreparedBatch {
 static b2dgpu_result prepare_batch(const b2dgpu_batch_view* v, PreparedBatch& pb) {
   b2dgpu_result r = validate_batch(v);
   if (r) return r;
+  // device-built gradient tables
+  pb.fetch_lut_request.assign(v->fetch_count, -1);
+  pb.lut_table_offsets.assign(v->lut_request_count, 0u);
+  pb.gen_lut_bytes = 0;
+  if (v->lut_request_count) {
+    if (!v->lut_requests || !v->lut_stops) return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: table requests without stops");
+    for (uint32_t i = 0; i < v->lut_request_count; i++) {
+      const b2dgpu_lut_request& q = v->lut_requests[i];
+      if (q.fetch_index >= v->fetch_count || !q.stop_count || uint64_t(q.stop_offset) + q.stop_count > v->lut_stop_count ||
+          q.lut_size < 2u || q.lut_size > 65536u || q.lut_size != v->fetch_data[q.fetch_index].gradient.lut.size ||
+          v->fetch_data[q.fetch_index].gradient.lut.data != nullptr || pb.fetch_lut_request[q.fetch_index] >= 0)
+        return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: invalid gradient table request");
+      for (uint32_t k = 0; k < q.stop_count; k++) {
+        const double o = v->lut_stops[q.stop_offset + k].offset;
+        if (!(o >= 0.0 && o <= 1.0) || (k && o < v->lut_stops[q.stop_offset + k - 1].offset))
+          return fail(B2DGPU_ERROR_INVALID_VALUE, "batch view: gradient stops out of order");
+      }
+      pb.fetch_lut_request[q.fetch_index] = int32_t(i);
+      pb.lut_table_offsets[i] = uint32_t(pb.gen_lut_bytes / 4);
+      pb.gen_lut_bytes += align_up(size_t(q.lut_size) * 4, 256);
+    }
+  }
   size_t blob_bytes = 0;
-  r = collect_blobs(v, pb.uses, pb.blobs, pb.fetch_blob, blob_bytes);
+  r = collect_blobs(v, pb.uses, pb.blobs, pb.fetch_blob, blob_bytes, pb.fetch_lut_request);
   if (r) return r;
-  plan_layout(v, blob_bytes, pb.lay);
+  plan_layout(v, blob_bytes, pb.gen_lut_bytes, pb.lay);
   pb.has_analytic = false;
   for (uint32_t i = 0; i < v->command_count; i++) if (v->commands[i].type == B2DGPU_CMD_FILL_ANALYTIC) pb.has_analytic = true;
   pb.solid = detect_solid_fill(v);
@@ -882,8 +914,17 @@ static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v
 
   // Patch host pointers inside FetchData to their device copies.
   b2dgpu_fetch_data* fd = reinterpret_cast<b2dgpu_fetch_data*>(host_block + pb.lay.fetch_data);
+  if (v->lut_request_count) {
+    memcpy(host_block + pb.lay.lut_requests, v->lut_requests, sizeof(b2dgpu_lut_request) * v->lut_request_count);
+    memcpy(host_block + pb.lay.lut_stops, v->lut_stops, sizeof(b2dgpu_gradient_stop) * v->lut_stop_count);
+    memcpy(host_block + pb.lay.lut_offsets, pb.lut_table_offsets.data(), sizeof(uint32_t) * v->lut_request_count);
+  }
   for (uint32_t i = 0; i < v->fetch_count; i++) {
     if (!pb.uses[i].used) continue;
+    if (pb.fetch_lut_request[i] >= 0 && pb.fetch_blob[i] == size_t(-1)) {
+      fd[i].gradient.lut.data = dev_block + pb.lay.gen_luts + size_t(pb.lut_table_offsets[size_t(pb.fetch_lut_request[i])]) * 4;
+      continue;
+    }
     const uint8_t* dev = dev_block + pb.lay.blobs + pb.blobs[pb.fetch_blob[i]].offset;
     if (pb.uses[i].fetch_type >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD) fd[i].gradient.lut.data = dev;
     else fd[i].pattern.src.pixel_data = dev;
@@ -895,6 +936,15 @@ static b2dgpu_result upload_block(b2dgpu_runtime* rt, const b2dgpu_batch_view* v
   CU_TRY(cudaEventRecord(st.free_event, stream));
   st.in_flight = true;
   rt->stats.h2d_bytes += pb.lay.upload1_bytes + pb.lay.seg_upload_bytes;
+  if (v->lut_request_count) {
+    LutParams LP;
+    LP.requests = reinterpret_cast<const b2dgpu_lut_request*>(dev_block + pb.lay.lut_requests);
+    LP.request_count = v->lut_request_count;
+    LP.stops = reinterpret_cast<const b2dgpu_gradient_stop*>(dev_block + pb.lay.lut_stops);
+    LP.table_offsets = reinterpret_cast<const uint32_t*>(dev_block + pb.lay.lut_offsets);
+    LP.tables = reinterpret_cast<uint32_t*>(dev_block + pb.lay.gen_luts);
+    rt->stats.kernel_launches += uint64_t(launch_build_luts(LP, stream));
+  }
   return sync_glyph_cache(rt, v, stream);
 }
 

@@ -346,6 +346,18 @@ typedef struct b2dgpu_glyph_instance {
   uint32_t command;            /* the FILL_GEOMETRY command the segments belong to                                  */
 } b2dgpu_glyph_instance;
 
+/* Gradient table interpolation on the device.  A gradient FetchData whose `lut.data` is NULL (and whose
+ * `lut.size` is set) gets its table built by the runtime from the gradient's stops - core/gradient.cpp:289-330 calling
+ * interpolate_prgb32 (pixelops/interpolation_avx2.cpp:18-205) - instead of receiving it from the host: 16 bytes per stop
+ * travel instead of 1-4 KB per gradient.  Nearest-neighbour (32-bit) tables only. */
+typedef struct b2dgpu_gradient_stop { double offset; uint64_t rgba64; } b2dgpu_gradient_stop;   /* = BLGradientStop */
+typedef struct b2dgpu_lut_request {
+  uint32_t fetch_index;        /* the FetchData entry the table belongs to                                         */
+  uint32_t stop_offset;        /* first stop in b2dgpu_batch_view::lut_stops                                       */
+  uint32_t stop_count;         /* >= 1, offsets ascending in [0, 1]                                                */
+  uint32_t lut_size;           /* entries; must equal fetch_data[fetch_index].gradient.lut.size                    */
+} b2dgpu_lut_request;
+
 typedef struct b2dgpu_batch_view {
   uint32_t struct_size;
   uint32_t command_count;
@@ -362,6 +374,9 @@ typedef struct b2dgpu_batch_view {
   const b2dgpu_glyph_instance* glyph_instances; uint32_t glyph_instance_count; uint32_t _pad6;
   uint32_t generated_vertex_count;       /* vertices / segments the instances write: commands may refer to segment */
   uint32_t generated_segment_count;      /* indices up to segment_count + generated_segment_count                 */
+  /* --- device-built gradient tables; absent or zero when unused --- */
+  const b2dgpu_lut_request* lut_requests;  uint32_t lut_request_count;  uint32_t _pad7;
+  const b2dgpu_gradient_stop* lut_stops;   uint32_t lut_stop_count;     uint32_t _pad8;
 } b2dgpu_batch_view;
 #define B2DGPU_BATCH_VIEW_SIZE_V1 ((uint32_t)offsetof(b2dgpu_batch_view, glyph_cache))
 

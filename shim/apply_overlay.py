@@ -29,6 +29,12 @@ HOOKS = [
      "    if (GpuShim::is_gpu(ctx_impl))\n"
      "      BL_PROPAGATE(GpuShim::sync_to_host(ctx_impl));\n"),
 
+    # 2b. ensure_fetch_and_dispatch_data_slow(), rastercontext.cpp:1130-1131: a gradient whose table does not exist yet is
+    #     not interpolated on the host for a GPU context - the device builds it from the stops.
+    ("    BL_PROPAGATE(compute_pending_fetch_data(static_cast<RenderFetchData*>(fetch_data)));", "replace",
+     "    if (!(GpuShim::is_gpu(ctx_impl) && GpuShim::defer_gradient_table(ctx_impl, static_cast<RenderFetchData*>(fetch_data))))\n"
+     "      BL_PROPAGATE(compute_pending_fetch_data(static_cast<RenderFetchData*>(fetch_data)));\n"),
+
     # 3. implementation, placed after the asynchronous enqueue helpers it uses (rastercontext.cpp:2410-2630).
     ("// bl::RasterEngine - ContextImpl - Internals - Fill Clipped Box", "before",
      '#include "b2dgpu_shim_impl.h"\n\n'),

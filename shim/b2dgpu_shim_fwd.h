@@ -52,6 +52,10 @@ static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::Pip
 //! flush_render_batch(): consumes the batch instead of WorkerProc::process_work_data().
 static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, RenderBatch* batch) noexcept;
 
+//! ensure_fetch_and_dispatch_data_slow(): leaves a pending nearest-neighbour gradient table to the device (the FetchData
+//! keeps lut.data == nullptr; consume_batch() ships the stops).  Returns false when the host has to build it.
+static bool defer_gradient_table(BLRasterContextImpl* ctx_impl, RenderFetchData* fetch_data) noexcept;
+
 //! flush_impl(BL_CONTEXT_FLUSH_SYNC): makes the host pixels of the target image coherent.
 static BLResult sync_to_host(BLRasterContextImpl* ctx_impl) noexcept;
 

@@ -59,6 +59,9 @@ struct State {
   std::vector<b2dgpu_glyph_instance> instances;     // vertex_base / segment_base relative to the generated ranges until submit
   uint32_t gen_vertices = 0, gen_segments = 0;
   bool use_glyph_cache = true;
+  bool device_luts = true;          // gradient tables interpolated on the device (B2DGPU_SHIM_DEVICE_LUTS=0: on the host)
+  std::vector<b2dgpu_lut_request> lut_requests;
+  std::vector<b2dgpu_gradient_stop> lut_stops;
   uint64_t glyphs_instanced = 0, glyph_runs_on_host = 0;    // B2DGPU_SHIM_STATS=1 prints them when the context goes away
 
   void clear_geometry() noexcept { vtx.clear(); segs.clear(); states.clear(); direct.clear(); instances.clear(); gen_vertices = 0; gen_segments = 0; }
@@ -152,6 +155,8 @@ static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::Pip
   st->cpu_edges = e && e[0] == '1';
   e = getenv("B2DGPU_SHIM_PIN");
   st->pin_images = !(e && e[0] == '0');
+  e = getenv("B2DGPU_SHIM_DEVICE_LUTS");
+  st->device_luts = !(e && e[0] == '0');
   e = getenv("B2DGPU_SHIM_GLYPH_CACHE");
   st->use_glyph_cache = !(e && e[0] == '0');
 
@@ -164,6 +169,16 @@ static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::Pip
   rt->state = st;
   *runtime = rt;
   return BL_SUCCESS;
+}
+
+static bool defer_gradient_table(BLRasterContextImpl* ctx_impl, RenderFetchData* fetch_data) noexcept {
+  State* st = state_of(ctx_impl);
+  if (!st->device_luts || !fetch_data->signature.is_gradient()) return false;
+  if (BLGradientQuality(fetch_data->extra.custom[0]) >= BL_GRADIENT_QUALITY_DITHER) return false;   // 64-bit tables: host
+  // what compute_pending_fetch_data() (raster/renderfetchdata.cpp:14-35) does, minus ensure_lut32()
+  fetch_data->signature.clear_pending_bit();
+  fetch_data->pipeline_data.gradient.lut.data = nullptr;
+  return true;
 }
 
 // The device canvas is created on first use from ctx_impl->dst_data (known only at the end of attach()) and
@@ -797,16 +812,27 @@ static void append_edge_vectors(State* st, const EdgeVector<int>* ev) noexcept {
   }
 }
 
-static uint32_t add_fetch_data(State* st, const void* key, const void* pipeline_data) noexcept {
+static uint32_t add_fetch_data(State* st, const RenderFetchData* rfd) noexcept {
   // Consecutive commands usually share their style: look at the most recent entries first.
+  const void* key = rfd;
   const size_t n = st->fetch_keys.size();
   for (size_t k = 0; k < n && k < 4; k++)
     if (st->fetch_keys[n - 1 - k] == key)
       return uint32_t(n - 1 - k);
   b2dgpu_fetch_data fd;
-  memcpy(&fd, pipeline_data, sizeof(fd));
+  memcpy(&fd, &rfd->pipeline_data, sizeof(fd));
   st->fetch.push_back(fd);
   st->fetch_keys.push_back(key);
+  if (rfd->signature.is_gradient() && !fd.gradient.lut.data) {
+    // deferred by defer_gradient_table(): the device interpolates the table from the gradient's stops, which the
+    // FetchData keeps alive through its style reference (renderfetchdata_p.h:43, 181-184)
+    const BLGradientPrivateImpl* gi = GradientInternal::get_impl(&rfd->style_as<BLGradientCore>());
+    b2dgpu_lut_request q;
+    q.fetch_index = uint32_t(n); q.stop_offset = uint32_t(st->lut_stops.size());
+    q.stop_count = uint32_t(gi->size); q.lut_size = fd.gradient.lut.size;
+    for (size_t k = 0; k < gi->size; k++) st->lut_stops.push_back(b2dgpu_gradient_stop{ gi->stops[k].offset, gi->stops[k].rgba.value });
+    st->lut_requests.push_back(q);
+  }
   return uint32_t(n);
 }
 
@@ -823,6 +849,8 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
   st->cmds.resize(command_count);
   st->fetch.clear();
   st->fetch_keys.clear();
+  st->lut_requests.clear();
+  st->lut_stops.clear();
   st->edges.clear();
 
   // Queues are chained; a job addresses its command as (queue, index).
@@ -945,7 +973,7 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
       }
 
       if (rc.has_style_fetch_data())
-        c.fetch_index = add_fetch_data(st, rc._source.fetch_data, &rc._source.fetch_data->pipeline_data);
+        c.fetch_index = add_fetch_data(st, static_cast<const RenderFetchData*>(rc._source.fetch_data));
       else
         c.solid_prgb32 = rc._source.solid.prgb32;
       st->cmds[out_count++] = c;
@@ -963,6 +991,8 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
     v.vertices = st->vtx.data();            v.vertex_count = uint32_t(st->vtx.size() / 2);
     v.segments = st->segs.data();           v.segment_count = uint32_t(st->segs.size());
     v.geometry_states = st->states.data();  v.geometry_state_count = uint32_t(st->states.size());
+    v.lut_requests = st->lut_requests.data();  v.lut_request_count = uint32_t(st->lut_requests.size());
+    v.lut_stops = st->lut_stops.data();        v.lut_stop_count = uint32_t(st->lut_stops.size());
     if (!st->instances.empty()) {
       // the generated ranges start where the uploaded arrays end
       const uint32_t v0 = v.vertex_count, s0 = v.segment_count;
