@@ -59,6 +59,7 @@ struct State {
   std::vector<b2dgpu_glyph_instance> instances;     // vertex_base / segment_base relative to the generated ranges until submit
   uint32_t gen_vertices = 0, gen_segments = 0;
   bool use_glyph_cache = true;
+  bool adaptive_batches = false;
   bool device_luts = true;          // gradient tables interpolated on the device (B2DGPU_SHIM_DEVICE_LUTS=0: on the host)
   std::vector<b2dgpu_lut_request> lut_requests;
   std::vector<b2dgpu_gradient_stop> lut_stops;
@@ -115,6 +116,9 @@ static void BL_CDECL runtime_destroy(Pipeline::PipeRuntime* self) noexcept {
   delete rt;
 }
 
+static constexpr uint32_t kCreateFlagAdaptiveBatches = 0x20000000u;    // private: set by adjust_create_info() on its own copy
+static constexpr uint32_t kFirstBatch = 512, kLargestBatch = 8192;
+
 static const BLContextCreateInfo* adjust_create_info(const BLContextCreateInfo* options, BLContextCreateInfo* storage) noexcept {
   if (!(options->flags & kCreateFlagGpuRuntime))
     return options;
@@ -123,8 +127,17 @@ static const BLContextCreateInfo* adjust_create_info(const BLContextCreateInfo* 
   storage->flags &= ~uint32_t(BL_CONTEXT_CREATE_FLAG_FALLBACK_TO_SYNC);
   // b2dgpu_submit() is asynchronous and double buffered: shorter batches let the device start while the frontend is
   // still recording (the reference's default is 10240 commands, rastercontext_p.h:62).
-  if (!storage->command_queue_limit)
-    storage->command_queue_limit = 2048;
+  if (!storage->command_queue_limit) {
+    // Adaptive (B2DGPU_SHIM_ADAPTIVE=0: fixed 2048): the first batch of a frame is small so that the device starts early,
+    // every further batch doubles - the frontend records faster than the device composites, so bigger batches only
+    // mean fewer per-batch kernels; consume_batch() and sync_to_host() move the limit.
+    const char* e = getenv("B2DGPU_SHIM_ADAPTIVE");
+    if (e && e[0] == '0') storage->command_queue_limit = 2048;
+    else {
+      storage->command_queue_limit = kFirstBatch;
+      storage->flags |= kCreateFlagAdaptiveBatches;
+    }
+  }
   return storage;
 }
 
@@ -157,6 +170,7 @@ static BLResult create_runtime(const BLContextCreateInfo* options, Pipeline::Pip
   st->pin_images = !(e && e[0] == '0');
   e = getenv("B2DGPU_SHIM_DEVICE_LUTS");
   st->device_luts = !(e && e[0] == '0');
+  st->adaptive_batches = (options->flags & kCreateFlagAdaptiveBatches) != 0;
   e = getenv("B2DGPU_SHIM_GLYPH_CACHE");
   st->use_glyph_cache = !(e && e[0] == '0');
 
@@ -210,6 +224,7 @@ static BLResult sync_to_host(BLRasterContextImpl* ctx_impl) noexcept {
   if (r != B2DGPU_SUCCESS)
     return ctx_impl->accumulate_error(bl_make_error(BLResult(r)));
   st->device_dirty = false;
+  if (st->adaptive_batches) ctx_impl->worker_mgr()._command_queue_limit = kFirstBatch;     // a new frame starts small again
   return BL_SUCCESS;
 }
 
@@ -1013,6 +1028,11 @@ static void consume_batch(BLRasterContextImpl* ctx_impl, WorkData* work_data, Re
   }
 
   st->clear_geometry();
+
+  if (st->adaptive_batches) {
+    WorkerManager& mgr = ctx_impl->worker_mgr();
+    if (mgr._command_queue_limit < kLargestBatch) mgr._command_queue_limit *= 2u;
+  }
 }
 
 } // {GpuShim}
