@@ -53,7 +53,10 @@ struct State {
 
   // Glyph cache: TrueType outlines in the format of dev_glyph.cuh, append-only, mirrored on the device by
   // the runtime; a text fill is described by one b2dgpu_glyph_instance per glyph instead of its decoded outline.
-  struct GlyphEntry { uint32_t blob_offset, vertices, segments; uint8_t kind; };   // kind: 0 cached, 1 no outline, 2 decode on the host
+  // kind: 0 cached outline, 1 no outline, 2 decode on the host, 3 compound: components [comp_begin, comp_begin + comp_count)
+  struct GlyphEntry { uint32_t blob_offset, vertices, segments; uint8_t kind; uint32_t comp_begin, comp_count; };
+  struct GlyphComponent { uint32_t glyph_id; BLMatrix2D local; };                   // opentype/otglyf.cpp:505-596
+  std::vector<GlyphComponent> glyph_components;
   std::unordered_map<uint64_t, GlyphEntry> glyph_map;
   std::vector<uint32_t> glyph_cache;
   std::vector<b2dgpu_glyph_instance> instances;     // vertex_base / segment_base relative to the generated ranges until submit
@@ -442,12 +445,131 @@ struct GlyphPathPut {
   }
 };
 
+static State::GlyphEntry build_glyph_entry(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id) noexcept;
+
+static const State::GlyphEntry& glyph_entry(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id) noexcept {
+  const uint64_t key = (uint64_t(face_impl->unique_id) << 32) | glyph_id;
+  auto it = st->glyph_map.find(key);
+  if (it == st->glyph_map.end()) {
+    const State::GlyphEntry e = build_glyph_entry(st, face_impl, glyph_id);       // may insert other glyphs (components)
+    it = st->glyph_map.emplace(key, e).first;
+  }
+  return it->second;
+}
+
+// Every vertex a cached glyph (simple or compound) produces under `m`, in the reference's order, through `sink(x, y)`;
+// CLOSE slots are reported as NaN.  Returns false when some component is not cached.
+template<typename Sink>
+static bool replay_glyph(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id, const BLMatrix2D& m, Sink& sink, int level) noexcept {
+  const State::GlyphEntry e = glyph_entry(st, face_impl, glyph_id);
+  if (e.kind == 1) return true;
+  if (e.kind == 0) {
+    struct Put {
+      std::vector<BLPoint>* v; size_t base;
+      void operator()(uint32_t index, double x, double y) noexcept { (*v)[base + index] = BLPoint(x, y); }
+    };
+    std::vector<BLPoint> tmp(e.vertices, BLPoint(Math::nan<double>(), Math::nan<double>()));
+    Put put = { &tmp, 0 };
+    const double mm[6] = { m.m00, m.m01, m.m10, m.m11, m.m20, m.m21 };
+    if (b2d::glyph_emit(b2d::glyph_blob_view(st->glyph_cache.data() + e.blob_offset), mm, put) != e.vertices) return false;
+    for (const BLPoint& pt : tmp) sink(pt.x, pt.y);
+    return true;
+  }
+  if (e.kind != 3 || level >= 15) return false;
+  for (uint32_t k = 0; k < e.comp_count; k++) {
+    const State::GlyphComponent comp = st->glyph_components[e.comp_begin + k];
+    BLMatrix2D cm = comp.local;
+    TransformInternal::multiply(cm, cm, m);                                      // otglyf.cpp:601
+    if (!replay_glyph(st, face_impl, comp.glyph_id, cm, sink, level + 1)) return false;
+  }
+  return true;
+}
+
+// A compound glyph: the list of its components with their local matrices (opentype/otglyf.cpp:505-601, restated: flags,
+// glyph id, byte / word arguments, F2Dot14 scale / scale-xy / 2x2, FreeType-style scaled offsets).  An instance of it is
+// expanded on the host into instances of the components with the composed matrices the reference would use; like a
+// simple entry it is only kept if that reproduces the reference's decoder bit for bit under two matrices.
+static State::GlyphEntry build_compound_entry(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id, const uint8_t* p, const uint8_t* end) noexcept {
+  State::GlyphEntry host = { 0, 0, 0, 2, 0, 0 };
+  const OpenType::OTFaceImpl* ot = static_cast<const OpenType::OTFaceImpl*>(face_impl);
+  std::vector<State::GlyphComponent> comps;
+  for (;;) {
+    if (end - p < 6) return host;
+    const uint32_t flags = MemOps::readU16uBE(p);
+    const uint32_t comp_glyph = MemOps::readU16uBE(p + 2);
+    if (comp_glyph >= ot->face_info.glyph_count || comp_glyph == glyph_id) return host;
+    int arg1 = int(int8_t(p[4])), arg2 = int(int8_t(p[5]));
+    p += 6;
+    if (flags & 0x0001u) {                                                          // kArgsAreWords
+      if (end - p < 2) return host;
+      arg1 = int(uint32_t(arg1) << 8) | (arg2 & 0xFF);
+      arg2 = int(int16_t(MemOps::readU16uBE(p)));
+      p += 2;
+    }
+    if (!(flags & 0x0002u)) { arg1 &= 0xFFFF; arg2 &= 0xFFFF; }                     // kArgsAreXYValues
+    const double kScaleF2x14 = 1.0 / 16384.0;
+    BLMatrix2D cm(1.0, 0.0, 0.0, 1.0, double(arg1), double(arg2));
+    if (flags & (0x0008u | 0x0040u | 0x0080u)) {                                    // kAnyCompoundScale
+      if (flags & 0x0008u) {
+        if (end - p < 2) return host;
+        const double scale = double(int16_t(MemOps::readU16uBE(p))) * kScaleF2x14;
+        cm.m00 = scale; cm.m11 = scale; p += 2;
+      }
+      else if (flags & 0x0040u) {
+        if (end - p < 4) return host;
+        cm.m00 = double(int16_t(MemOps::readU16uBE(p))) * kScaleF2x14;
+        cm.m11 = double(int16_t(MemOps::readU16uBE(p + 2))) * kScaleF2x14; p += 4;
+      }
+      else {
+        if (end - p < 8) return host;
+        cm.m00 = double(int16_t(MemOps::readU16uBE(p))) * kScaleF2x14;
+        cm.m01 = double(int16_t(MemOps::readU16uBE(p + 2))) * kScaleF2x14;
+        cm.m10 = double(int16_t(MemOps::readU16uBE(p + 4))) * kScaleF2x14;
+        cm.m11 = double(int16_t(MemOps::readU16uBE(p + 6))) * kScaleF2x14; p += 8;
+      }
+      if ((flags & (0x0002u | 0x0800u | 0x1000u)) == (0x0002u | 0x0800u)) {          // scaled component offset
+        cm.m20 *= Geometry::magnitude(BLPoint(cm.m00, cm.m01));
+        cm.m21 *= Geometry::magnitude(BLPoint(cm.m10, cm.m11));
+      }
+    }
+    comps.push_back(State::GlyphComponent{ comp_glyph, cm });
+    if (comps.size() > 64) return host;
+    if (!(flags & 0x0020u)) break;                                                  // kMoreComponents
+  }
+
+  // register (tentatively) so that replay_glyph() can walk it, verify against the reference, roll back on a mismatch
+  State::GlyphEntry e = { 0, 0, 0, 3, uint32_t(st->glyph_components.size()), uint32_t(comps.size()) };
+  st->glyph_components.insert(st->glyph_components.end(), comps.begin(), comps.end());
+  const uint64_t key = (uint64_t(face_impl->unique_id) << 32) | glyph_id;
+  st->glyph_map[key] = e;
+  bool ok = true;
+  const BLMatrix2D tests[2] = { BLMatrix2D(1.0, 0.0, 0.0, 1.0, 0.0, 0.0), BLMatrix2D(0.37109375, -0.113, 0.2291, 0.90625, 5.53, -3.2517) };
+  for (const BLMatrix2D& m : tests) {
+    BLPath path;
+    size_t contour_count = 0;
+    ScopedBufferTmp<BL_FONT_GET_GLYPH_OUTLINE_BUFFER_SIZE> tmp_buffer;
+    if (face_impl->funcs.get_glyph_outlines(face_impl, glyph_id, &m, &path, &contour_count, &tmp_buffer) != BL_SUCCESS) { ok = false; break; }
+    struct Check {
+      const BLPoint* want; size_t size, at; bool ok;
+      void operator()(double x, double y) noexcept {
+        if (at >= size) { ok = false; return; }
+        const bool close_slot = x != x;
+        if (close_slot ? !(want[at].x != want[at].x) : (memcmp(&want[at].x, &x, 8) != 0 || memcmp(&want[at].y, &y, 8) != 0)) ok = false;
+        at++;
+      }
+    } check = { path.vertex_data(), path.size(), 0, true };
+    if (!replay_glyph(st, face_impl, glyph_id, m, check, 0) || !check.ok || check.at != path.size()) { ok = false; break; }
+  }
+  if (!ok) { st->glyph_map[key] = host; return host; }
+  return e;
+}
+
 // Builds the cache entry of one glyph: parses its `glyf` record (TrueType "Simple Glyph Description": flags with
 // repeats, byte / word coordinate deltas), takes the path STRUCTURE from the reference's own decoder and keeps the entry
 // only if replaying the deltas (b2d::glyph_emit) reproduces the reference's vertices bit for bit under the identity AND
 // under a general matrix.  Anything else - compound glyphs, empty contours, malformed data - is decoded on the host.
 static State::GlyphEntry build_glyph_entry(State* st, const BLFontFacePrivateImpl* face_impl, BLGlyphId glyph_id) noexcept {
-  State::GlyphEntry host = { 0, 0, 0, 2 };
+  State::GlyphEntry host = { 0, 0, 0, 2, 0, 0 };
   const OpenType::OTFaceImpl* ot = static_cast<const OpenType::OTFaceImpl*>(face_impl);
   if (glyph_id >= ot->face_info.glyph_count) return host;
   const OpenType::RawTable glyf = ot->glyf.glyf_table, loca = ot->glyf.loca_table;
@@ -464,13 +586,14 @@ static State::GlyphEntry build_glyph_entry(State* st, const BLFontFacePrivateImp
     offset = MemOps::readU32uBE(loca.data + index);
     end_off = MemOps::readU32uBE(loca.data + index + 4);
   }
-  if (offset == end_off && end_off <= glyf.size) return State::GlyphEntry{ 0, 0, 0, 1 };      // no outline (space)
+  if (offset == end_off && end_off <= glyf.size) return State::GlyphEntry{ 0, 0, 0, 1, 0, 0 };      // no outline (space)
   if (offset >= end_off || end_off > glyf.size || end_off - offset < 12u) return host;
 
   const uint8_t* p = glyf.data + offset;
   const uint8_t* end = glyf.data + end_off;
   const int contours = int(int16_t(MemOps::readU16uBE(p)));
-  if (contours <= 0 || contours > 4096) return host;                                            // compound (-1) or nothing
+  if (contours == -1) return build_compound_entry(st, face_impl, glyph_id, p + 10, end);
+  if (contours <= 0 || contours > 4096) return host;
   p += 10;
   if (size_t(end - p) < size_t(contours) * 2u + 2u) return host;
   std::vector<uint32_t> ends(size_t(contours), 0u);
@@ -552,7 +675,7 @@ static State::GlyphEntry build_glyph_entry(State* st, const BLFontFacePrivateImp
     if (b2d::glyph_emit(view, m, put) != nv || !put.ok) return host;
   }
 
-  State::GlyphEntry e = { uint32_t(st->glyph_cache.size()), uint32_t(nv), uint32_t(ns), 0 };
+  State::GlyphEntry e = { uint32_t(st->glyph_cache.size()), uint32_t(nv), uint32_t(ns), 0, 0, 0 };
   st->glyph_cache.insert(st->glyph_cache.end(), blob.begin(), blob.end());
   return e;
 }
@@ -571,13 +694,22 @@ static bool instance_glyph_run(State* st, const BLFontCore* font, const BLGlyphR
   const uint32_t gen_v0 = st->gen_vertices, gen_s0 = st->gen_segments;
   bool ok = true;
 
-  auto emit = [&](BLGlyphId glyph_id, const BLMatrix2D& m) noexcept {
-    const uint64_t key = (uint64_t(face_impl->unique_id) << 32) | glyph_id;
-    auto it = st->glyph_map.find(key);
-    if (it == st->glyph_map.end()) it = st->glyph_map.emplace(key, build_glyph_entry(st, face_impl, glyph_id)).first;
-    const State::GlyphEntry& e = it->second;
+  struct Emit {
+    State* st; const BLFontFacePrivateImpl* face_impl; bool* ok;
+    void operator()(BLGlyphId glyph_id, const BLMatrix2D& m, int level = 0) const noexcept {
+    const State::GlyphEntry e = glyph_entry(st, face_impl, glyph_id);
     if (e.kind == 1) return;
-    if (e.kind != 0) { ok = false; return; }
+    if (e.kind == 3 && level < 15) {
+      // a compound glyph: one instance per component with the matrix the reference composes (otglyf.cpp:601)
+      for (uint32_t k = 0; k < e.comp_count && *ok; k++) {
+        const State::GlyphComponent comp = st->glyph_components[e.comp_begin + k];
+        BLMatrix2D cm = comp.local;
+        TransformInternal::multiply(cm, cm, m);
+        (*this)(comp.glyph_id, cm, level + 1);
+      }
+      return;
+    }
+    if (e.kind != 0) { *ok = false; return; }
     b2dgpu_glyph_instance gi;
     gi.m[0] = m.m00; gi.m[1] = m.m01; gi.m[2] = m.m10; gi.m[3] = m.m11; gi.m[4] = m.m20; gi.m[5] = m.m21;
     gi.blob_offset = e.blob_offset;
@@ -587,7 +719,8 @@ static bool instance_glyph_run(State* st, const BLFontCore* font, const BLGlyphR
     st->instances.push_back(gi);
     st->gen_vertices += e.vertices;
     st->gen_segments += e.segments;
-  };
+    }
+  } emit = { st, face_impl, &ok };
 
   BLMatrix2D final_transform;
   const BLFontMatrix& fMat = font_impl->matrix;
