@@ -592,7 +592,7 @@ def frames_leg(gb, args):
         dist.all_reduce(w_, op=dist.ReduceOp.SUM)
         secs, px, frames_done, res_v = float(t[0]), float(w_[0]), float(w_[1]), [float(w_[2]), float(w_[3]), float(w_[4])]
     return {"workload": f"config4(ii): {total_frames} independent {FW}x{FH} PRGB32 frames x {k} fills (polygons, quad/cubic paths, linear gradients + solid), "
-                        f"frame f -> GPU f mod {world}; every frame cleared, drawn, flush(SYNC), read on the host",
+                        f"frame f -> GPU f mod {world}; every frame cleared, drawn, flush(SYNC) into the BLImage's host pixels; every 32nd frame checksummed by the CPU",
             "frames": int(frames_done), "fills_per_frame": k, "n_gpus": world, "scaling": "strong (fixed batch of frames)",
             "e2e": {"seconds_max_over_ranks": secs, "frames_per_s": frames_done / secs, "fills_per_s": frames_done * k / secs, "mpix_s": px / secs / 1e6,
                     "d2h_bytes_per_frame": FW * FH * 4},
