@@ -449,9 +449,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_
   return s_warp[warp] + inc - v;
 }
 
-// out[i] = exclusive prefix of in[0..n); block_sums[b] = sum of block b.  `out` has n + 1 entries when `tail` != 0.
-__global__ void __launch_bounds__(kScanThreads) k_scan_blocks(const uint32_t* in, uint32_t* out, uint32_t* block_sums, uint32_t n) {
+// out[i] = exclusive prefix of in[0..n); block_sums[b] = sum of block b.  `out` has n + 1 entries (k_scan_add writes the total).
+__global__ void __launch_bounds__(kScanThreads) k_scan_blocks(const uint32_t* in, uint32_t* out, uint32_t* block_sums, uint32_t n, const uint32_t* n_dev) {
   __shared__ uint32_t s_warp[9];
+  if (n_dev) n = min(n, *n_dev);                       // the item count is only known on the device (k_bin_*)
   const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
@@ -470,22 +471,24 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_blocks(const uint32_t* in
   if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* out, const uint32_t* block_offsets, uint32_t n, uint32_t* total_out) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* out, const uint32_t* block_offsets, uint32_t n, uint32_t* total_out, const uint32_t* n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const uint32_t base = blockIdx.x * kScanBlock + threadIdx.x * kScanItems;
   const uint32_t add = block_offsets[blockIdx.x];
   #pragma unroll
   for (int k = 0; k < kScanItems; k++)
     if (base + k < n) out[base + k] += add;
-  if (total_out && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     // block_offsets has one extra entry holding the grand total (written by the level above).
     out[n] = block_offsets[gridDim.x];
-    *total_out = block_offsets[gridDim.x];
+    if (total_out) *total_out = block_offsets[gridDim.x];
   }
 }
 
 // Single-block scan for <= kScanBlock items; writes out[n] = total as well.
-__global__ void __launch_bounds__(kScanThreads) k_scan_small(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_small(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* total_out, const uint32_t* n_dev) {
   __shared__ uint32_t s_warp[9];
+  if (n_dev) n = min(n, *n_dev);
   const uint32_t base = threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   uint32_t sum = 0;
@@ -626,6 +629,7 @@ __global__ void __launch_bounds__(1024) k_bin_fill(BinParams B) {
       // a box's pixel box is exact; a shape starts empty and k_bin_extents widens it
       B.cell_ext[pos] = command_has_edges(B.commands[c].type) ? make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu) : make_uint2(uint32_t(bb.x), ~uint32_t(bb.z - 1));
       B.cm_index[B.cm_base[c] + uint32_t(b - (bb.y - B.y_begin) / B.tile_h)] = pos;
+      if (B.band_edges) B.cell_edge_cnt[pos] = 0;
     }
     run += total;
     __syncthreads();
@@ -652,9 +656,46 @@ __global__ void __launch_bounds__(256) k_bin_extents(BinParams B) {
     for (int b = (row_first - B.y_begin) / B.tile_h; b <= (row_last - B.y_begin) / B.tile_h; b++) {
       int lo, hi;
       band_edge_extent(ne, B.y_begin + b * B.tile_h, lo, hi, B.tile_h);
-      uint32_t* cell = reinterpret_cast<uint32_t*>(B.cell_ext + index[b - band0]);
+      const uint32_t ci = index[b - band0];
+      uint32_t* cell = reinterpret_cast<uint32_t*>(B.cell_ext + ci);
       atomicMin(cell, uint32_t(lo));
       atomicMin(cell + 1, ~uint32_t(hi));
+      if (B.band_edges) atomicAdd(B.cell_edge_cnt + ci, 1u);
+    }
+  }
+}
+
+// After the scan of the per-cell pair counts: do the edge lists fit?
+__global__ void k_bin_check_edges(BinParams B) {
+  if (!B.state[1]) { B.state[2] = 0; B.state[3] = 0; return; }
+  const uint32_t pairs = B.cell_edge_off[B.state[0]];
+  B.state[3] = pairs;
+  B.state[2] = pairs <= B.edge_list_capacity ? 1u : 0u;
+}
+
+// Second pass over the (edge, band) pairs: every pair drops its edge index into its cell's list.  The counters run back
+// down to zero, the order inside a list is irrelevant (u32 cover / area adds commute).
+__global__ void __launch_bounds__(256) k_bin_edges(BinParams B) {
+  if (!B.state[1] || !B.state[2]) return;
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  if (c >= B.command_count) return;
+  const int4 bb = B.cmd_bbox_px[c];
+  if (bb.x >= bb.z || bb.y >= bb.w) return;
+  if (!command_has_edges(B.commands[c].type)) return;
+  const int band0 = (bb.y - B.y_begin) / B.tile_h;
+  const uint32_t* __restrict__ index = B.cm_index + B.cm_base[c];
+  const uint2 er = B.cmd_edges[c];
+  const int4* __restrict__ edges = reinterpret_cast<const int4*>(B.edges);
+  for (uint32_t e = lane; e < er.y; e += 32) {
+    const NormEdge ne = load_edge(edges, er.x + e);
+    if (ne.y0 == ne.y1) continue;
+    const int row_first = max(ne.y0 >> 8, bb.y), row_last = min((ne.y1 - 1) >> 8, bb.w - 1);
+    if (row_first > row_last) continue;
+    for (int b = (row_first - B.y_begin) / B.tile_h; b <= (row_last - B.y_begin) / B.tile_h; b++) {
+      const uint32_t ci = index[b - band0];
+      const uint32_t k = atomicSub(B.cell_edge_cnt + ci, 1u) - 1u;
+      B.band_edges[B.cell_edge_off[ci] + k] = er.x + e;
     }
   }
 }
@@ -862,6 +903,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   const bool binned = P.bin_state != nullptr && P.bin_state[1] != 0u;
   const uint32_t list_begin = binned ? P.band_off[tile_y] : 0u;
   const uint32_t list_count = binned ? P.band_off[tile_y + 1] - list_begin : P.command_count;
+  const bool edge_lists = binned && P.band_edges != nullptr && P.bin_state[2] != 0u;
   for (uint32_t base = 0; base < list_count || ring_head != ring_tail; base += kThreads) {
     // ---- cull: which of the next kThreads candidates touch this tile? (order preserving compaction) ----
     if (base < list_count) {
@@ -871,7 +913,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         if (binned) {
           const uint2 ex = P.cell_ext[list_begin + base + tid];
           hit = uint32_t(tx0 + kTileW) > ex.x && uint32_t(tx0) <= ~ex.y;
-          c = P.cell_cmd[list_begin + base + tid];
+          c = list_begin + base + tid;                  // the ring holds the CELL; the command is cell_cmd[cell]
         }
         else {
           c = base + tid;
@@ -905,7 +947,8 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
       for (uint32_t k = warp; k < sub_n; ) {
-        const uint32_t ci = s_list[(sub + k) & (kRing - 1)];
+        const uint32_t cell = s_list[(sub + k) & (kRing - 1)];
+        const uint32_t ci = binned ? __ldg(P.cell_cmd + cell) : cell;
         PreCmd* pre = &s_pre[k];
         if (lane < TH) { pre->carry4[lane] = make_uint4(0, 0, 0, 0); pre->nent[lane] = 0; pre->ovf_head[lane] = 0; }
         if (lane < (TH + 7) / 8) pre->blk_has[lane] = 0;
@@ -924,7 +967,15 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         const bool is_box = !command_has_edges(pre->cmd_words[0]);
 
         if (!is_box) {
-          const uint2 er = P.cmd_edges[ci];
+          // The edges to look at: the cell's list (the edges of the command that cross this band) or, without lists,
+          // every edge of the command.
+          uint2 er = P.cmd_edges[ci];
+          const uint32_t* __restrict__ elist = nullptr;
+          if (edge_lists) {
+            const uint32_t o0 = __ldg(P.cell_edge_off + cell), o1 = __ldg(P.cell_edge_off + cell + 1);
+            elist = P.band_edges + o0;
+            er.y = o1 - o0;
+          }
           EntrySink<TH> sink; sink.pre = pre; sink.pool_cap = uint32_t(kPool); sink.pool = s_pool; sink.pool_link = s_pool_link; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
             const uint32_t e = e0 + lane;
@@ -932,8 +983,10 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             uint32_t rows_crossed = 0, first_row = 0;
             int ey0 = 0, ey1 = 0;
             uint32_t esign = 0;
+            uint32_t eidx = 0;
             if (e < er.y) {
-              NormEdge ne = load_edge(edges, er.x + e);
+              eidx = elist ? __ldg(elist + e) : er.x + e;
+              NormEdge ne = load_edge(edges, eidx);
               cls = tile_edge_class(ne, tx0, ty0, TH);
               ey0 = ne.y0; ey1 = ne.y1; esign = ne.sign_bit;
               if (cls == kEdgeStraddle) {
@@ -978,9 +1031,10 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
               const uint32_t j_inc = __shfl_sync(0xFFFFFFFFu, inc, int(j & 31u));
               const uint32_t j_rows = __shfl_sync(0xFFFFFFFFu, rows_crossed, int(j & 31u));
               const uint32_t j_first = __shfl_sync(0xFFFFFFFFu, first_row, int(j & 31u));
+              const uint32_t j_eidx = __shfl_sync(0xFFFFFFFFu, eidx, int(j & 31u));
               if (i < chunk_items) {
                 const int r = int(j_first + (i - (j_inc - j_rows)));
-                NormEdge ne = load_edge(edges, er.x + e0 + j);
+                NormEdge ne = load_edge(edges, j_eidx);
                 sink.row = r;
                 tile_rasterize_edge_row(ne, ty0 + r, sink);
               }
@@ -1142,7 +1196,8 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           else {
             // Slow path: the group's four warps rasterize one row each, then read their blocks of all four rows.
             const int my_row = grp * kBlockRows + blk;
-            slow_group_rows(edges, P.cmd_edges[s_list[(sub + k) & (kRing - 1)]], tx0, ty0, my_row, lane, &s_cells[my_row][0], &s_carry[my_row],
+            const uint32_t ring_entry = s_list[(sub + k) & (kRing - 1)];
+            slow_group_rows(edges, P.cmd_edges[binned ? __ldg(P.cell_cmd + ring_entry) : ring_entry], tx0, ty0, my_row, lane, &s_cells[my_row][0], &s_carry[my_row],
                             (256u << 9) + pre.carry_left[my_row], TH, grp);
             const uint4 c = *reinterpret_cast<const uint4*>(&s_cells[row][blk * kBlockW + (lane & 7) * 4]);
             asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");      // the cells may be overwritten after this
@@ -1414,19 +1469,19 @@ size_t scan_scratch_items(uint32_t n) {
   return total + 8;
 }
 
-int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s) {
+int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s, const uint32_t* n_dev) {
   if (n <= kScanBlock) {
-    k_scan_small<<<1, kScanThreads, 0, s>>>(in, out, n, total_out);
+    k_scan_small<<<1, kScanThreads, 0, s>>>(in, out, n, total_out, n_dev);
     return 1;
   }
   uint32_t nb = div_up(n, kScanBlock);
   uint32_t* block_sums = scratch;               // nb + 1 entries; scanned in place
-  k_scan_blocks<<<nb, kScanThreads, 0, s>>>(in, out, block_sums, n);
+  k_scan_blocks<<<nb, kScanThreads, 0, s>>>(in, out, block_sums, n, n_dev);
   int launches = 1;
   // Scan the block sums in place (out == in is fine: every element is read before it is written by its own thread,
-  // and blocks only touch their own range).
-  launches += launch_exclusive_scan(block_sums, block_sums, nb, scratch + nb + 1, nullptr, s);
-  k_scan_add<<<nb, kScanThreads, 0, s>>>(out, block_sums, n, total_out);
+  // and blocks only touch their own range).  Blocks beyond a device-side count contribute zero.
+  launches += launch_exclusive_scan(block_sums, block_sums, nb, scratch + nb + 1, nullptr, s, nullptr);
+  k_scan_add<<<nb, kScanThreads, 0, s>>>(out, block_sums, n, total_out, n_dev);
   return launches + 1;
 }
 
@@ -1516,8 +1571,18 @@ int launch_binning(const BinParams& B, cudaStream_t s) {
   k_bin_check<<<1, 1, 0, s>>>(B);
   k_bin_fill<<<B.tiles_y, 1024, 0, s>>>(B);
   k_bin_extents<<<div_up(B.command_count * 32, 256), 256, 0, s>>>(B);
-  return launches + 3;
+  launches += 3;
+  if (B.band_edges) {
+    // per-cell edge lists: scan of the pair counts over the cells (their number lives in state[0]), then the fill pass
+    launches += launch_exclusive_scan(B.cell_edge_cnt, B.cell_edge_off, B.capacity, B.scan_scratch2, nullptr, s, B.state);
+    k_bin_check_edges<<<1, 1, 0, s>>>(B);
+    k_bin_edges<<<div_up(B.command_count * 32, 256), 256, 0, s>>>(B);
+    launches += 2;
+  }
+  return launches;
 }
+
+size_t bin_cell_scan_scratch_items(uint32_t capacity) { return scan_scratch_items(capacity); }
 
 // Tile height for a target of `rows` rows and `tiles_x` tile columns: 32-row tiles (one 32-warp CTA per SM, the
 // configuration the 4K bench runs) when they give every SM a couple of tiles, shorter tiles for small canvases.

@@ -49,7 +49,12 @@ struct TileParams {
   const uint32_t* band_off;
   const uint32_t* cell_cmd;
   const uint2* cell_ext;
-  const uint32_t* bin_state;              // [0] cells needed, [1] lists valid; nullptr = no lists
+  const uint32_t* bin_state;              // [0] cells needed, [1] lists valid, [2] per-cell edge lists valid; nullptr = no lists
+  // Per (band, command) cell: the edges of the command that cross the band, as indices into `edges`:
+  // band_edges[cell_edge_off[cell] .. cell_edge_off[cell + 1]).  Phase 1 of the compositor walks these instead of all
+  // the edges of the command (the reference's per-band edge lists, edgestorage_p.h:38-178).
+  const uint32_t* cell_edge_off;
+  const uint32_t* band_edges;
   const b2dgpu_edge* edges;
   const b2dgpu_fetch_data* fetch_data;
   const uint8_t* bayer;
@@ -97,10 +102,16 @@ struct BinParams {
   uint32_t* cell_cmd;                     // band-major cells                                  (capacity)
   uint2* cell_ext;                        //                                                   (capacity)
   uint32_t capacity;
-  uint32_t* state;                        // [0] cells needed, [1] lists valid
+  uint32_t* state;                        // [0] cells needed, [1] lists valid, [2] edge lists valid, [3] (edge, band) pairs needed
   uint32_t* scan_scratch;
+  uint32_t* cell_edge_cnt;                // (edge, band) pairs per cell; counted down to zero again by k_bin_edges     (capacity)
+  uint32_t* cell_edge_off;                // exclusive scan of it                                                      (capacity + 1)
+  uint32_t* band_edges;                   // edge indices, grouped by cell                                             (edge_list_capacity)
+  uint32_t edge_list_capacity;
+  uint32_t* scan_scratch2;                // for the scan over the cells
 };
 size_t bin_scratch_items(uint32_t command_count, int tiles_y);
+size_t bin_cell_scan_scratch_items(uint32_t capacity);
 
 // One solid box fill over a large region (fill_all / clear_all / big FillRectA): pure streaming, see k_stream_solid.
 struct SolidStreamParams {
@@ -133,7 +144,8 @@ struct StreamOneParams {
 int launch_count_edges(const BuildParams& P, cudaStream_t s);
 int launch_write_edges(const BuildParams& P, cudaStream_t s);
 size_t scan_scratch_items(uint32_t n);
-int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s);
+// `n_dev` (optional): the item count lives on the device; at most `n` items, out[min(n, *n_dev)] = total.
+int launch_exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* scratch, uint32_t* total_out, cudaStream_t s, const uint32_t* n_dev = nullptr);
 int launch_init_bbox(int4* bbox, uint32_t n, cudaStream_t s);
 int launch_analytic_bbox(const b2dgpu_command* cmds, uint32_t ncmd, const b2dgpu_edge* edges, int4* bbox, cudaStream_t s);
 int launch_finalize_commands(const FinalizeParams& P, cudaStream_t s);

@@ -1110,6 +1110,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   T.origin_y = in.origin_y;
   T.pixel_counter = rt->count_pixels ? rt->d_pixel_counter : nullptr;
   T.band_off = nullptr; T.cell_cmd = nullptr; T.cell_ext = nullptr; T.bin_state = nullptr;
+  T.cell_edge_off = nullptr; T.band_edges = nullptr;
   // Per-band command lists with x-extents (k_bin_*).  Their size is only known on the device: the buffer holds
   // `bin_capacity` cells (the dense bound tiles_y * commands when that is small); a render that needed more renders
   // without lists (every tile scans every command - slow but correct) and the buffer is grown for the next one.
@@ -1142,6 +1143,15 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     const size_t o_cm_index = take(sizeof(uint32_t) * size_t(cap));
     const size_t o_cell_cmd = take(sizeof(uint32_t) * size_t(cap));
     const size_t o_cell_ext = take(sizeof(uint2) * size_t(cap));
+    // per-cell edge lists: (edge, band) pairs; an edge of a flattened curve rarely spans more than two bands
+    const bool with_edge_lists = total_edges != 0;
+    size_t pair_cap = with_edge_lists ? total_edges * 3 + (size_t(1) << 16) : 0;
+    if (pair_cap > 0xFFFFFF00u) pair_cap = 0xFFFFFF00u;
+    if (const char* e = getenv("B2DGPU_EDGE_LIST_CAPACITY")) if (with_edge_lists) pair_cap = size_t(strtoull(e, nullptr, 10));   // test knob
+    const size_t o_cell_edge_cnt = take(with_edge_lists ? sizeof(uint32_t) * size_t(cap) : 0);
+    const size_t o_cell_edge_off = take(with_edge_lists ? sizeof(uint32_t) * (size_t(cap) + 1) : 0);
+    const size_t o_scratch2 = take(with_edge_lists ? sizeof(uint32_t) * bin_cell_scan_scratch_items(cap) : 0);
+    const size_t o_band_edges = take(sizeof(uint32_t) * pair_cap);
     const size_t need = align_up(off, 256);
     if (need > rt->bins.cap) {
       CU_TRY(cudaStreamSynchronize(s));
@@ -1160,9 +1170,21 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     Bn.cm_index = reinterpret_cast<uint32_t*>(bp + o_cm_index); Bn.cell_cmd = reinterpret_cast<uint32_t*>(bp + o_cell_cmd);
     Bn.cell_ext = reinterpret_cast<uint2*>(bp + o_cell_ext);
     Bn.capacity = cap;
+    Bn.cell_edge_cnt = reinterpret_cast<uint32_t*>(bp + o_cell_edge_cnt);
+    Bn.cell_edge_off = reinterpret_cast<uint32_t*>(bp + o_cell_edge_off);
+    Bn.scan_scratch2 = reinterpret_cast<uint32_t*>(bp + o_scratch2);
+    Bn.band_edges = with_edge_lists ? reinterpret_cast<uint32_t*>(bp + o_band_edges) : nullptr;
+    Bn.edge_list_capacity = uint32_t(pair_cap);
     launches += launch_binning(Bn, s);
     CU_TRY(cudaMemcpyAsync(rt->h_bin_state, Bn.state, 8, cudaMemcpyDeviceToHost, s));    // read by a LATER render, never waited for
+    if (getenv("B2DGPU_DEBUG_BINS")) {
+      uint32_t st[4] = {0, 0, 0, 0};
+      cudaStreamSynchronize(s);
+      cudaMemcpy(st, Bn.state, 16, cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[bins] cmds %u tiles_y %d cap %u need %zu buf %zu pair_cap %zu edges %zu state %u %u %u %u err %s\n", in.command_count, T.tiles_y, cap, need, rt->bins.cap, pair_cap, total_edges, st[0], st[1], st[2], st[3], cudaGetErrorString(cudaGetLastError()));
+    }
     T.band_off = Bn.band_off; T.cell_cmd = Bn.cell_cmd; T.cell_ext = Bn.cell_ext; T.bin_state = Bn.state;
+    T.cell_edge_off = Bn.cell_edge_off; T.band_edges = Bn.band_edges;
   }
   if (rt->profiling && ti == 0) CU_TRY(cudaEventRecord(ev[1], s));
   bool streamed = false;

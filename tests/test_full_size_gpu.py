@@ -113,6 +113,10 @@ def test_unbinned_fallback_equals_binned(gpu, scene, monkeypatch):
     assert np.array_equal(a, plain.to_numpy())
     regrown, _ = replay(gpu, scene, count)                   # the next render builds its lists again
     assert np.array_equal(a, regrown.to_numpy())
+    monkeypatch.setenv("B2DGPU_EDGE_LIST_CAPACITY", "100")   # command lists yes, per-cell edge lists no: phase 1 walks all edges
+    no_edge_lists, _ = replay(gpu, scene, count)
+    monkeypatch.delenv("B2DGPU_EDGE_LIST_CAPACITY")
+    assert np.array_equal(a, no_edge_lists.to_numpy())
 
 
 def test_many_commands_and_many_tiles(ref, gpu):
