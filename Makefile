@@ -3,7 +3,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CSRC      := blend2d_b200/csrc
 OUT       := blend2d_b200/libb2dgpu.so
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false \
-             -Xcompiler -fPIC,-fvisibility=hidden,-O2 -Xptxas -v --expt-relaxed-constexpr
+             -Xcompiler -fPIC,-fvisibility=hidden,-O2 -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 HOSTSRC   := $(wildcard $(CSRC)/host/*.cpp)
 DEVHDR    := $(wildcard $(CSRC)/*.cuh) $(CSRC)/kernels.h include/b2dgpu.h
 

@@ -599,6 +599,7 @@ __global__ void k_bin_check(BinParams B) {
   const uint32_t total = B.cm_base[B.command_count];
   B.state[0] = total;
   B.state[1] = total <= B.capacity ? 1u : 0u;
+  B.state[2] = 1u; B.state[3] = 0u;                     // overwritten by k_bin_check_edges when edge lists are built
 }
 
 __global__ void __launch_bounds__(1024) k_bin_fill(BinParams B) {
@@ -816,8 +817,9 @@ __device__ __noinline__ uint4 box_mask_a_row(const b2dgpu_command& cmd, const b2
 // nearly horizontal edges).  Called by the four warps of a row group together: warp `b` rasterizes row 4g + b of the
 // tile into that row's shared-memory cells and turns them, in place, into the running coverage of the reference's
 // scanline walk (fillgeneric_p.h:285-297); after the group's barrier every warp reads its own block of all four rows.
+// `elist` != nullptr: the edges are elist[0 .. er.y) (the band's list of the command), otherwise er.x .. er.x + er.y.
 // Out of line: it is rare and large.
-__device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uint2 er, int tx0, int ty0, int row, int lane,
+__device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uint2 er, const uint32_t* __restrict__ elist, int tx0, int ty0, int row, int lane,
                                              uint32_t* cells_row, uint32_t* carry_row, uint32_t base, int tile_h, int group) {
   *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(0, 0, 0, 0);
   if (lane == 0) *carry_row = 0;
@@ -827,8 +829,8 @@ __device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uin
   sink.row = row;
   const int py = ty0 + row;
   for (uint32_t e = lane; e < er.y; e += 32) {
-    NormEdge ne = load_edge(edges, er.x + e);
-    if (tile_edge_class(ne, tx0, ty0, tile_h) == kEdgeStraddle && py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8))
+    NormEdge ne = load_edge(edges, elist ? __ldg(elist + e) : er.x + e);
+    if (py >= (ne.y0 >> 8) && py <= ((ne.y1 - 1) >> 8) && tile_edge_class(ne, tx0, ty0, tile_h) == kEdgeStraddle)
       tile_rasterize_edge_row(ne, py, sink);
   }
   __syncwarp();
@@ -844,6 +846,23 @@ __device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uin
   *reinterpret_cast<uint4*>(cells_row + lane * 4) = make_uint4(c.x + add, c.y + add, c.z + add, c.w + add);
   asm volatile("bar.sync %0, 128;" :: "r"(group + 1) : "memory");
 }
+
+#ifdef B2D_PHASE_TIMING
+// Experiment build only (make EXTRA=-DB2D_PHASE_TIMING): cycles the warps of k_tile_render spend in / wait for each phase.
+//   [0] phase-1 busy (sum over warps)  [1] wait at the barrier behind phase 1  [2] phase-2 busy  [3] cull + wait before phase 1
+//   [4] phase-1 length seen by warp 0 (barrier to barrier)  [5] sub-chunks  [6] commands replayed (per CTA)  [7] longest phase-1 command (sum over sub-chunks)
+__device__ unsigned long long g_phase_cycles[8];
+extern "C" __attribute__((visibility("default"))) int b2dgpu_debug_phase_cycles(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+  return 0;
+}
+__device__ __forceinline__ long long pt_now() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+#define PT(x) x
+#else
+#define PT(x)
+#endif
 
 template<int BPP, int TH>
 __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) {
@@ -894,6 +913,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   }
   bool dirty = false;
   uint32_t px_written = 0;
+  PT(long long pt_busy1 = 0; long long pt_wait1 = 0; long long pt_busy2 = 0; long long pt_wait2 = 0; long long pt_len1 = 0; long long pt_sub = 0; long long pt_cmds = 0; long long pt_maxcmd = 0; long long pt_last = pt_now(); __shared__ unsigned long long s_pt_max;)
   const bool count_pixels = P.pixel_counter != nullptr;
 
   // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
@@ -943,10 +963,12 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       ring_head += sub_n;
       if (tid == 0) { s_next = TH; s_pool_next = 0; } // commands beyond the first TH are handed out dynamically
       __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
+      PT(const long long pt_a = pt_now(); pt_wait2 += pt_a - pt_last; pt_sub++; pt_cmds += sub_n; if (tid == 0) s_pt_max = 0;)
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
       for (uint32_t k = warp; k < sub_n; ) {
+        PT(const long long pt_c0 = pt_now();)
         const uint32_t cell = s_list[(sub + k) & (kRing - 1)];
         const uint32_t ci = binned ? __ldg(P.cell_cmd + cell) : cell;
         PreCmd* pre = &s_pre[k];
@@ -1100,12 +1122,15 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           if (lane == 0) { pre->warp_mask = wm; s_wmask[k] = wm; }
           if (lane < TH) reinterpret_cast<uint8_t*>(pre->wrec4)[lane] = uint8_t(uniform_mask);
         }
+        PT(if (lane == 0) atomicMax(&s_pt_max, (unsigned long long)(pt_now() - pt_c0));)
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
         uint32_t nk = 0;
         if (lane == 0) nk = atomicAdd(&s_next, 1u);
         k = __shfl_sync(0xFFFFFFFFu, nk, 0);
       }
+      PT(const long long pt_b = pt_now();)
       __syncthreads();
+      PT(const long long pt_c = pt_now(); pt_busy1 += pt_b - pt_a; pt_wait1 += pt_c - pt_b; pt_len1 += pt_c - pt_a; pt_maxcmd += (long long)s_pt_max;)
 
       // ---- phase 2 (K3): every warp replays, in order, the commands that concern ITS block; warps never wait for each
       //      other (except the four warps of a row group inside the slow path) ----
@@ -1196,9 +1221,16 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           else {
             // Slow path: the group's four warps rasterize one row each, then read their blocks of all four rows.
             const int my_row = grp * kBlockRows + blk;
+            // The edges to rasterize: the band's list of the command (k_bin_edges) or, without lists, all its edges.
             const uint32_t ring_entry = s_list[(sub + k) & (kRing - 1)];
-            slow_group_rows(edges, P.cmd_edges[binned ? __ldg(P.cell_cmd + ring_entry) : ring_entry], tx0, ty0, my_row, lane, &s_cells[my_row][0], &s_carry[my_row],
-                            (256u << 9) + pre.carry_left[my_row], TH, grp);
+            uint2 er = P.cmd_edges[binned ? __ldg(P.cell_cmd + ring_entry) : ring_entry];
+            const uint32_t* elist = nullptr;
+            if (edge_lists) {
+              const uint32_t o0 = __ldg(P.cell_edge_off + ring_entry);
+              elist = P.band_edges + o0;
+              er.y = __ldg(P.cell_edge_off + ring_entry + 1) - o0;
+            }
+            slow_group_rows(edges, er, elist, tx0, ty0, my_row, lane, &s_cells[my_row][0], &s_carry[my_row], (256u << 9) + pre.carry_left[my_row], TH, grp);
             const uint4 c = *reinterpret_cast<const uint4*>(&s_cells[row][blk * kBlockW + (lane & 7) * 4]);
             asm volatile("bar.sync %0, 128;" :: "r"(grp + 1) : "memory");      // the cells may be overwritten after this
             m[0] = calc_mask(c.x, rule, alpha); m[1] = calc_mask(c.y, rule, alpha);
@@ -1238,8 +1270,13 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
         if (count_pixels) px_written += (m[0] != 0) + (m[1] != 0) + (m[2] != 0) + (m[3] != 0);
       }
       }
+      PT(pt_last = pt_now(); pt_busy2 += pt_last - pt_c;)
     }
   }
+  PT(if (lane == 0) { atomicAdd(&g_phase_cycles[0], (unsigned long long)pt_busy1); atomicAdd(&g_phase_cycles[1], (unsigned long long)pt_wait1);
+                      atomicAdd(&g_phase_cycles[2], (unsigned long long)pt_busy2); atomicAdd(&g_phase_cycles[3], (unsigned long long)pt_wait2);
+                      if (warp == 0) { atomicAdd(&g_phase_cycles[4], (unsigned long long)pt_len1); atomicAdd(&g_phase_cycles[5], (unsigned long long)pt_sub);
+                                       atomicAdd(&g_phase_cycles[6], (unsigned long long)pt_cmds); atomicAdd(&g_phase_cycles[7], (unsigned long long)pt_maxcmd); } })
 
   if (dirty) {
     if (BPP == 4) *reinterpret_cast<uint4*>(dst_row + size_t(px) * 4) = make_uint4(d[0], d[1], d[2], d[3]);

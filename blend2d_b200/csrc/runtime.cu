@@ -117,7 +117,9 @@ struct b2dgpu_runtime {
   cudaEvent_t glyph_cache_ready;            // recorded behind the last upload into the mirror
   DevBuffer bins;                           // per-band command lists (k_bin_*), rebuilt by every render
   uint32_t bin_capacity;                    // cells the lists can hold; grown when a render reports that it needed more
-  uint32_t* h_bin_state;                    // pinned: [0] cells the last render needed, [1] whether its lists were built
+  uint32_t* h_bin_state;                    // pinned: [0] cells the last render needed, [1] whether its lists were built,
+                                            // [2] whether its per-cell edge lists were built, [3] (edge, band) pairs it needed
+  size_t edge_pair_capacity;                // grown when a render reports that its edge lists did not fit
   PinnedBuffer image_staging;
 
   b2dgpu_stats stats;
@@ -312,7 +314,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
   rt->slot_done[0] = rt->slot_done[1] = nullptr; rt->slot_busy[0] = rt->slot_busy[1] = false;
   rt->d_bayer = nullptr; rt->d_pixel_counter = nullptr; rt->d_scalars = nullptr; rt->h_scalars = nullptr;
   rt->staging_next = 0;
-  rt->bin_capacity = 0; rt->h_bin_state = nullptr;
+  rt->bin_capacity = 0; rt->h_bin_state = nullptr; rt->edge_pair_capacity = 0;
   rt->glyph_cache_words = 0; rt->glyph_cache_id = 0; rt->glyph_cache_ready = nullptr;
   rt->profiling = false;
   rt->count_pixels = true;
@@ -340,7 +342,7 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
     b2dgpu_runtime_destroy(rt);
     return cuda_fail(e, "b2dgpu_runtime_create: device allocation");
   }
-  rt->h_bin_state[0] = 0; rt->h_bin_state[1] = 1;
+  rt->h_bin_state[0] = 0; rt->h_bin_state[1] = 1; rt->h_bin_state[2] = 1; rt->h_bin_state[3] = 0;
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
   cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
@@ -1145,7 +1147,10 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     const size_t o_cell_ext = take(sizeof(uint2) * size_t(cap));
     // per-cell edge lists: (edge, band) pairs; an edge of a flattened curve rarely spans more than two bands
     const bool with_edge_lists = total_edges != 0;
+    if (rt->h_bin_state[1] != 0u && rt->h_bin_state[2] == 0u && rt->h_bin_state[3] > rt->edge_pair_capacity)
+      rt->edge_pair_capacity = size_t(rt->h_bin_state[3]) + rt->h_bin_state[3] / 4u;      // reported by an earlier render
     size_t pair_cap = with_edge_lists ? total_edges * 3 + (size_t(1) << 16) : 0;
+    if (with_edge_lists && pair_cap < rt->edge_pair_capacity) pair_cap = rt->edge_pair_capacity;
     if (pair_cap > 0xFFFFFF00u) pair_cap = 0xFFFFFF00u;
     if (const char* e = getenv("B2DGPU_EDGE_LIST_CAPACITY")) if (with_edge_lists) pair_cap = size_t(strtoull(e, nullptr, 10));   // test knob
     const size_t o_cell_edge_cnt = take(with_edge_lists ? sizeof(uint32_t) * size_t(cap) : 0);
@@ -1176,7 +1181,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
     Bn.band_edges = with_edge_lists ? reinterpret_cast<uint32_t*>(bp + o_band_edges) : nullptr;
     Bn.edge_list_capacity = uint32_t(pair_cap);
     launches += launch_binning(Bn, s);
-    CU_TRY(cudaMemcpyAsync(rt->h_bin_state, Bn.state, 8, cudaMemcpyDeviceToHost, s));    // read by a LATER render, never waited for
+    CU_TRY(cudaMemcpyAsync(rt->h_bin_state, Bn.state, 16, cudaMemcpyDeviceToHost, s));    // read by a LATER render, never waited for
     if (getenv("B2DGPU_DEBUG_BINS")) {
       uint32_t st[4] = {0, 0, 0, 0};
       cudaStreamSynchronize(s);
