@@ -6,6 +6,7 @@
 // contains the host instantiation.
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #  define B2D_HD __host__ __device__ __forceinline__

@@ -144,7 +144,8 @@ B2D_HD uint32_t comp_screen(uint32_t d, uint32_t s, uint32_t m) {
 enum CompOpId : uint32_t {
   kOpSrcOver = 0, kOpSrcCopy = 1, kOpSrcIn = 2, kOpSrcOut = 3, kOpSrcAtop = 4, kOpDstOver = 5, kOpDstCopy = 6, kOpDstIn = 7,
   kOpDstOut = 8, kOpDstAtop = 9, kOpXor = 10, kOpClear = 11, kOpPlus = 12, kOpMinus = 13, kOpModulate = 14, kOpMultiply = 15,
-  kOpScreen = 16, kOpDarken = 18, kOpLighten = 19, kOpLinearBurn = 22, kOpDifference = 27, kOpExclusion = 28
+  kOpScreen = 16, kOpOverlay = 17, kOpDarken = 18, kOpLighten = 19, kOpColorDodge = 20, kOpColorBurn = 21, kOpLinearBurn = 22,
+  kOpLinearLight = 23, kOpPinLight = 24, kOpHardLight = 25, kOpSoftLight = 26, kOpDifference = 27, kOpExclusion = 28
 };
 
 B2D_HD uint32_t w16(uint32_t v) { return v & 0xFFFFu; }
@@ -238,6 +239,164 @@ B2D_HD uint32_t comp_jit_ext(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
   return out;
 }
 
+// Overlay, HardLight, PinLight, LinearLight (16-bit integer lanes) and ColorDodge, ColorBurn, SoftLight (the JIT's
+// one-pixel float variants), masked forms with Da and Sa used (jit/compoppart.cpp:4466-4540, 5091-5147, 4954-5001,
+// 4889-4935, 4724-4778, 4784-4841, 5152-5247).  Per channel; `sa` / `da` are the alphas of S.m and D, a value written
+// `-x` is the 16-bit two's complement the JIT's psubw produces, comparisons are the signed pcmpgtw / pminsw.
+// Float steps are single IEEE operations in the JIT's order (mulps, divps, sqrtps, no contraction; v_madd_f32 is
+// mul + add on the baseline target), conversions are cvttps2dq / cvtps2dq.  Unpinned (no JIT in the reference build here).
+B2D_HD int32_t s16(uint32_t v) { return int32_t(int16_t(uint16_t(v))); }
+B2D_HD float f_mul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+B2D_HD float f_add(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+B2D_HD float f_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+B2D_HD float f_sqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+B2D_HD float f_max_ps(float a, float b) { return a > b ? a : b; }               // maxps / minps: the second operand unless the test holds
+B2D_HD float f_min_ps(float a, float b) { return a < b ? a : b; }
+B2D_HD int f_trunc_i32(float v) {                                                // cvttps2dq
+#if defined(__CUDA_ARCH__)
+  return (v >= 2147483648.0f || v != v) ? int(0x80000000u) : __float2int_rz(v);
+#else
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return int(0x80000000u);
+  return int(v);
+#endif
+}
+B2D_HD int f_round_i32(float v) {                                                // cvtps2dq (round to nearest even)
+#if defined(__CUDA_ARCH__)
+  return (v >= 2147483648.0f || v != v) ? int(0x80000000u) : __float2int_rn(v);
+#else
+  if (!(v >= -2147483648.0f && v < 2147483648.0f)) return int(0x80000000u);
+  return int(lrintf(v));
+#endif
+}
+B2D_HD uint32_t packus_dw(int v) { return uint32_t(v < 0 ? 0 : v > 65535 ? 65535 : v); }   // packusdw
+
+B2D_HD uint32_t comp_jit_light(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
+  const uint32_t da = d >> 24;
+  const uint32_t sa = jit_div255_u16(w16((s >> 24) * m));
+  const uint32_t sada = jit_div255_u16(w16(sa * da));
+  uint32_t out = 0;
+
+  if (op == kOpSoftLight) {
+    // Dca' = Dca + Sca.(1 - Da) + (2.Sca - Sa).Da.F(Dc), Dc = Dca / max(Da, 0.001), everything in 0..1 floats;
+    // F = Dc.(1 - Dc) for 2.Sca <= Sa, else 4.Dc.(4.Dc.Dc + Dc - 4.Dc + 1) - Dc for 4.Dc <= 1, else sqrt(Dc) - Dc.
+    const float k = 1.0f / 255.0f;
+    const float fsa = f_mul(float(int(sa)), k), fda = f_mul(float(int(da)), k);
+    const float b0 = f_max_ps(fda, 1e-3f);
+    #pragma unroll
+    for (int sh = 0; sh < 32; sh += 8) {
+      const float sc = f_mul(float(int(jit_div255_u16(w16(((s >> sh) & 0xFFu) * m)))), k);
+      const float dc = f_mul(float(int((d >> sh) & 0xFFu)), k);
+      const float a0 = f_div(dc, b0);
+      float r = f_add(f_add(dc, sc), -f_mul(sc, fda));                          // Dca + Sca - Sca.Da
+      if (sh != 24) {
+        const float t = f_mul(f_add(f_add(sc, sc), -fsa), b0);                   // (2.Sca - Sa).Da
+        const float q = f_mul(a0, 4.0f);
+        const float poly = f_mul(f_add(f_add(f_add(f_mul(q, a0), a0), -q), 1.0f), q);
+        const float hi = q <= 1.0f ? poly : f_sqrt(a0);
+        const float f = 0.0f < t ? f_add(hi, -a0) : f_mul(f_add(1.0f, -a0), a0);
+        r = f_add(r, f_mul(t, f));
+      }
+      else r = f_add(r, f_mul(0.0f, 0.0f));                                     // the alpha lane of (2.Sca - Sa).Da is masked to +0
+      int v = f_round_i32(f_mul(r, 255.0f));
+      v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;                           // packssdw, then packuswb
+      out |= uint32_t(v < 0 ? 0 : v > 255 ? 255 : v) << sh;
+    }
+    return out;
+  }
+
+  if (op == kOpColorDodge || op == kOpColorBurn) {
+    // Dodge: Dca' = min(Dca.Sa.Sa / max(Sa - Sca, 0.001), Sa.Da) + Sca.(1 - Da) + Dca.(1 - Sa)
+    // Burn:  Dca' = Sa.Da - min(Sa.Da, (Da - Dca).Sa.Sa / max(Sca, 0.001)) + Sca.(1 - Da) + Dca.(1 - Sa)
+    // in 0..255 units: the float term is truncated and added to the 16-bit sum before the division by 255.
+    const float fsa = float(int(sa)), fda = float(int(da));
+    const float dasa = f_mul(fda, fsa);
+    float lim;                                                                   // the alpha lane of the float term
+    if (op == kOpColorDodge) lim = f_mul(f_div(dasa, f_max_ps(fsa, 1e-3f)), fsa);
+    else { const float ya = f_max_ps(fsa, 1e-3f); lim = f_mul(f_div(dasa, ya), ya); }
+    #pragma unroll
+    for (int sh = 0; sh < 32; sh += 8) {
+      const uint32_t dc = (d >> sh) & 0xFFu, sc = jit_div255_u16(w16(((s >> sh) & 0xFFu) * m));
+      const float fd = float(int(dc)), fs = float(int(sc));
+      float term;
+      if (op == kOpColorDodge) {
+        const float den = f_max_ps(sh == 24 ? fsa : f_add(-fs, fsa), 1e-3f);
+        term = f_min_ps(f_mul(f_div(f_mul(fd, fsa), den), fsa), lim);
+      }
+      else {
+        const float num = sh == 24 ? dasa : f_add(-f_mul(fd, fsa), dasa);
+        const float z = f_min_ps(f_mul(f_div(num, f_max_ps(fs, 1e-3f)), f_max_ps(fsa, 1e-3f)), lim);
+        term = f_add(lim, -(sh == 24 ? 0.0f : z));
+      }
+      const uint32_t ip = w16(w16(dc * (255u - sa)) + w16(sc * (255u - da)));
+      out |= packus_i16(jit_div255_u16(w16(ip + packus_dw(f_trunc_i32(term))))) << sh;
+    }
+    return out;
+  }
+
+  #pragma unroll
+  for (int sh = 0; sh < 32; sh += 8) {
+    const bool is_alpha = sh == 24;
+    const uint32_t dc = (d >> sh) & 0xFFu, sc = jit_div255_u16(w16(((s >> sh) & 0xFFu) * m));
+    uint32_t v;
+    switch (op) {
+      case kOpOverlay:
+      case kOpHardLight: {
+        // X = Dca.Sa + Sca.Da - 2.Sca.Dca; Overlay tests 2.Dca < Da, HardLight 2.Sca < Sa:
+        //   true:  Dca' = Dca + Sca - X          false: Dca' = Dca + Sca + X - Sa.Da          Da' = Da + Sa - Sa.Da
+        uint32_t x = w16(w16(w16(sc * da) - w16(dc * sc)) + w16(sa * dc));
+        x = jit_div255_u16(is_alpha ? (op == kOpOverlay ? w16(sa * da) : 0u) : w16(x - w16(dc * sc)));
+        const bool lt = is_alpha ? op == kOpOverlay : (op == kOpOverlay ? s16(da) > s16(w16(dc << 1)) : s16(sa) > s16(w16(sc << 1)));
+        const uint32_t y = (lt && !(is_alpha && op == kOpHardLight)) ? 0u : sada;
+        v = w16(w16(w16(dc + sc) + (lt ? w16(0u - x) : x)) - (is_alpha && op == kOpOverlay ? 0u : y));
+        break;
+      }
+      case kOpPinLight: {
+        // 2.Sca <= Sa: min(Dca + Sca - Sca.Da, Dca + Sca + Sca.Da - Dca.Sa); else max(.., .. - Da.Sa)
+        const uint32_t y = jit_div255_u16(w16(sa * dc)), x = jit_div255_u16(w16(da * sc)), sum = w16(dc + sc);
+        const uint32_t a = w16(sum - x);
+        uint32_t b = w16(x - w16(y - sum));
+        const bool gt = s16(w16(sc << 1)) > s16(sa);
+        if (gt) b = w16(b - sada);
+        v = gt ? (s16(a) > s16(b) ? a : b) : (s16(a) < s16(b) ? a : b);
+        break;
+      }
+      default: {              // kOpLinearLight: Dca' = min(max(Dca.Sa + 2.Sca.Da - Sa.Da, 0), Sa.Da) + Sca.(1 - Da) + Dca.(1 - Sa)
+        uint32_t t = w16(jit_div255_u16(w16(dc * sa)) + 2u * jit_div255_u16(w16(sc * da)));
+        t = subs_u16(t, sada);
+        t = s16(t) < s16(sada) ? t : sada;
+        v = w16(t + jit_div255_u16(w16(w16(dc * (255u - sa)) + w16(sc * (255u - da)))));
+        break;
+      }
+    }
+    out |= packus_i16(v) << sh;
+  }
+  return out;
+}
+
 B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) {
   switch (comp_op) {
     case kOpSrcOver:  return comp_src_over(d, s, m);
@@ -245,6 +404,8 @@ B2D_HD uint32_t composite(uint32_t comp_op, uint32_t d, uint32_t s, uint32_t m) 
     case kOpPlus:     return comp_plus(d, s, m);
     case kOpMultiply: return comp_multiply(d, s, m);
     case kOpScreen:   return comp_screen(d, s, m);
+    case kOpOverlay: case kOpColorDodge: case kOpColorBurn: case kOpLinearLight: case kOpPinLight: case kOpHardLight: case kOpSoftLight:
+                      return comp_jit_light(comp_op, d, s, m);
     default:          return comp_jit_ext(comp_op, d, s, m);
   }
 }
@@ -255,6 +416,8 @@ B2D_HD_COLD uint32_t composite_cold(uint32_t comp_op, uint32_t d, uint32_t s, ui
     case kOpPlus:     return comp_plus(d, s, m);
     case kOpMultiply: return comp_multiply(d, s, m);
     case kOpScreen:   return comp_screen(d, s, m);
+    case kOpOverlay: case kOpColorDodge: case kOpColorBurn: case kOpLinearLight: case kOpPinLight: case kOpHardLight: case kOpSoftLight:
+                      return comp_jit_light(comp_op, d, s, m);
     default:          return comp_jit_ext(comp_op, d, s, m);
   }
 }

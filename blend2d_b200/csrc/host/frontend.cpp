@@ -148,7 +148,8 @@ inline uint32_t format_from_rgba32(uint32_t rgba32) {                          /
 enum SolidId : uint32_t { kSolidNone = 0, kSolidTransparent = 1, kSolidOpaqueBlack = 2, kSolidOpaqueWhite = 3, kSolidNop = 4 };
 enum : uint32_t { kOpSrcOver = 0, kOpSrcCopy = 1, kOpSrcIn = 2, kOpSrcOut = 3, kOpSrcAtop = 4, kOpDstOver = 5, kOpDstCopy = 6, kOpDstIn = 7,
                   kOpDstOut = 8, kOpDstAtop = 9, kOpXor = 10, kOpClear = 11, kOpPlus = 12, kOpMinus = 13, kOpModulate = 14, kOpMultiply = 15,
-                  kOpScreen = 16, kOpDarken = 18, kOpLighten = 19, kOpLinearBurn = 22, kOpDifference = 27, kOpExclusion = 28 };
+                  kOpScreen = 16, kOpOverlay = 17, kOpDarken = 18, kOpLighten = 19, kOpColorDodge = 20, kOpColorBurn = 21, kOpLinearBurn = 22,
+                  kOpLinearLight = 23, kOpPinLight = 24, kOpHardLight = 25, kOpSoftLight = 26, kOpDifference = 27, kOpExclusion = 28 };
 
 struct Simplified { uint32_t op, dst, src, solid; bool implemented; };
 
@@ -232,6 +233,7 @@ Simplified simplify(uint32_t op, uint32_t d, uint32_t s) {
     // that through the real frontend (shim/).
     case kOpSrcIn: case kOpSrcOut: case kOpSrcAtop: case kOpDstOver: case kOpDstIn: case kOpDstOut: case kOpDstAtop: case kOpXor:
     case kOpMinus: case kOpModulate: case kOpDarken: case kOpLighten: case kOpLinearBurn: case kOpDifference: case kOpExclusion:
+    case kOpOverlay: case kOpColorDodge: case kOpColorBurn: case kOpLinearLight: case kOpPinLight: case kOpHardLight: case kOpSoftLight:
       return d == P && s == P ? mk_op(op, d, s) : mk_unimpl(op, d, s);
     default: return mk_unimpl(op, d, s);
   }

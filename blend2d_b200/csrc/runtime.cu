@@ -226,15 +226,11 @@ static bool signature_supported(uint32_t sig) {
         dst == B2DGPU_FORMAT_FRGB32 || dst == B2DGPU_FORMAT_ZERO32)) return false;
   const bool base_op = op == B2DGPU_COMP_OP_SRC_OVER || op == B2DGPU_COMP_OP_SRC_COPY || op == B2DGPU_COMP_OP_PLUS ||
                        op == B2DGPU_COMP_OP_MULTIPLY || op == B2DGPU_COMP_OP_SCREEN;
-  // The rest of the Porter-Duff set and the separable operators that need no division (dev_pixel.cuh comp_jit_ext):
-  // only on a PRGB32 destination - the JIT has separate code for A8 and for destinations without alpha.  Overlay, the
-  // dodge / burn / light family stay unimplemented; Clear and DstCopy never arrive (the frontend simplifies them,
-  // core/compopsimplifyimpl_p.h).
-  const bool ext_op = dst == B2DGPU_FORMAT_PRGB32 &&
-      (op == B2DGPU_COMP_OP_SRC_IN || op == B2DGPU_COMP_OP_SRC_OUT || op == B2DGPU_COMP_OP_SRC_ATOP || op == B2DGPU_COMP_OP_DST_OVER ||
-       op == B2DGPU_COMP_OP_DST_IN || op == B2DGPU_COMP_OP_DST_OUT || op == B2DGPU_COMP_OP_DST_ATOP || op == B2DGPU_COMP_OP_XOR ||
-       op == B2DGPU_COMP_OP_MINUS || op == B2DGPU_COMP_OP_MODULATE || op == B2DGPU_COMP_OP_DARKEN || op == B2DGPU_COMP_OP_LIGHTEN ||
-       op == B2DGPU_COMP_OP_LINEAR_BURN || op == B2DGPU_COMP_OP_DIFFERENCE || op == B2DGPU_COMP_OP_EXCLUSION);
+  // The rest of BLCompOp (dev_pixel.cuh comp_jit_ext / comp_jit_light): only on a PRGB32 destination - the JIT has
+  // separate code for A8 and for destinations without alpha.  Clear and DstCopy never arrive (the frontend simplifies
+  // them, core/compopsimplifyimpl_p.h).
+  const bool ext_op = dst == B2DGPU_FORMAT_PRGB32 && op >= B2DGPU_COMP_OP_SRC_IN && op <= B2DGPU_COMP_OP_EXCLUSION &&
+                      op != B2DGPU_COMP_OP_DST_COPY && op != B2DGPU_COMP_OP_CLEAR;
   if (!base_op && !ext_op) return false;
   if (fill < B2DGPU_FILL_BOX_A || fill > B2DGPU_FILL_ANALYTIC) return false;
   if (fetch > B2DGPU_FETCH_GRADIENT_CONIC_DITHER) return false;

@@ -31,6 +31,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define ORC_API __attribute__((visibility("default")))
 
@@ -126,7 +127,8 @@ static v4 v_minmax_u8(v4 a, v4 b, int take_min) {
 static uint32_t v_packus(v4 a) { uint32_t p = 0; for (int i = 0; i < 4; i++) p |= jit_packus(a.l[i]) << (8 * i); return p; }
 
 enum { ORC_SRC_IN = 2, ORC_SRC_OUT = 3, ORC_SRC_ATOP = 4, ORC_DST_OVER = 5, ORC_DST_IN = 7, ORC_DST_OUT = 8, ORC_DST_ATOP = 9, ORC_XOR = 10,
-       ORC_MINUS = 13, ORC_MODULATE = 14, ORC_DARKEN = 18, ORC_LIGHTEN = 19, ORC_LINEAR_BURN = 22, ORC_DIFFERENCE = 27, ORC_EXCLUSION = 28 };
+       ORC_MINUS = 13, ORC_MODULATE = 14, ORC_OVERLAY = 17, ORC_DARKEN = 18, ORC_LIGHTEN = 19, ORC_COLOR_DODGE = 20, ORC_COLOR_BURN = 21,
+       ORC_LINEAR_BURN = 22, ORC_LINEAR_LIGHT = 23, ORC_PIN_LIGHT = 24, ORC_HARD_LIGHT = 25, ORC_SOFT_LIGHT = 26, ORC_DIFFERENCE = 27, ORC_EXCLUSION = 28 };
 
 static uint32_t orc_jit_ext(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
   v4 sv = v_load(s), dv = v_load(d), vm = v_set1(m), vn = v_inv255(vm), xv, yv, uv;
@@ -208,6 +210,145 @@ static uint32_t orc_jit_ext(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
   }
 }
 
+/* More of the JIT's vector vocabulary, for Overlay / HardLight / PinLight / LinearLight (16-bit integer lanes) and the
+ * scalar-float operators ColorDodge / ColorBurn / SoftLight (one pixel per iteration: four 32-bit float lanes b, g, r, a). */
+static v4 v_slli1(v4 a) { for (int i = 0; i < 4; i++) a.l[i] = (a.l[i] << 1) & 0xFFFFu; return a; }
+static v4 v_cmpgt_i16(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = (int16_t)a.l[i] > (int16_t)b.l[i] ? 0xFFFFu : 0u; return a; }   /* pcmpgtw */
+static v4 v_xor(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] ^= b.l[i]; return a; }
+static v4 v_and(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] &= b.l[i]; return a; }
+static v4 v_bic(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] &= ~b.l[i] & 0xFFFFu; return a; }                                       /* a & ~b */
+static v4 v_fill_alpha(v4 a) { a.l[3] = 0xFFFFu; return a; }                                                                              /* por p_FFFF000000000000 */
+static v4 v_min_i16(v4 a, v4 b) { for (int i = 0; i < 4; i++) a.l[i] = (int16_t)a.l[i] < (int16_t)b.l[i] ? a.l[i] : b.l[i]; return a; } /* pminsw */
+
+typedef struct { float l[4]; } f4;
+static f4 f_from(v4 a) { f4 r; for (int i = 0; i < 4; i++) r.l[i] = (float)(int32_t)a.l[i]; return r; }                                  /* cvtdq2ps */
+static f4 f_set1(float x) { f4 r; for (int i = 0; i < 4; i++) r.l[i] = x; return r; }
+static f4 f_alpha(f4 a) { return f_set1(a.l[3]); }                                                                                        /* vExpandAlphaPS */
+static f4 f_mul(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] * b.l[i]; return a; }
+static f4 f_add(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] + b.l[i]; return a; }
+static f4 f_sub(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] - b.l[i]; return a; }
+static f4 f_div(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] / b.l[i]; return a; }
+static f4 f_sqrt(f4 a) { for (int i = 0; i < 4; i++) a.l[i] = sqrtf(a.l[i]); return a; }
+static f4 f_max(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] > b.l[i] ? a.l[i] : b.l[i]; return a; }                        /* maxps: the second operand unless a > b */
+static f4 f_min(f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = a.l[i] < b.l[i] ? a.l[i] : b.l[i]; return a; }                        /* minps */
+static f4 f_neg(f4 a) { for (int i = 0; i < 4; i++) a.l[i] = -a.l[i]; return a; }                                                        /* xorps sign bit */
+static f4 f_zero_alpha(f4 a) { a.l[3] = 0.0f; return a; }                                                                                 /* andps p_FFFFFFFF_FFFFFFFF_FFFFFFFF_0 */
+static f4 f_sel(const int* mask, f4 a, f4 b) { for (int i = 0; i < 4; i++) a.l[i] = mask[i] ? a.l[i] : b.l[i]; return a; }                /* andps / andnps / orps */
+static int32_t cvtt_f32(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? (int32_t)v : INT32_MIN; }                          /* cvttps2dq */
+static int32_t cvt_f32(float v) { return (v >= -2147483648.0f && v < 2147483648.0f) ? (int32_t)lrintf(v) : INT32_MIN; }                   /* cvtps2dq, round to nearest even */
+static v4 f_trunc_pack_u16(f4 a) {                                                                                                         /* cvttps2dq + packusdw */
+  v4 r;
+  for (int i = 0; i < 4; i++) { int32_t x = cvtt_f32(a.l[i]); r.l[i] = x < 0 ? 0u : x > 65535 ? 65535u : (uint32_t)x; }
+  return r;
+}
+
+/* ColorDodge / ColorBurn share their integer half: Dca.(1 - Sa) + Sca.(1 - Da) on the packed [Dca | Sca] register
+ * (compoppart.cpp:4760-4766, 4819-4825). */
+static v4 dodge_burn_int_part(v4 dv, v4 sv) {
+  v4 isa = v_inv255(v_alpha(sv)), ida = v_inv255(v_alpha(dv));
+  return v_add(v_mul(dv, isa), v_mul(sv, ida));
+}
+
+static uint32_t orc_jit_light(uint32_t op, uint32_t d, uint32_t s, uint32_t m) {
+  v4 sv = v_load(s), dv = v_load(d), vm = v_set1(m), xv, yv, zv;
+  sv = v_mul(sv, vm); sv = v_d255(sv);                                               /* has_mask: S = S.m */
+  switch (op) {
+    case ORC_OVERLAY:                                                                /* compoppart.cpp:4466-4540 (use_sa, use_da) */
+      xv = v_alpha(dv); yv = v_alpha(sv);
+      xv = v_mul(xv, sv); yv = v_mul(yv, dv); zv = v_mul(dv, sv);
+      sv = v_add(sv, dv); xv = v_sub(xv, zv); zv = v_zero_alpha(zv); xv = v_add(xv, yv);
+      yv = v_alpha(dv); xv = v_sub(xv, zv);
+      dv = v_slli1(dv); yv = v_cmpgt_i16(yv, dv); xv = v_d255(xv); yv = v_fill_alpha(yv);
+      zv = v_alpha(xv);
+      xv = v_xor(xv, yv); xv = v_sub(xv, yv);
+      yv = v_bic(zv, yv);
+      sv = v_add(sv, xv); sv = v_sub(sv, yv);
+      return v_packus(sv);
+    case ORC_HARD_LIGHT:                                                             /* :5091-5147 */
+      xv = v_alpha(dv); yv = v_alpha(sv);
+      xv = v_mul(xv, sv); yv = v_mul(yv, dv); zv = v_mul(dv, sv);
+      dv = v_add(dv, sv); xv = v_sub(xv, zv); xv = v_add(xv, yv); xv = v_sub(xv, zv);
+      yv = v_alpha(yv); zv = v_alpha(sv); xv = v_d255(xv); yv = v_d255(yv);
+      sv = v_slli1(sv); zv = v_cmpgt_i16(zv, sv);
+      xv = v_xor(xv, zv); xv = v_sub(xv, zv); zv = v_zero_alpha(zv); zv = v_bic(yv, zv);
+      dv = v_add(dv, xv); dv = v_sub(dv, zv);
+      return v_packus(dv);
+    case ORC_PIN_LIGHT:                                                              /* :4954-5001 (use_sa && use_da) */
+      yv = v_alpha(sv); xv = v_alpha(dv);
+      yv = v_mul(yv, dv); xv = v_mul(xv, sv); dv = v_add(dv, sv); yv = v_d255(yv); xv = v_d255(xv);
+      yv = v_sub(yv, dv); dv = v_sub(dv, xv); xv = v_sub(xv, yv);
+      yv = v_alpha(sv); sv = v_slli1(sv); sv = v_cmpgt_i16(sv, yv);
+      zv = v_sub(dv, xv); zv = v_alpha(zv); zv = v_and(zv, sv); xv = v_add(xv, zv);
+      dv = v_xor(dv, sv); xv = v_xor(xv, sv); dv = v_min_i16(dv, xv); dv = v_xor(dv, sv);
+      return v_packus(dv);
+    case ORC_LINEAR_LIGHT: {                                                         /* :4889-4935: [Dca | Sca] in one register */
+      v4 d_lo = dv, d_hi = sv, x_lo = v_alpha(sv), x_hi = v_alpha(dv), s_lo, s_hi, y_lo, t;
+      s_lo = d_lo; s_hi = d_hi;
+      d_lo = v_mul(d_lo, x_lo); d_hi = v_mul(d_hi, x_hi);                            /* [Dca.Sa | Sca.Da] */
+      x_lo = v_inv255(x_lo); x_hi = v_inv255(x_hi);
+      d_lo = v_d255(d_lo); d_hi = v_d255(d_hi);
+      s_lo = v_mul(s_lo, x_lo); s_hi = v_mul(s_hi, x_hi);                            /* [Dca.(1 - Sa) | Sca.(1 - Da)] */
+      t = s_hi; y_lo = d_hi;                                                         /* the swapped halves (low part is all that is kept) */
+      s_lo = v_add(s_lo, t);
+      d_lo = v_add(d_lo, y_lo);
+      xv = v_alpha(y_lo);                                                            /* Sa.Da */
+      d_lo = v_add(d_lo, y_lo);
+      s_lo = v_d255(s_lo);
+      d_lo = v_subs(d_lo, xv); d_lo = v_min_i16(d_lo, xv);
+      d_lo = v_add(d_lo, s_lo);
+      return v_packus(d_lo);
+    }
+    case ORC_COLOR_DODGE: {                                                          /* :4724-4778 */
+      f4 y0 = f_from(sv), z0 = f_from(dv), x0;
+      x0 = f_alpha(y0); y0 = f_neg(y0); z0 = f_mul(z0, x0); y0 = f_zero_alpha(y0); y0 = f_add(y0, x0);
+      y0 = f_max(y0, f_set1(1e-3f)); z0 = f_div(z0, y0);
+      xv = dodge_burn_int_part(dv, sv);
+      z0 = f_mul(z0, x0); x0 = f_alpha(z0); z0 = f_min(z0, x0);
+      xv = v_add(xv, f_trunc_pack_u16(z0)); xv = v_d255(xv);
+      return v_packus(xv);
+    }
+    case ORC_COLOR_BURN: {                                                           /* :4784-4841 */
+      f4 y0 = f_from(sv), z0 = f_from(dv), x0;
+      x0 = f_alpha(y0); y0 = f_max(y0, f_set1(1e-3f)); z0 = f_mul(z0, x0);
+      x0 = f_alpha(z0); z0 = f_neg(z0); z0 = f_zero_alpha(z0); z0 = f_add(z0, x0); z0 = f_div(z0, y0);
+      xv = dodge_burn_int_part(dv, sv);
+      x0 = f_alpha(y0); z0 = f_mul(z0, x0); x0 = f_alpha(z0); z0 = f_min(z0, x0); z0 = f_zero_alpha(z0); x0 = f_sub(x0, z0);
+      xv = v_add(xv, f_trunc_pack_u16(x0)); xv = v_d255(xv);
+      return v_packus(xv);
+    }
+    case ORC_SOFT_LIGHT: {                                                           /* :5152-5247; v_madd_f32 as mul + add (no FMA in the baseline) */
+      f4 s0 = f_from(sv), d0 = f_from(dv), x0 = f_set1(1.0f / 255.0f), a0, b0, y0, z0;
+      int le[4], gt[4];
+      uint32_t out = 0;
+      s0 = f_mul(s0, x0); d0 = f_mul(d0, x0);
+      b0 = f_alpha(d0); x0 = f_mul(s0, b0); b0 = f_max(b0, f_set1(1e-3f));
+      a0 = f_div(d0, b0); d0 = f_add(d0, s0);
+      y0 = f_alpha(s0);
+      d0 = f_sub(d0, x0); s0 = f_add(s0, s0); z0 = f_mul(a0, f_set1(4.0f));
+      x0 = f_sqrt(a0); s0 = f_sub(s0, y0);
+      y0 = z0; z0 = f_add(f_mul(z0, a0), a0); s0 = f_mul(s0, b0);
+      z0 = f_sub(z0, y0); b0 = f_set1(1.0f);
+      z0 = f_add(z0, b0); z0 = f_mul(z0, y0);
+      for (int i = 0; i < 4; i++) le[i] = y0.l[i] <= b0.l[i];
+      z0 = f_sel(le, z0, x0);                                                        /* 4.Dc <= 1 ? polynomial : sqrt(Dc) */
+      for (int i = 0; i < 4; i++) gt[i] = 0.0f < s0.l[i];
+      z0 = f_sub(z0, a0); b0 = f_sub(b0, a0);
+      b0 = f_mul(b0, a0);
+      z0 = f_sel(gt, z0, b0);                                                        /* (2.Sca - Sa).Da > 0 ? [..] - Dc : Dc.(1 - Dc) */
+      s0 = f_zero_alpha(s0);
+      s0 = f_mul(s0, z0); d0 = f_add(d0, s0); d0 = f_mul(d0, f_set1(255.0f));
+      for (int i = 0; i < 4; i++) {
+        int32_t v = cvt_f32(d0.l[i]);
+        v = v < -32768 ? -32768 : v > 32767 ? 32767 : v;                             /* packssdw */
+        out |= (uint32_t)(v < 0 ? 0 : v > 255 ? 255 : v) << (8 * i);                /* packuswb */
+      }
+      return out;
+    }
+    default:
+      return d;
+  }
+}
+
 /* A8 pixels (P8_Alpha / U8_Alpha, pixelgeneric_p.h:85-200): one 16-bit lane, packed adds wrap at 8 bits. */
 static uint32_t a8_div255(uint32_t u) { u = (u + 0x80u) & 0xFFFFu; return ((u + ((u >> 8) & 0xFFu)) >> 8) & 0xFFu; }
 static uint32_t orc_a8_src_copy(uint32_t d, uint32_t s, uint32_t m) { return a8_div255(d * (m ^ 0xFFu) + s * m); }
@@ -226,6 +367,8 @@ ORC_API uint32_t orc_composite_prgb32(uint32_t op, uint32_t d, uint32_t s, uint3
     case ORC_PLUS: return orc_plus(d, s, m);
     case ORC_MULTIPLY: return orc_multiply(d, s, m);
     case ORC_SCREEN: return orc_screen(d, s, m);
+    case ORC_OVERLAY: case ORC_COLOR_DODGE: case ORC_COLOR_BURN: case ORC_LINEAR_LIGHT: case ORC_PIN_LIGHT: case ORC_HARD_LIGHT: case ORC_SOFT_LIGHT:
+      return orc_jit_light(op, d, s, m);
     default: return orc_jit_ext(op, d, s, m);
   }
 }

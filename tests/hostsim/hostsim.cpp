@@ -229,6 +229,13 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
   return written;
 }
 
+// dst[i] = composite(op, dst[i], src[i], mask[i]) with the device's operator code (dev_pixel.cuh) - swept against the C
+// oracle's replay of the JIT sequences by tests/test_oracle.py.
+__attribute__((visibility("default")))
+void hostsim_composite_plane(uint32_t op, uint32_t* dst, const uint32_t* src, const uint8_t* mask, size_t n) {
+  for (size_t i = 0; i < n; i++) if (mask[i]) dst[i] = b2d::composite(op, dst[i], src[i], mask[i]);
+}
+
 } // extern "C"
 
 // Equivalence check for the device edge builder's node expansion (dev_flatten.cuh piece_root / node_split / node_walk):

@@ -33,7 +33,7 @@ def simple_view(gpu, N, mutate):
     ("alpha out of range", lambda c, v: setattr(c, "alpha", 300), INVALID_VALUE),
     ("empty box", lambda c, v: c.box.__setitem__(2, 1), INVALID_VALUE),
     ("fetch index out of range", lambda c, v: (setattr(c, "signature", c.signature | (15 << 16)), setattr(c, "fetch_index", 5)), INVALID_VALUE),
-    ("operator outside the table (Overlay)", lambda c, v: setattr(c, "signature", (c.signature & ~0x3F00) | (17 << 8)), NOT_IMPLEMENTED),
+    ("operator outside the table (internal alpha inversion, 29)", lambda c, v: setattr(c, "signature", (c.signature & ~0x3F00) | (29 << 8)), NOT_IMPLEMENTED),
     ("edge range out of bounds", lambda c, v: (setattr(c, "type", 3), setattr(c, "signature", (c.signature & ~0xC000) | (3 << 14)), setattr(c, "data_count", 4)), INVALID_VALUE),
     ("bad struct size", lambda c, v: setattr(v, "struct_size", 8), INVALID_VALUE),
 ])

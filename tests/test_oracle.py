@@ -310,11 +310,13 @@ def test_gpu_plus_against_reference_templates(ref, refint, gpu, seed):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# the rest of the Porter-Duff set and the division-free separable operators (dev_pixel.cuh comp_jit_ext).
+# the rest of BLCompOp - the Porter-Duff set and the separable blend operators (dev_pixel.cuh comp_jit_ext,
+# comp_jit_light).
 # UNPINNED like Multiply / Screen: the checker is oracle/b2d_oracle.c orc_jit_ext, which replays the JIT's instruction
 # sequences (pipeline/jit/compoppart.cpp:3731-5350); masks come from the pinned rasterizer restatement.
 # ---------------------------------------------------------------------------------------------------------------------
-EXT_OPS = [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 18, 19, 22, 27, 28]
+EXT_OPS = [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28]
+LIGHT_OPS = [17, 20, 21, 23, 24, 25, 26]      # Overlay, ColorDodge, ColorBurn, LinearLight, PinLight, HardLight, SoftLight
 
 
 def translucent_shapes(seed, w, h, n):
@@ -368,3 +370,64 @@ def test_extended_operator_identities():
     assert one(27, 0xFF808080, 0xFF808080, 255) == 0xFF000000  # Difference of equal opaque colours
     for op in EXT_OPS:
         assert one(op, d, s, 0) == d
+
+
+def _w3c_blend(op, cb, cs):
+    """The separable blend functions B(Cb, Cs) of the operators (compositing spec; the JIT's comments state the same
+    formulas in premultiplied form, pipeline/jit/compoppart.cpp:4466-5247)."""
+    import math
+    if op == 17: return _w3c_blend(25, cs, cb)
+    if op == 25: return 2 * cb * cs if cs <= 0.5 else 1 - 2 * (1 - cb) * (1 - cs)
+    if op == 20: return 0 if cb == 0 else (1 if cs >= 1 else min(1, cb / (1 - cs)))
+    if op == 21: return 1 if cb >= 1 else (0 if cs <= 0 else 1 - min(1, (1 - cb) / cs))
+    if op == 23: return min(1, max(0, cb + 2 * cs - 1))
+    if op == 24: return min(cb, 2 * cs) if cs <= 0.5 else max(cb, 2 * cs - 1)
+    if cs <= 0.5: return cb - (1 - 2 * cs) * cb * (1 - cb)
+    return cb + (2 * cs - 1) * ((((16 * cb - 12) * cb + 4) * cb if cb <= 0.25 else math.sqrt(cb)) - cb)
+
+
+@pytest.mark.parametrize("op", LIGHT_OPS)
+def test_light_operators_follow_their_blend_formula(op):
+    """The restated instruction sequences are unpinned (no JIT here); what CAN be checked is that each one computes its
+    operator: Co = Sca.(1 - Da) + Dca.(1 - Sa) + Sa.Da.B(Dc, Sc), Ao = Sa + Da - Sa.Da, within the 8-bit rounding of the
+    sequence (two LSB for the integer-only operators)."""
+    one = lambda d, s: int(O.lib().orc_composite_prgb32(op, d, s, 255))
+    rng = np.random.default_rng(op)
+    for _ in range(1500):
+        da, sa = (int(v) for v in rng.integers(1, 256, 2))
+        dc = [int(rng.integers(0, da + 1)) for _ in range(3)]
+        sc = [int(rng.integers(0, sa + 1)) for _ in range(3)]
+        r = one((da << 24) | (dc[0] << 16) | (dc[1] << 8) | dc[2], (sa << 24) | (sc[0] << 16) | (sc[1] << 8) | sc[2])
+        Da, Sa = da / 255, sa / 255
+        assert abs((r >> 24) - (Sa + Da - Sa * Da) * 255) <= 1.0
+        for i in range(3):
+            Dca, Sca = dc[i] / 255, sc[i] / 255
+            co = Sca * (1 - Da) + Dca * (1 - Sa) + Sa * Da * _w3c_blend(op, Dca / Da, Sca / Sa)
+            assert abs(((r >> (16 - 8 * i)) & 255) - co * 255) <= 2.0, (op, hex(r), da, sa, dc, sc)
+
+
+@pytest.mark.parametrize("op", EXT_OPS + [12, 15, 16])
+def test_device_operator_code_equals_oracle_sequences(op):
+    """dev_pixel.cuh (compiled for the host by tests/hostsim) states every operator channel by channel, the oracle replays
+    the JIT's vector instruction sequence: two formulations, swept against each other on valid and on arbitrary
+    (non-premultiplied) pixel values and every mask."""
+    from tests import hostsim
+    rng = np.random.default_rng(1000 + op)
+    n = 200000
+    for valid in (True, False):
+        a = rng.integers(0, 256, n, dtype=np.uint32)
+        a = np.where(rng.random(n) < 0.15, 255, a); a = np.where(rng.random(n) < 0.1, 0, a)
+        def pixels():
+            al = rng.permutation(a).astype(np.uint32)
+            ch = []
+            for _ in range(3):
+                c = rng.integers(0, 256, n, dtype=np.uint32)
+                if valid:
+                    c = np.minimum(c, al); c = np.where(rng.random(n) < 0.1, al, c); c = np.where(rng.random(n) < 0.1, 0, c)
+                ch.append(c.astype(np.uint32))
+            return ((al << 24) | (ch[0] << 16) | (ch[1] << 8) | ch[2]).astype(np.uint32)
+        d, s = pixels(), pixels()
+        m = np.where(rng.random(n) < 0.3, 255, rng.integers(1, 256, n)).astype(np.uint8)
+        got = d.copy()
+        hostsim.lib().hostsim_composite_plane(op, got.ctypes.data, s.ctypes.data, m.ctypes.data, n)
+        assert np.array_equal(got, O.composite_prgb32(op, d, s, m))

@@ -196,9 +196,11 @@ def test_pipe_runtime_lookup_semantics(gpu):
     assert N.lib.b2dgpu_runtime_get(rt._h, ok, C.byref(dd), None) == 0 and dd.fill_func
     assert N.lib.b2dgpu_runtime_test(rt._h, ok, C.byref(dd), None) == 0
     assert N.lib.b2dgpu_runtime_get(rt._h, sig(1, 1, 2, 3, 0), C.byref(dd), None) == 0 # BL_COMP_OP_SRC_IN on PRGB32: implemented
-    overlay = sig(1, 1, 17, 3, 0)                             # BL_COMP_OP_OVERLAY: outside the runtime's table
-    src_in_a8 = sig(3, 1, 2, 3, 0)                            # SrcIn on an A8 destination: the JIT has separate code, we have none
-    for missing in (overlay, src_in_a8):
+    assert N.lib.b2dgpu_runtime_get(rt._h, sig(1, 1, 17, 3, 0), C.byref(dd), None) == 0 # BL_COMP_OP_OVERLAY on PRGB32: implemented
+    overlay_xrgb = sig(2, 1, 17, 3, 0)                        # Overlay on an XRGB32 destination: the JIT has separate code, we have none
+    src_in_a8 = sig(3, 1, 2, 3, 0)                            # SrcIn on an A8 destination: likewise
+    custom = sig(1, 1, 29, 3, 0)                              # beyond BL_COMP_OP_EXCLUSION: the internal alpha-inversion operator
+    for missing in (overlay_xrgb, src_in_a8, custom):
         assert N.lib.b2dgpu_runtime_get(rt._h, missing, C.byref(dd), None) == 0x10007      # BL_ERROR_NOT_IMPLEMENTED
         assert N.lib.b2dgpu_runtime_test(rt._h, missing, C.byref(dd), None) == 0x10017     # BL_ERROR_NO_ENTRY
     assert N.lib.b2dgpu_runtime_get(rt._h, ok | 0x80000000, C.byref(dd), None) != 0    # pending flag: not a pipeline

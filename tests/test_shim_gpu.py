@@ -152,12 +152,12 @@ def test_many_small_batches(B):
     assert_same(cpu, gpu, 1)
 
 
-@pytest.mark.parametrize("op", [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 18, 19, 22, 27, 28])
+@pytest.mark.parametrize("op", [2, 3, 4, 5, 7, 8, 9, 10, 13, 14, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28])
 def test_extended_operators_through_blend2d(B, op):
     """SURVEY 8f-2 through the real frontend: bl_context_set_comp_op(op) on a GPU context.  The reference's portable
     pipeline has none of these operators (its CPU context answers BL_ERROR_NOT_IMPLEMENTED), so the expected image is
     built from the masks the CPU context rasterizes (SrcCopy of opaque white) and the C restatement of the JIT's
-    operator (oracle/b2d_oracle.c orc_jit_ext; unpinned)."""
+    operator (oracle/b2d_oracle.c orc_jit_ext / orc_jit_light; unpinned)."""
     from oracle import c_oracle as O
     from tests.test_oracle import premul, premultiply_rgba32
     w, h = 320, 200
