@@ -8,11 +8,13 @@
 //                                                                                                fillgeneric_p.h:22-65
 //   ref_build_edges         EdgeBuilder<int>::begin / add_path / done over an EdgeStorage<int>   raster/edgebuilder_p.h:934-1070,
 //                                                                                                raster/edgestorage_p.h:38-178
+//   ref_rasterize_edges     AnalyticRasterizer::prepare / rasterize<kOptionBandOffset> into cells       raster/analyticrasterizer_p.h:289-1210
 #include <blend2d/core/api-build_p.h>
 #include <blend2d/core/path_p.h>
 #include <blend2d/pipeline/reference/compopgeneric_p.h>
 #include <blend2d/pipeline/reference/fillgeneric_p.h>
 #include <blend2d/raster/edgebuilder_p.h>
+#include <blend2d/raster/analyticrasterizer_p.h>
 #include <blend2d/support/arenaallocator_p.h>
 
 #include <stdlib.h>
@@ -123,4 +125,36 @@ REF_API int64_t ref_build_edges(const double* vertices, const uint8_t* commands,
   }
   free(lists);
   return count;
+}
+
+// Rasterizes `n` lines (x0, y0, x1, y1 in 24.8 fixed point, any direction, inside [0, w] x [0, h]) with the reference's
+// AnalyticRasterizer as ONE band of h scanlines and returns the accumulated cells: cells_out[y * (w + 2) + x], x <= w + 1.
+// This is the quantity FillAnalytic's scanline walk sums up (cover << 9 / area merged per cell, cell_merge :1202-1210).
+REF_API int ref_rasterize_edges(const int32_t* lines, size_t n, int w, int h, uint32_t* cells_out) {
+  using namespace bl::RasterEngine;
+  if (w <= 0 || h <= 0) return 1;
+  const size_t required_width = IntOps::align_up(uint32_t(w) + 1u + BL_PIPE_PIXELS_PER_ONE_BIT, BL_PIPE_PIXELS_PER_ONE_BIT);
+  const size_t bit_stride = IntOps::word_count_from_bit_count<BLBitWord>(required_width / BL_PIPE_PIXELS_PER_ONE_BIT) * sizeof(BLBitWord);
+  const size_t cell_stride = required_width * sizeof(uint32_t);
+  const size_t bits_size = size_t(h) * bit_stride;
+  const size_t cells_start = IntOps::align_up(bits_size, size_t(16));
+  uint8_t* buffer = static_cast<uint8_t*>(calloc(cells_start + size_t(h) * cell_stride + 16, 1));
+  if (!buffer) return 2;
+  uint32_t* cells = IntOps::align_up(reinterpret_cast<uint32_t*>(buffer + cells_start), 16);
+
+  AnalyticRasterizer ras;
+  ras.init(reinterpret_cast<BLBitWord*>(buffer), bit_stride, cells, cell_stride, 0, uint32_t(h));
+  for (size_t i = 0; i < n; i++) {
+    EdgePoint<int> p0{lines[i * 4 + 0], lines[i * 4 + 1]}, p1{lines[i * 4 + 2], lines[i * 4 + 3]};
+    uint32_t sign_bit = 0;
+    if (p0.y > p1.y) { EdgePoint<int> t = p0; p0 = p1; p1 = t; sign_bit = 1; }
+    ras.set_sign_mask_from_bit(sign_bit);
+    if (!ras.prepare(p0, p1)) continue;
+    ras.template rasterize<AnalyticRasterizer::kOptionBandOffset>();
+  }
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w + 2; x++)
+      cells_out[size_t(y) * size_t(w + 2) + size_t(x)] = size_t(x) < required_width ? cells[size_t(y) * required_width + size_t(x)] : 0u;
+  free(buffer);
+  return 0;
 }

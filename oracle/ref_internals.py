@@ -25,6 +25,8 @@ def lib():
         _lib.ref_build_edges.restype = C.c_int64
         _lib.ref_build_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_double,
                                          C.c_int, C.c_uint32, C.c_void_p, C.c_size_t]
+        _lib.ref_rasterize_edges.restype = C.c_int
+        _lib.ref_rasterize_edges.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
     return _lib
 
 
@@ -63,3 +65,13 @@ def build_edges(vertices, commands, closed, matrix, transform_type, clip, tolera
         if n <= cap:
             return out[:n].copy()
         cap = int(n)
+
+
+def rasterize_edges(lines, w, h):
+    """The reference's AnalyticRasterizer on (n, 4) int32 lines (24.8 fixed point) -> (h, w + 2) uint32 cells."""
+    ln = np.ascontiguousarray(lines, np.int32).reshape(-1, 4)
+    out = np.zeros((h, w + 2), np.uint32)
+    rc = lib().ref_rasterize_edges(ln.ctypes.data, len(ln), w, h, out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"ref_rasterize_edges failed ({rc})")
+    return out

@@ -229,6 +229,45 @@ uint64_t hostsim_render(const b2dgpu_batch_view* B, uint8_t* pixels, intptr_t st
   return written;
 }
 
+// Cells of `n` lines (x0, y0, x1, y1 in 24.8, any direction) accumulated with the device's rasterizer (dev_raster.cuh):
+// cells[y * (w + 2) + x].  mode 0: prepare once, one edge_step_scanline per row (the reference's walk); mode 1: every
+// (edge, row) on its own - prepare, edge_advance_to_y, one step - which is what a GPU lane does
+// (tile_rasterize_edge_row).  KAT against the reference's AnalyticRasterizer: tests/test_rasterizer_kat.py.
+namespace {
+struct CellImageSink {
+  uint32_t* cells; int w, h, y;
+  void merge(int x, uint32_t cover, uint32_t area) {
+    if (y < 0 || y >= h || x < 0 || x > w) return;
+    cells[size_t(y) * size_t(w + 2) + size_t(x)] += (cover << 9) - area;
+    cells[size_t(y) * size_t(w + 2) + size_t(x) + 1] += area;
+  }
+};
+}
+__attribute__((visibility("default")))
+void hostsim_rasterize_cells(const int32_t* lines, size_t n, int w, int h, int mode, uint32_t* cells) {
+  for (size_t i = 0; i < n; i++) {
+    b2dgpu_edge raw; raw.x0 = lines[i * 4]; raw.y0 = lines[i * 4 + 1]; raw.x1 = lines[i * 4 + 2]; raw.y1 = lines[i * 4 + 3];
+    const b2d::NormEdge ne = b2d::normalize_edge(raw);
+    if (ne.y0 == ne.y1) continue;
+    const int y_first = ne.y0 >> 8, y_last = (ne.y1 - 1) >> 8;
+    CellImageSink sink{ cells, w, h, 0 };
+    if (mode == 0) {
+      b2d::EdgeState st;
+      if (!b2d::edge_prepare(st, ne.x0, ne.y0, ne.x1, ne.y1, ne.sign_bit)) continue;
+      for (int y = y_first; y <= y_last; y++) { sink.y = y; if (b2d::edge_step_scanline(st, sink)) break; }
+    }
+    else {
+      for (int y = y_first; y <= y_last; y++) {
+        b2d::EdgeState st;
+        if (!b2d::edge_prepare(st, ne.x0, ne.y0, ne.x1, ne.y1, ne.sign_bit)) break;
+        b2d::edge_advance_to_y(st, y);
+        sink.y = y;
+        b2d::edge_step_scanline(st, sink);
+      }
+    }
+  }
+}
+
 // dst[i] = composite(op, dst[i], src[i], mask[i]) with the device's operator code (dev_pixel.cuh) - swept against the C
 // oracle's replay of the JIT sequences by tests/test_oracle.py.
 __attribute__((visibility("default")))
