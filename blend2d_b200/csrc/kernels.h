@@ -133,6 +133,8 @@ struct StreamOneParams {
   int y_begin;
   int x0, y0, x1, y1;                     // the box in pixels, clipped to the target (y absolute)
   uint32_t fetch_type, src_format, comp_op, alpha;
+  uint32_t stage_lut;                     // entries of the gradient table if it is to be staged in shared memory by one
+                                          // cp.async.bulk (stream.cu); 0 = look it up in global memory
   const b2dgpu_fetch_data* fd;            // device copy of the command's FetchData
   const uint8_t* bayer;
   int origin_x, origin_y;

@@ -158,7 +158,7 @@ struct BlockLayout {
 
 // A batch that is a single solid box fill (fill_all, clear_all, one big FillRectA).
 // `one`: the batch is a single FillBoxA with SrcOver / SrcCopy, any source (k_stream_one); `ok`: ... with a solid source.
-struct SolidFill { bool ok, one; int box[4]; uint32_t comp_op, alpha, prgb32, fetch_type, src_format, fetch_index; };
+struct SolidFill { bool ok, one; int box[4]; uint32_t comp_op, alpha, prgb32, fetch_type, src_format, fetch_index, lut_entries; };
 
 struct b2dgpu_batch {
   b2dgpu_runtime* rt;
@@ -621,6 +621,8 @@ static SolidFill detect_solid_fill(const b2dgpu_batch_view* v) {
   f.fetch_type = B2DGPU_SIG_FETCH_TYPE(c.signature); f.src_format = B2DGPU_SIG_SRC_FORMAT(c.signature); f.fetch_index = c.fetch_index;
   f.ok = f.fetch_type == B2DGPU_FETCH_SOLID;
   f.one = !f.ok;
+  if (f.fetch_type >= B2DGPU_FETCH_GRADIENT_LINEAR_NN_PAD && f.fetch_index < v->fetch_count && v->fetch_data)
+    f.lut_entries = v->fetch_data[f.fetch_index].gradient.lut.size;
   return f;
 }
 
@@ -1215,6 +1217,8 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
         S.dst = t->d_pixels; S.dst_stride = intptr_t(t->stride); S.y_begin = t->y0;
         S.x0 = box[0]; S.y0 = box[1]; S.x1 = box[2]; S.y1 = box[3];
         S.fetch_type = in.solid.fetch_type; S.src_format = in.solid.src_format; S.comp_op = in.solid.comp_op; S.alpha = in.solid.alpha;
+        { static const int stage = [] { const char* e = getenv("B2DGPU_STREAM_LUT_SMEM"); return e ? atoi(e) : 1; }();   // experiment knob
+          S.stage_lut = stage ? in.solid.lut_entries : 0u; }
         S.fd = T.fetch_data + in.solid.fetch_index;
         S.bayer = rt->d_bayer; S.origin_x = in.origin_x; S.origin_y = in.origin_y;
         S.pixels = (unsigned long long)(box[2] - box[0]) * (unsigned long long)(box[3] - box[1]);

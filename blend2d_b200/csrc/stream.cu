@@ -57,7 +57,32 @@ __device__ __forceinline__ PatCols pattern_cols4(const b2dgpu_fetch_pattern& p, 
   return o;
 }
 
-template<int FC>
+// Gradient table staged in shared memory by ONE bulk asynchronous copy (cp.async.bulk, the TMA engine's 1-D form; SASS
+// UBLKCP + SYNCS.ARRIVE.TRANS64): thread 0 arms an mbarrier with the byte count and issues the copy, every thread waits
+// on the barrier's phase before its first lookup.  Tables of up to kLutSmemEntries entries (the reference builds 256 to
+// 1024 entries per gradient, core/gradient.cpp) that are 16-byte aligned are staged; anything else stays on LDG.
+enum : uint32_t { kLutSmemEntries = 2048 };
+
+__device__ __forceinline__ void lut_stage_begin(uint32_t* s_lut, uint64_t* s_bar, const uint32_t* lut, uint32_t bytes) {
+  const uint32_t bar = uint32_t(__cvta_generic_to_shared(s_bar));
+  const uint32_t dst = uint32_t(__cvta_generic_to_shared(s_lut));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(lut), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void lut_stage_wait(uint64_t* s_bar) {
+  const uint32_t bar = uint32_t(__cvta_generic_to_shared(s_bar));
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar) : "memory");
+  }
+}
+
+template<int FC, bool STAGED>
 __global__ void __launch_bounds__(256) k_stream_one(StreamOneParams P) {
   const int lane = threadIdx.x & 31;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
@@ -75,6 +100,22 @@ __global__ void __launch_bounds__(256) k_stream_one(StreamOneParams P) {
   if (FC == kOneRadial) { rad = fdg.gradient.radial; lut = static_cast<const uint32_t*>(fdg.gradient.lut.data); }
   if (FC == kOneConic) { con = fdg.gradient.conic; lut = static_cast<const uint32_t*>(fdg.gradient.lut.data); }
   if (FC == kOnePattern32) pat = fdg.pattern;
+  // Gradient table in shared memory (STAGED: the launcher saw a table of at most kLutSmemEntries entries).
+  __shared__ __align__(128) uint32_t s_lut[STAGED ? kLutSmemEntries : 4];
+  __shared__ __align__(8) uint64_t s_lut_bar;
+  if (STAGED) {
+    const uint32_t entries = min(fdg.gradient.lut.size, uint32_t(kLutSmemEntries));
+    if ((entries & 3u) == 0u && (uintptr_t(lut) & 15u) == 0u) {          // block uniform
+      if (threadIdx.x == 0) lut_stage_begin(s_lut, &s_lut_bar, lut, entries * 4u);
+      __syncthreads();                                   // the barrier is initialised before anybody polls it
+      lut_stage_wait(&s_lut_bar);
+    }
+    else {
+      // a table the bulk copy cannot take (16-byte granularity): plain cooperative copy
+      for (uint32_t i = threadIdx.x; i < entries; i += blockDim.x) s_lut[i] = __ldg(lut + i);
+      __syncthreads();
+    }
+  }
   FetchEnv env;
   env.fd = P.fd;
   env.bayer = P.bayer;
@@ -150,7 +191,7 @@ __global__ void __launch_bounds__(256) k_stream_one(StreamOneParams P) {
         for (int i = 0; i < 4; i++) {
           uint32_t idx = uint32_t(pt >> 32);
           idx = pad ? grad_index_pad(idx, l.maxi) : grad_index_ror(idx, l.maxi, l.rori);
-          s[i] = __ldg(lut + idx);
+          s[i] = STAGED ? s_lut[idx] : __ldg(lut + idx);
           pt += l.dt.u64;
         }
       }
@@ -162,13 +203,13 @@ __global__ void __launch_bounds__(256) k_stream_one(StreamOneParams P) {
         for (int i = 0; i < 4; i++) {
           uint32_t idx = radial_index(r, row, uint32_t(x + i));
           idx = pad ? grad_index_pad(idx, r.maxi) : grad_index_ror(idx, r.maxi, r.rori);
-          s[i] = __ldg(lut + idx);
+          s[i] = STAGED ? s_lut[idx] : __ldg(lut + idx);
         }
       }
       else if (FC == kOneConic) {
         ConicRow row; row.tx = f32_from_bits(rj.a); row.ay = f32_from_bits(rj.b); row.by = f32_from_bits(rj.c);
         #pragma unroll
-        for (int i = 0; i < 4; i++) s[i] = __ldg(lut + conic_index(con, row, uint32_t(x + i)));
+        for (int i = 0; i < 4; i++) { const uint32_t idx = conic_index(con, row, uint32_t(x + i)); s[i] = STAGED ? s_lut[idx] : __ldg(lut + idx); }
       }
       else if (FC == kOnePattern32) {
         const uint8_t* srow = pat.src.pixel_data + intptr_t(prj) * pat.src.stride;
@@ -198,19 +239,19 @@ __global__ void __launch_bounds__(256) k_stream_one(StreamOneParams P) {
   if (P.pixel_counter && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.pixel_counter, P.pixels);
 }
 
-template<int FC>
+template<int FC, bool STAGED>
 static int launch_one(const StreamOneParams& P, int sm_count, cudaStream_t s) {
   static int per_sm = 0;
   if (!per_sm) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_stream_one<FC>, 256, 0) != cudaSuccess || n < 1) n = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_stream_one<FC, STAGED>, 256, 0) != cudaSuccess || n < 1) n = 2;
     per_sm = n;
   }
   const long long ncb = (P.x1 + 127) / 128 - P.x0 / 128, nrq = (P.y1 - P.y0 + 3) / 4;
   const long long want = (ncb * nrq + 7) / 8;
   const long long cap = (long long)sm_count * per_sm;
   const int grid = int(want < cap ? (want < 1 ? 1 : want) : cap);
-  k_stream_one<FC><<<grid, 256, 0, s>>>(P);
+  k_stream_one<FC, STAGED><<<grid, 256, 0, s>>>(P);
   return 1;
 }
 
@@ -226,12 +267,14 @@ static int stream_one_class(uint32_t ft, uint32_t src_format) {
 
 int launch_stream_one(const StreamOneParams& P, int sm_count, cudaStream_t s) {
   if (P.x0 >= P.x1 || P.y0 >= P.y1) return 0;
+  // stage_lut: entries of the gradient table when it fits the shared-memory copy (0: look it up through LDG)
+  const bool staged = P.stage_lut != 0u && P.stage_lut <= uint32_t(kLutSmemEntries);
   switch (stream_one_class(P.fetch_type, P.src_format)) {
-    case kOneLinear:    return launch_one<kOneLinear>(P, sm_count, s);
-    case kOneRadial:    return launch_one<kOneRadial>(P, sm_count, s);
-    case kOneConic:     return launch_one<kOneConic>(P, sm_count, s);
-    case kOnePattern32: return launch_one<kOnePattern32>(P, sm_count, s);
-    default:            return launch_one<kOneGeneric>(P, sm_count, s);
+    case kOneLinear:    return staged ? launch_one<kOneLinear, true>(P, sm_count, s) : launch_one<kOneLinear, false>(P, sm_count, s);
+    case kOneRadial:    return staged ? launch_one<kOneRadial, true>(P, sm_count, s) : launch_one<kOneRadial, false>(P, sm_count, s);
+    case kOneConic:     return staged ? launch_one<kOneConic, true>(P, sm_count, s) : launch_one<kOneConic, false>(P, sm_count, s);
+    case kOnePattern32: return launch_one<kOnePattern32, false>(P, sm_count, s);
+    default:            return launch_one<kOneGeneric, false>(P, sm_count, s);
   }
 }
 

@@ -109,6 +109,11 @@ def curve_paths(kind, count, W, H, rule=0, style="solid", extend=0, op=SRC_OVER,
             p.move_to(x[0], y[0])
             if kind == "quad":
                 p.quad_to(x[1], y[1], x[2], y[2])
+            elif kind == "conic":
+                # rational quadratic (BL_PATH_CMD_CONIC; EdgeBuilder::conic_to, edgebuilder_p.h): weights from a flat arc
+                # to a sharp hyperbola-like bulge, and a second segment so that the path has an interior join
+                p.conic_to(x[1], y[1], x[2], y[2], float(rng.choice([0.25, 0.7071067811865476, 1.0, 2.5, 8.0])))
+                p.conic_to(x[3], y[3], x[0] + 7.5, y[0] - 3.25, float(rng.uniform(0.1, 4.0)))
             else:
                 p.cubic_to(x[1], y[1], x[2], y[2], x[3], y[3])
             bx, by = float(min(x)), float(min(y))

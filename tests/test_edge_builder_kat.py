@@ -59,11 +59,13 @@ def random_paths(api, rng, n, margin):
         pt = lambda: (float(rng.uniform(-margin, W + margin)), float(rng.uniform(-margin, H + margin)))
         p.move_to(*pt())
         for _ in range(int(rng.integers(2, 9))):
-            k = int(rng.integers(0, 3))
+            k = int(rng.integers(0, 4))
             if k == 0:
                 p.line_to(*pt())
             elif k == 1:
                 p.quad_to(*pt(), *pt())
+            elif k == 3:
+                p.conic_to(*pt(), *pt(), float(rng.choice([0.2, 0.7071067811865476, 1.0, 3.0, rng.uniform(0.05, 6.0)])))
             else:
                 p.cubic_to(*pt(), *pt(), *pt())
         if i % 2:

@@ -52,6 +52,14 @@ def test_mixed_scene(B, fmt):
     assert_same(cpu, gpu, 1)
 
 
+@pytest.mark.parametrize("rule", [0, 1])
+def test_conic_segments(B, rule):
+    """BL_PATH_CMD_CONIC through the device edge builder (B2DGPU_SEG_CONIC, dev_flatten.cuh build_conic): rational
+    quadratics with weights below, at and above 1, partly off the canvas, NonZero and EvenOdd."""
+    cpu, gpu = both(B, S.curve_paths("conic", 250, 640, 400, rule=rule, margin=120.0), 640, 400, seed=5 + rule)
+    assert_same(cpu, gpu)
+
+
 @pytest.mark.parametrize("kind", ["A", "U"])
 def test_bl_bench_rects(B, kind):
     cpu, gpu = both(B, S.rects(kind, 300, 32, 512, 600), 512, 600)
