@@ -339,10 +339,15 @@ extern "C" b2dgpu_result b2dgpu_runtime_create(const b2dgpu_create_info* info, b
     return cuda_fail(e, "b2dgpu_runtime_create: device allocation");
   }
   rt->h_bin_state[0] = 0; rt->h_bin_state[1] = 1; rt->h_bin_state[2] = 1; rt->h_bin_state[3] = 0;
-  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
-  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&rt->glyph_cache_ready, cudaEventDisableTiming);
+  e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&rt->staging[i].free_event, cudaEventDisableTiming);
+  for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&rt->slot_done[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rt->prep_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rt->glyph_cache_ready, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    b2dgpu_runtime_destroy(rt);
+    return cuda_fail(e, "b2dgpu_runtime_create: cudaEventCreate");
+  }
   {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -1040,7 +1045,13 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
 
   uint32_t* d_seg_offsets = reinterpret_cast<uint32_t*>(blk + L.seg_offsets);
 
-  cudaEvent_t ev[3] = { nullptr, nullptr, nullptr };
+  // Profiling events: owned by this guard until they are handed to rt->prof_events (an early error return frees them).
+  struct EventTriple {
+    cudaEvent_t e[3] = { nullptr, nullptr, nullptr };
+    bool handed_over = false;
+    ~EventTriple() { if (!handed_over) for (int i = 0; i < 3; i++) if (e[i]) cudaEventDestroy(e[i]); }
+    cudaEvent_t& operator[](int i) { return e[i]; }
+  } ev;
   if (rt->profiling) {
     for (int i = 0; i < 3; i++) CU_TRY(cudaEventCreate(&ev[i]));
     CU_TRY(cudaEventRecord(ev[0], s));
@@ -1236,6 +1247,7 @@ static b2dgpu_result render_block(b2dgpu_runtime* rt, b2dgpu_target* const* targ
   if (rt->profiling) {
     CU_TRY(cudaEventRecord(ev[2], s));
     for (int i = 0; i < 3; i++) rt->prof_events.push_back(ev[i]);
+    ev.handed_over = true;
   }
 
   CU_TRY(cudaGetLastError());
