@@ -227,7 +227,15 @@ B2D_HD void edge_advance_to_y(EdgeState& s, int y_target) {
 // Rasterizes scanline `s.ey0` and moves the state to the next one.  Returns true when the edge has ended.
 //
 // `Sink::merge(x, cover, area)` must perform  cell[x] += (cover << 9) - area;  cell[x + 1] += area.
-template<typename Sink>
+//
+// kWindow (one-row use only - tile_rasterize_edge_row; the state is NOT valid afterwards): the sink only keeps the cells
+// of a window of columns [win_lo(), win_hi()), everything left of it as one sum (add_left) and nothing right of it.  A
+// shallow edge can cross hundreds of cells in one scanline; instead of walking them
+//   * the cells before the window are jumped over with the same closed form advanceToY() uses for whole scanlines
+//     (err_multi_step on the y accumulator: the covers of j cells are j * y_lift + the corrections of j steps),
+//   * the walk stops at the far side of the window: the covers of a scanline add up to the signed y-extent of the edge
+//     in the row, so what is left of the window is that total minus the covers already seen.
+template<bool kWindow = false, typename Sink>
 B2D_HD bool edge_step_scanline(EdgeState& s, Sink& sink) {
   const uint32_t sm = s.sign_mask;
   s.ey0 += 1;
@@ -379,8 +387,30 @@ B2D_HD bool edge_step_scanline(EdgeState& s, Sink& sink) {
       int fx_local = x_local & kA8Mask;
       area = cover * uint32_t(s.fx0);
 
+      uint32_t total = 0, done = 0;                     // kWindow: signed y-extent of the edge in this row / covers seen
+      if constexpr (kWindow) {
+        total = apply_sign(uint32_t(s.fy1 - s.fy0), sm);
+        // cells at or right of win_hi() are dropped: jump over them (right to left: they come first)
+        const int j = s.ex0 - tmax(ex_local, sink.win_hi() - 1);
+        if (j >= 2) {
+          int corr = 0;
+          err_multi_step(corr, s.y_err, s.y_rem, s.dx, j - 1);
+          const uint32_t tn = uint32_t(s.y_lift) * uint32_t(j - 1) + uint32_t(corr);
+          s.y_dlt += int(tn);
+          done = cover + apply_sign(tn, sm);
+          cover = uint32_t(s.y_lift);
+          err_step_u(cover, s.y_err, s.y_rem, s.dx);
+          s.y_dlt += int(cover);
+          cover = apply_sign(cover, sm);
+          area = cover * kA8Scale;
+          s.ex0 -= j;
+        }
+      }
+
       while (s.ex0 != ex_local) {
+        if constexpr (kWindow) { if (s.ex0 < sink.win_lo() - 1) { sink.add_left((total - done) << 9); return true; } }   // the rest is left of the window
         sink.merge(s.ex0, cover, area);
+        if constexpr (kWindow) done += cover;
         cover = uint32_t(s.y_lift);
         err_step_u(cover, s.y_err, s.y_rem, s.dx);
         s.y_dlt += int(cover);
@@ -451,7 +481,26 @@ B2D_HD bool edge_step_scanline(EdgeState& s, Sink& sink) {
       int fx_local = ((x_local - 1) & kA8Mask) + 1;
       area = cover * (uint32_t(s.fx0) + kA8Scale);
 
+      if constexpr (kWindow) {
+        // cells up to win_lo() - 2 only feed the sum left of the window: jump over them (left to right: they come first)
+        const int j = tmin(ex_local, sink.win_lo() - 1) - s.ex0;
+        if (j >= 2) {
+          int corr = 0;
+          err_multi_step(corr, s.y_err, s.y_rem, s.dx, j - 1);
+          const uint32_t tn = uint32_t(s.y_lift) * uint32_t(j - 1) + uint32_t(corr);
+          s.y_dlt += int(tn);
+          sink.add_left((cover + apply_sign(tn, sm)) << 9);
+          cover = uint32_t(s.y_lift);
+          err_step_u(cover, s.y_err, s.y_rem, s.dx);
+          s.y_dlt += int(cover);
+          cover = apply_sign(cover, sm);
+          area = cover * kA8Scale;
+          s.ex0 += j;
+        }
+      }
+
       while (s.ex0 != ex_local) {
+        if constexpr (kWindow) { if (s.ex0 >= sink.win_hi()) return true; }   // the rest is right of the window: dropped
         sink.merge(s.ex0, cover, area);
         cover = uint32_t(s.y_lift);
         err_step_u(cover, s.y_err, s.y_rem, s.dx);

@@ -63,6 +63,10 @@ struct TileSink {
     put(x, (cover << 9) - area);
     put(x + 1, area);
   }
+  // window interface of edge_step_scanline<true>
+  B2D_HD int win_lo() const { return tx0; }
+  B2D_HD int win_hi() const { return tx0 + kTileW; }
+  B2D_HD void add_left(uint32_t v) { if (v) { store.add_carry(row, v); touched = 1; } }
 };
 
 // Relation of an edge to the tile whose top-left pixel is (tx0, ty0).
@@ -148,7 +152,7 @@ B2D_HD void tile_rasterize_edge_row(const NormEdge& ed, int y, Sink& sink) {
   EdgeState st;
   if (!edge_prepare(st, ed.x0, ed.y0, ed.x1, ed.y1, ed.sign_bit)) return;
   edge_advance_to_y(st, y);
-  edge_step_scanline(st, sink);
+  edge_step_scanline<true>(st, sink);                  // windowed: a shallow edge's cells outside the tile are not walked
 }
 
 B2D_HD bool command_has_edges(uint32_t type) { return type == B2DGPU_CMD_FILL_ANALYTIC || type == B2DGPU_CMD_FILL_GEOMETRY; }

@@ -795,6 +795,10 @@ struct EntrySink {
     const int first_full = bi + 1 + int(spill);
     if (first_full < kBlocks) atomicAdd(reinterpret_cast<uint32_t*>(&pre->carry4[row]) + first_full, v0 + area);
   }
+  // window interface of edge_step_scanline<true> (dev_raster.cuh)
+  __device__ __forceinline__ int win_lo() const { return tx0; }
+  __device__ __forceinline__ int win_hi() const { return tx0 + kTileW; }
+  __device__ __forceinline__ void add_left(uint32_t v) { if (v) atomicAdd(&pre->carry4[row].x, v); }
   __device__ __forceinline__ void merge(int x, uint32_t cover, uint32_t area) {
     const uint32_t v0 = (cover << 9) - area;
     const int rel = x - tx0;
