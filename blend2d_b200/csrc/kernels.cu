@@ -855,17 +855,17 @@ __device__ __noinline__ void slow_group_rows(const int4* __restrict__ edges, uin
 // Experiment build only (make EXTRA=-DB2D_PHASE_TIMING): cycles the warps of k_tile_render spend in / wait for each phase.
 //   [0] phase-1 busy (sum over warps)  [1] wait at the barrier behind phase 1  [2] phase-2 busy  [3] cull + wait before phase 1
 //   [4] phase-1 length seen by warp 0 (barrier to barrier)  [5] sub-chunks  [6] commands replayed (per CTA)  [7] longest phase-1 command (sum over sub-chunks)
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[16];   // [8] cycles in item rounds [9] rounds [10] cycles classifying chunks [11] chunks [12] finalize cycles [13] prologue cycles [14] cycles inside commands (all by lane 0 of every warp)
 extern "C" __attribute__((visibility("default"))) int b2dgpu_debug_phase_cycles(unsigned long long* out, int reset) {
   cudaDeviceSynchronize();
   if (out) cudaMemcpyFromSymbol(out, g_phase_cycles, sizeof(g_phase_cycles));
-  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
   return 0;
 }
 __device__ __forceinline__ long long pt_now() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
-#define PT(x) x
+#define PT(...) __VA_ARGS__
 #else
-#define PT(x)
+#define PT(...)
 #endif
 
 template<int BPP, int TH>
@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   }
   bool dirty = false;
   uint32_t px_written = 0;
-  PT(long long pt_busy1 = 0; long long pt_wait1 = 0; long long pt_busy2 = 0; long long pt_wait2 = 0; long long pt_len1 = 0; long long pt_sub = 0; long long pt_cmds = 0; long long pt_maxcmd = 0; long long pt_last = pt_now(); __shared__ unsigned long long s_pt_max;)
+  PT(long long pt_busy1 = 0; long long pt_wait1 = 0; long long pt_busy2 = 0; long long pt_wait2 = 0; long long pt_len1 = 0; long long pt_sub = 0; long long pt_cmds = 0; long long pt_maxcmd = 0; long long pt_last = pt_now(); long long pt_round = 0, pt_rounds = 0, pt_cls = 0, pt_chunks = 0, pt_fin = 0, pt_pro = 0, pt_in = 0; __shared__ unsigned long long s_pt_max;)
   const bool count_pixels = P.pixel_counter != nullptr;
 
   // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
@@ -1003,7 +1003,9 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             er.y = o1 - o0;
           }
           EntrySink<TH> sink; sink.pre = pre; sink.pool_cap = uint32_t(kPool); sink.pool = s_pool; sink.pool_link = s_pool_link; sink.pool_next = &s_pool_next; sink.tx0 = tx0; sink.row = 0;
+          PT(pt_pro += pt_now() - pt_c0;)
           for (uint32_t e0 = 0; e0 < er.y; e0 += 32) {
+            PT(const long long pt_k0 = pt_now(); pt_chunks++;)
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
             uint32_t rows_crossed = 0, first_row = 0;
@@ -1045,8 +1047,10 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             items += chunk_items;
             // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
             // row of the replay is rasterized as a whole (slow_group_rows).
+            PT(pt_cls += pt_now() - pt_k0;)
             if (items > kDenseItemsPerRow * uint32_t(TH)) continue;
             for (uint32_t base_i = 0; base_i < chunk_items; base_i += 32) {
+              PT(const long long pt_r0 = pt_now(); pt_rounds++;)
               const uint32_t i = base_i + lane;
               uint32_t j = 0;
               #pragma unroll
@@ -1064,9 +1068,11 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
                 sink.row = r;
                 tile_rasterize_edge_row(ne, ty0 + r, sink);
               }
+              PT(__syncwarp(); pt_round += pt_now() - pt_r0;)
             }
           }
         }
+        PT(const long long pt_f0 = pt_now();)
         if (lane < TH) pre->carry_left[lane] = left_acc;
         const bool dense = nstr && items > kDenseItemsPerRow * uint32_t(TH);
         if (lane == 0 && nstr) atomicOr(&pre->flags, dense ? (kPreStraddle | kPreOverflow) : kPreStraddle);
@@ -1126,6 +1132,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
           if (lane == 0) { pre->warp_mask = wm; s_wmask[k] = wm; }
           if (lane < TH) reinterpret_cast<uint8_t*>(pre->wrec4)[lane] = uint8_t(uniform_mask);
         }
+        PT(pt_fin += pt_now() - pt_f0; pt_in += pt_now() - pt_c0;)
         PT(if (lane == 0) atomicMax(&s_pt_max, (unsigned long long)(pt_now() - pt_c0));)
         // next command: whichever warp is free takes it (edge counts differ a lot between commands)
         uint32_t nk = 0;
@@ -1277,6 +1284,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       PT(pt_last = pt_now(); pt_busy2 += pt_last - pt_c;)
     }
   }
+  PT(if (lane == 0) { atomicAdd(&g_phase_cycles[8], (unsigned long long)pt_round); atomicAdd(&g_phase_cycles[9], (unsigned long long)pt_rounds); atomicAdd(&g_phase_cycles[10], (unsigned long long)pt_cls); atomicAdd(&g_phase_cycles[11], (unsigned long long)pt_chunks); atomicAdd(&g_phase_cycles[12], (unsigned long long)pt_fin); atomicAdd(&g_phase_cycles[13], (unsigned long long)pt_pro); atomicAdd(&g_phase_cycles[14], (unsigned long long)pt_in); })
   PT(if (lane == 0) { atomicAdd(&g_phase_cycles[0], (unsigned long long)pt_busy1); atomicAdd(&g_phase_cycles[1], (unsigned long long)pt_wait1);
                       atomicAdd(&g_phase_cycles[2], (unsigned long long)pt_busy2); atomicAdd(&g_phase_cycles[3], (unsigned long long)pt_wait2);
                       if (warp == 0) { atomicAdd(&g_phase_cycles[4], (unsigned long long)pt_len1); atomicAdd(&g_phase_cycles[5], (unsigned long long)pt_sub);
