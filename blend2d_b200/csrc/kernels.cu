@@ -917,7 +917,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
   }
   bool dirty = false;
   uint32_t px_written = 0;
-  PT(long long pt_busy1 = 0; long long pt_wait1 = 0; long long pt_busy2 = 0; long long pt_wait2 = 0; long long pt_len1 = 0; long long pt_sub = 0; long long pt_cmds = 0; long long pt_maxcmd = 0; long long pt_last = pt_now(); long long pt_round = 0, pt_rounds = 0, pt_cls = 0, pt_chunks = 0, pt_fin = 0, pt_pro = 0, pt_in = 0; __shared__ unsigned long long s_pt_max;)
+  PT(long long pt_busy1 = 0; long long pt_wait1 = 0; long long pt_busy2 = 0; long long pt_wait2 = 0; long long pt_len1 = 0; long long pt_sub = 0; long long pt_cmds = 0; long long pt_maxcmd = 0; long long pt_last = pt_now(); long long pt_round = 0, pt_rounds = 0, pt_cls = 0, pt_chunks = 0, pt_fin = 0, pt_pro = 0, pt_in = 0; __shared__ unsigned long long s_pt_max; __shared__ unsigned long long s_pt_maxround;)
   const bool count_pixels = P.pixel_counter != nullptr;
 
   // Commands that touch the tile are appended, in order, to a ring in shared memory; whenever kSub of them are
@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       ring_head += sub_n;
       if (tid == 0) { s_next = TH; s_pool_next = 0; } // commands beyond the first TH are handed out dynamically
       __syncthreads();                                  // ring entries written / previous sub-chunk's s_pre consumed
-      PT(const long long pt_a = pt_now(); pt_wait2 += pt_a - pt_last; pt_sub++; pt_cmds += sub_n; if (tid == 0) s_pt_max = 0;)
+      PT(const long long pt_a = pt_now(); pt_wait2 += pt_a - pt_last; pt_sub++; pt_cmds += sub_n; if (tid == 0) { s_pt_max = 0; s_pt_maxround = 0; })
 
       // ---- phase 1 (K2): one warp per command - classify its edges against the tile and rasterize the few that
       //      straddle it, one (edge, row) item per lane, into the command's per-row entry lists.  No block barrier.
@@ -1009,6 +1009,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
             const uint32_t e = e0 + lane;
             int cls = kEdgeNone;
             uint32_t rows_crossed = 0, first_row = 0;
+            uint32_t extra_cells = 0;                   // cells beyond one per row that a shallow edge will touch in the tile (estimate)
             int ey0 = 0, ey1 = 0;
             uint32_t esign = 0;
             uint32_t eidx = 0;
@@ -1020,6 +1021,11 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
               if (cls == kEdgeStraddle) {
                 first_row = uint32_t(max(ne.y0 >> 8, ty0) - ty0);
                 rows_crossed = uint32_t(min((ne.y1 - 1) >> 8, ty0 + TH - 1) - ty0) - first_row + 1u;
+                // a nearly horizontal edge is one entry per CELL, walked by one lane: count the columns it spans inside the
+                // tile's rows so that such a command takes the cell-row path of the replay instead (kDenseItemsPerRow)
+                const uint32_t edge_rows = uint32_t(((ne.y1 - 1) >> 8) - (ne.y0 >> 8)) + 1u;
+                const uint32_t cols = min(uint32_t(kTileW), (uint32_t(abs(ne.x1 - ne.x0)) >> 8) * rows_crossed / edge_rows);
+                extra_cells = cols > rows_crossed ? cols - rows_crossed : 0u;
               }
             }
             nstr += __popc(__ballot_sync(0xFFFFFFFFu, cls == kEdgeStraddle));
@@ -1044,7 +1050,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
               if (lane >= o) inc += t;
             }
             const uint32_t chunk_items = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            items += chunk_items;
+            items += chunk_items + __reduce_add_sync(0xFFFFFFFFu, extra_cells);
             // So many crossings that the entry lists and the pool would overflow anyway: do not rasterize here, every
             // row of the replay is rasterized as a whole (slow_group_rows).
             PT(pt_cls += pt_now() - pt_k0;)
@@ -1068,7 +1074,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
                 sink.row = r;
                 tile_rasterize_edge_row(ne, ty0 + r, sink);
               }
-              PT(__syncwarp(); pt_round += pt_now() - pt_r0;)
+              PT(__syncwarp(); { const long long dr = pt_now() - pt_r0; pt_round += dr; if (lane == 0) atomicMax(&s_pt_maxround, (unsigned long long)dr); })
             }
           }
         }
@@ -1141,7 +1147,7 @@ __global__ void __launch_bounds__(32 * TH, 32 / TH) k_tile_render(TileParams P) 
       }
       PT(const long long pt_b = pt_now();)
       __syncthreads();
-      PT(const long long pt_c = pt_now(); pt_busy1 += pt_b - pt_a; pt_wait1 += pt_c - pt_b; pt_len1 += pt_c - pt_a; pt_maxcmd += (long long)s_pt_max;)
+      PT(const long long pt_c = pt_now(); pt_busy1 += pt_b - pt_a; pt_wait1 += pt_c - pt_b; pt_len1 += pt_c - pt_a; pt_maxcmd += (long long)s_pt_max; if (tid == 0) atomicAdd(&g_phase_cycles[15], s_pt_maxround);)
 
       // ---- phase 2 (K3): every warp replays, in order, the commands that concern ITS block; warps never wait for each
       //      other (except the four warps of a row group inside the slow path) ----

@@ -27,3 +27,4 @@ print("phase-2 busy per sub-chunk per warp %.0f cycles" % (v[2] / 32 / v[5]))
 print("phase 1 anatomy: %d item rounds, %.0f cycles each; %d edge chunks classified, %.0f cycles each; finalize %.0f and prologue %.0f cycles per command; average command %.0f cycles"
       % (v[9], v[8] / max(v[9], 1), v[11], v[10] / max(v[11], 1), v[12] / max(v[6], 1), v[13] / max(v[6], 1), v[14] / max(v[6], 1)))
 print("share of the time inside commands: rounds %.1f%%, classification %.1f%%, finalize %.1f%%, prologue %.1f%%" % tuple(100.0 * x / max(v[14], 1) for x in (v[8], v[10], v[12], v[13])))
+print("longest item round of a sub-chunk, on average: %.0f cycles" % (v[15] / v[5]))
