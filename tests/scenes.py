@@ -334,3 +334,19 @@ def geometries(count, W, H, op=SRC_OVER):
             elif k == 4: ctx.fill_geometry(10, [x, y, s / 2, s / 3, float(rng.uniform(0, 6)), float(rng.uniform(0.5, 5))])
             else: ctx.fill_geometry(12, [x, y, x + s, y + s / 3, x + s / 4, y + s])
     return scene
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Thin slivers: nearly horizontal edges that cross hundreds of cells per scanline, in both directions, partly off the
+# canvas - the runs whose cells outside a tile the one-row stepper jumps over (dev_raster.cuh edge_step_scanline<kWindow>).
+# ---------------------------------------------------------------------------------------------------------------------
+def slivers(count, W, H):
+    def scene(api, ctx, rng):
+        for i in range(count):
+            x0 = rng.uniform(-50, W * 0.6); w = rng.uniform(100, W); y = rng.uniform(0, H); h = rng.uniform(0.3, 6.0)
+            ctx.set_fill_style(rand_rgba32(rng))
+            ctx.set_fill_rule(i & 1)
+            p = api.Path()
+            p.move_to(x0, y); p.line_to(x0 + w, y + rng.uniform(-3, 3)); p.line_to(x0 + w * rng.uniform(0.2, 0.9), y + h); p.close()
+            ctx.fill_path(p)
+    return scene

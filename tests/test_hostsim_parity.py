@@ -28,6 +28,12 @@ def test_polygons(ref, rule):
     compare(ref, S.polygons(200, 128, 20, W0, H0, rule), W0, H0)
 
 
+@pytest.mark.parametrize("size", [(700, 300), (1300, 200), (513, 97), (2000, 64)])
+def test_shallow_slivers(ref, size):
+    """Nearly horizontal edges: the window skip of the one-row stepper (edge_step_scanline<kWindow>)."""
+    compare(ref, S.slivers(150, *size), *size)
+
+
 @pytest.mark.parametrize("kind", ["quad", "cubic"])
 def test_curves_clipped_by_the_canvas(ref, kind):
     compare(ref, S.curve_paths(kind, 150, W0, H0, 1), W0, H0)

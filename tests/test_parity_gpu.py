@@ -48,6 +48,13 @@ def test_curve_paths(ref, gpu, kind, rule):
     compare(ref, gpu, S.curve_paths(kind, 200, W0, H0, rule), W0, H0)
 
 
+@pytest.mark.parametrize("size", [(700, 300), (1300, 200), (513, 97), (2000, 64)])
+def test_shallow_slivers(ref, gpu, size):
+    """Nearly horizontal edges crossing hundreds of cells per scanline: the cells outside a tile are skipped in closed
+    form (edge_step_scanline<kWindow>), commands made of such edges take the compositor's cell-row path."""
+    compare(ref, gpu, S.slivers(150, *size), *size)
+
+
 @pytest.mark.parametrize("style,tol", [("linear", 0), ("radial", 0), ("conic", 1)])
 @pytest.mark.parametrize("extend", [0, 1, 2])
 def test_gradients(ref, gpu, style, tol, extend):
