@@ -120,7 +120,12 @@ static void BL_CDECL runtime_destroy(Pipeline::PipeRuntime* self) noexcept {
 }
 
 static constexpr uint32_t kCreateFlagAdaptiveBatches = 0x20000000u;    // private: set by adjust_create_info() on its own copy
-static constexpr uint32_t kFirstBatch = 512, kLargestBatch = 8192;
+static constexpr uint32_t kFirstBatchDefault = 512, kLargestBatch = 8192;
+// B2DGPU_SHIM_FIRST_BATCH: experiment knob (commands in the first batch of a frame).
+static uint32_t first_batch() noexcept {
+  static const uint32_t n = [] { const char* e = getenv("B2DGPU_SHIM_FIRST_BATCH"); const int v = e ? atoi(e) : 0; return uint32_t(v >= 16 && v <= int(kLargestBatch) ? v : int(kFirstBatchDefault)); }();
+  return n;
+}
 
 static const BLContextCreateInfo* adjust_create_info(const BLContextCreateInfo* options, BLContextCreateInfo* storage) noexcept {
   if (!(options->flags & kCreateFlagGpuRuntime))
@@ -132,12 +137,12 @@ static const BLContextCreateInfo* adjust_create_info(const BLContextCreateInfo* 
   // still recording (the reference's default is 10240 commands, rastercontext_p.h:62).
   if (!storage->command_queue_limit) {
     // Adaptive (B2DGPU_SHIM_ADAPTIVE=0: fixed 2048): the first batch of a frame is small so that the device starts early,
-    // every further batch doubles - the frontend records faster than the device composites, so bigger batches only
+    // every further batch is four times larger - the frontend records faster than the device composites, so bigger batches only
     // mean fewer per-batch kernels; consume_batch() and sync_to_host() move the limit.
     const char* e = getenv("B2DGPU_SHIM_ADAPTIVE");
     if (e && e[0] == '0') storage->command_queue_limit = 2048;
     else {
-      storage->command_queue_limit = kFirstBatch;
+      storage->command_queue_limit = first_batch();
       storage->flags |= kCreateFlagAdaptiveBatches;
     }
   }
@@ -227,7 +232,7 @@ static BLResult sync_to_host(BLRasterContextImpl* ctx_impl) noexcept {
   if (r != B2DGPU_SUCCESS)
     return ctx_impl->accumulate_error(bl_make_error(BLResult(r)));
   st->device_dirty = false;
-  if (st->adaptive_batches) ctx_impl->worker_mgr()._command_queue_limit = kFirstBatch;     // a new frame starts small again
+  if (st->adaptive_batches) ctx_impl->worker_mgr()._command_queue_limit = first_batch();     // a new frame starts small again
   return BL_SUCCESS;
 }
 
