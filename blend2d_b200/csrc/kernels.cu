@@ -6,7 +6,8 @@
 //                                    give every command a contiguous edge range.
 //   K1b k_scan_*                     exclusive prefix sum of the per-segment edge counts.
 //   K1c k_analytic_bbox / k_finalize_commands   per-command pixel bounding boxes used for tile culling.
-//   K1d k_bin_*                      per-band ordered command lists + per (band, command) column extents (tile culling).
+//   K1d k_bin_*                      per-band ordered command lists + per (band, command) column extents (tile culling)
+//                                    and the list of the command's edges that cross the band (k_bin_edges).
 //   K2+K3 k_tile_render<BPP,TH>      one CTA of TH warps per 128 x TH destination tile, a warp per block of 32 columns x
 //                                    4 rows.  The tile's pixels are loaded ONCE into registers (16-byte vector loads),
 //                                    every command that touches the tile is replayed in submission order - phase 1: a
