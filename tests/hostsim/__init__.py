@@ -21,6 +21,8 @@ def lib():
         _lib.hostsim_build_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib.hostsim_rasterize_cells.restype = None
         _lib.hostsim_rasterize_cells.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.hostsim_err_multi_step_check.restype = C.c_uint32
+        _lib.hostsim_err_multi_step_check.argtypes = [C.c_uint64, C.c_uint32]
         _lib.hostsim_composite_plane.restype = None
         _lib.hostsim_composite_plane.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         _lib.hostsim_flatten_equivalence.restype = C.c_uint32

@@ -268,6 +268,28 @@ void hostsim_rasterize_cells(const int32_t* lines, size_t n, int w, int h, int m
   }
 }
 
+// err_multi_step(count) against `count` single err_step_u() calls on random DDA states (0 <= err < correction,
+// 0 <= step < correction): the closed form the windowed one-row stepper (edge_step_scanline<true>) and edge_advance_to_y
+// rest on.  Returns the number of mismatches.
+__attribute__((visibility("default")))
+uint32_t hostsim_err_multi_step_check(uint64_t seed, uint32_t cases) {
+  uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+  auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return uint32_t(s >> 16); };
+  uint32_t bad = 0;
+  for (uint32_t i = 0; i < cases; i++) {
+    const int corr = int(next() % ((i & 3) ? 1000000u : 16u)) + 1;      // dx (or dy): small and large
+    const int step = int(next() % uint32_t(corr));
+    const int err0 = int(next() % uint32_t(corr));
+    const int count = int(next() % ((i & 1) ? 4096u : 40u));
+    int acc_m = 0, err_m = err0;
+    b2d::err_multi_step(acc_m, err_m, step, corr, count);
+    uint32_t acc_s = 0; int err_s = err0;
+    for (int k = 0; k < count; k++) b2d::err_step_u(acc_s, err_s, step, corr);
+    if (uint32_t(acc_m) != acc_s || err_m != err_s) bad++;
+  }
+  return bad;
+}
+
 // dst[i] = composite(op, dst[i], src[i], mask[i]) with the device's operator code (dev_pixel.cuh) - swept against the C
 // oracle's replay of the JIT sequences by tests/test_oracle.py.
 __attribute__((visibility("default")))

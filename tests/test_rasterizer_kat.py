@@ -69,4 +69,10 @@ def test_jumping_equals_stepping_and_digest():
     assert hashlib.sha256(a.tobytes()).hexdigest() == DIGEST_50000
 
 
+def test_err_multi_step_equals_single_steps():
+    """The closed form behind edge_advance_to_y and the windowed one-row stepper: jumping `count` error steps at once
+    (AnalyticUtils::acc_err_multi_step, analyticrasterizer_p.h:84-100) == stepping `count` times, 2 M random states."""
+    assert hostsim.lib().hostsim_err_multi_step_check(12345, 2_000_000) == 0
+
+
 DIGEST_50000 = "a8e2b642fea5d2ee3fa61c615874990882e1d95b54d92459e9b7fbb5aff123aa"
