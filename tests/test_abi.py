@@ -70,6 +70,60 @@ int main(void) {
     assert got == [176, 64, 16, 12, 96, 16, 32, 16, 160]
 
 
+REFERENCE = "/root/reference"
+
+LAYOUT_CHECK = r'''
+// Every field the device reads, at the offset the reference's own headers give it (compile-time only).
+#include <blend2d/core/api-build_p.h>
+#include <blend2d/pipeline/pipedefs_p.h>
+#include <blend2d/raster/edgestorage_p.h>
+#include <stddef.h>
+#include "b2dgpu.h"
+using FD = bl::Pipeline::FetchData;
+#define SAME_OFF(ours, theirs) static_assert(offsetof(b2dgpu_fetch_data, ours) == offsetof(FD, theirs), #ours " vs " #theirs)
+static_assert(sizeof(b2dgpu_fetch_data) == sizeof(FD), "FetchData size");
+static_assert(sizeof(b2dgpu_dispatch_data) == sizeof(bl::Pipeline::DispatchData), "DispatchData size");
+static_assert(sizeof(b2dgpu_edge) == 2 * sizeof(bl::RasterEngine::EdgePoint<int>), "an edge is two EdgePoint<int>");
+SAME_OFF(solid.prgb32, solid.prgb32);
+SAME_OFF(pattern.src.pixel_data, pattern.src.pixel_data); SAME_OFF(pattern.src.stride, pattern.src.stride); SAME_OFF(pattern.src.w, pattern.src.size);
+SAME_OFF(pattern.simple.tx, pattern.simple.tx); SAME_OFF(pattern.simple.ty, pattern.simple.ty);
+SAME_OFF(pattern.simple.rx, pattern.simple.rx); SAME_OFF(pattern.simple.ry, pattern.simple.ry);
+SAME_OFF(pattern.simple.wa, pattern.simple.wa); SAME_OFF(pattern.simple.wd, pattern.simple.wd);
+SAME_OFF(pattern.affine.xx, pattern.affine.xx); SAME_OFF(pattern.affine.yy, pattern.affine.yy); SAME_OFF(pattern.affine.tx, pattern.affine.tx);
+SAME_OFF(pattern.affine.ox, pattern.affine.ox); SAME_OFF(pattern.affine.rx, pattern.affine.rx); SAME_OFF(pattern.affine.xx2, pattern.affine.xx2);
+SAME_OFF(pattern.affine.min_x, pattern.affine.min_x); SAME_OFF(pattern.affine.max_y, pattern.affine.max_y);
+SAME_OFF(pattern.affine.cor_x, pattern.affine.cor_x); SAME_OFF(pattern.affine.tw, pattern.affine.tw); SAME_OFF(pattern.affine.addr_mul32, pattern.affine.addr_mul32);
+SAME_OFF(gradient.lut.data, gradient.lut.data); SAME_OFF(gradient.lut.size, gradient.lut.size);
+SAME_OFF(gradient.linear.pt, gradient.linear.pt); SAME_OFF(gradient.linear.dy, gradient.linear.dy); SAME_OFF(gradient.linear.dt, gradient.linear.dt);
+SAME_OFF(gradient.linear.maxi, gradient.linear.maxi); SAME_OFF(gradient.linear.rori, gradient.linear.rori);
+SAME_OFF(gradient.radial.tx, gradient.radial.tx); SAME_OFF(gradient.radial.yx, gradient.radial.yx); SAME_OFF(gradient.radial.amul4, gradient.radial.amul4);
+SAME_OFF(gradient.radial.inv2a, gradient.radial.inv2a); SAME_OFF(gradient.radial.sq_fr, gradient.radial.sq_fr); SAME_OFF(gradient.radial.sq_inv2a, gradient.radial.sq_inv2a);
+SAME_OFF(gradient.radial.b0, gradient.radial.b0); SAME_OFF(gradient.radial.dd0, gradient.radial.dd0); SAME_OFF(gradient.radial.by, gradient.radial.by);
+SAME_OFF(gradient.radial.ddy, gradient.radial.ddy); SAME_OFF(gradient.radial.f32_ddd, gradient.radial.f32_ddd); SAME_OFF(gradient.radial.f32_bd, gradient.radial.f32_bd);
+SAME_OFF(gradient.radial.maxi, gradient.radial.maxi); SAME_OFF(gradient.radial.rori, gradient.radial.rori);
+SAME_OFF(gradient.conic.tx, gradient.conic.tx); SAME_OFF(gradient.conic.yx, gradient.conic.yx); SAME_OFF(gradient.conic.q_coeff, gradient.conic.q_coeff);
+SAME_OFF(gradient.conic.n_div_1_2_4, gradient.conic.n_div_1_2_4); SAME_OFF(gradient.conic.offset, gradient.conic.offset); SAME_OFF(gradient.conic.xx, gradient.conic.xx);
+SAME_OFF(gradient.conic.maxi, gradient.conic.maxi); SAME_OFF(gradient.conic.rori, gradient.conic.rori);
+// BLPipeSignature bit fields (pipedefs_p.h:232-366) behind the B2DGPU_SIG_* accessors
+static_assert(B2DGPU_SIG_COMP_OP(uint32_t(bl::Pipeline::Signature::from_comp_op(bl::CompOpExt(17)).value)) == 17u, "comp op field");
+static_assert(B2DGPU_SIG_FILL_TYPE(uint32_t(bl::Pipeline::Signature::from_fill_type(bl::Pipeline::FillType::kAnalytic).value)) == B2DGPU_FILL_ANALYTIC, "fill type field");
+static_assert(B2DGPU_SIG_FETCH_TYPE(uint32_t(bl::Pipeline::Signature::from_fetch_type(bl::Pipeline::FetchType::kGradientConicNN).value)) == B2DGPU_FETCH_GRADIENT_CONIC_NN, "fetch type field");
+static_assert(B2DGPU_SIG_DST_FORMAT(uint32_t(bl::Pipeline::Signature::from_dst_format(bl::FormatExt::kPRGB32).value)) == B2DGPU_FORMAT_PRGB32, "dst format field");
+static_assert(B2DGPU_SIG_SRC_FORMAT(uint32_t(bl::Pipeline::Signature::from_src_format(bl::FormatExt::kA8).value)) == B2DGPU_FORMAT_A8, "src format field");
+int main() { return 0; }
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "blend2d")), reason="needs the reference headers (/root/reference)")
+def test_struct_layouts_match_the_reference_headers(tmp_path):
+    """include/b2dgpu.h mirrors FetchData / DispatchData / EdgePoint / BLPipeSignature: checked field by field against the
+    reference's private headers themselves (they compile standalone), not against remembered numbers."""
+    src = tmp_path / "layout.cpp"
+    src.write_text(LAYOUT_CHECK)
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-w", "-DBL_STATIC", "-DBL_BUILD_NO_JIT", "-I", REFERENCE,
+                           "-I", os.path.join(ROOT, "include"), str(src)])
+
+
 def test_signature_queries_work_without_a_device():
     """PipeRuntime::test/get semantics are host logic: NOT_IMPLEMENTED / NO_ENTRY for signatures outside the table."""
     from blend2d_b200 import _native as N
