@@ -725,10 +725,10 @@ struct SmemRowStore {
 };
 
 // Result of the classification / rasterization phase for one (command, tile) pair, kept in shared memory.
-enum : int { kEntCap = 4, kRing = 2048, kBlockW = 32, kBlocks = kTileW / kBlockW, kBlockRows = 4 };
+enum : int { kEntCap = 2, kRing = 2048, kBlockW = 32, kBlocks = kTileW / kBlockW, kBlockRows = 4 };
 static_assert(kBlocks == 4, "a warp is addressed as (row group, one of four column blocks)");
 // Per tile height TH (= warps per CTA): commands per phase-1 round, chained-entry pool size.
-template<int TH> struct TileCfg { enum : int { kThreads = 32 * TH, kSub = TH == 32 ? 64 : 3 * TH, kPool = 128 * TH }; };
+template<int TH> struct TileCfg { enum : int { kThreads = 32 * TH, kSub = TH == 32 ? 84 : 3 * TH, kPool = 128 * TH }; };
 enum : uint32_t { kPreStraddle = 1u, kPreOverflow = 2u, kPreClipRight = 4u };   // ClipRight: the clipped box ends inside the tile
 enum : uint32_t { kDenseItemsPerRow = 8u };        // (edge, row) crossings per tile row beyond which phase 1 gives up
 
